@@ -1,0 +1,450 @@
+// Skinny f64 GEMM: persistent, warp-specialised (1 TMA producer warp + 8 DMMA warps), split-K with a
+// deterministic two-stage reduction.  See skinny_gemm.cuh for the contract.
+//
+// Shared-memory tile formats (both written by TMA with CU_TENSOR_MAP_SWIZZLE_128B, 128-byte rows):
+//   KC ("K-contiguous", reduce_inner): one box [128 Mside-rows][16 k]; element (r,k) lives at
+//        r*128 + (((k>>1) ^ (r&7)) << 4) + (k&1)*8.
+//        MMA row g of an 8-row block reads tile row 2*(g&3) + (g>>2): each half-warp then touches
+//        rows {0,2,4,6} or {1,3,5,7}, whose XOR patterns map the 16 lanes onto 16 distinct 8-byte
+//        bank pairs -> conflict-free LDS.64.
+//   MC ("M-contiguous", reduce_outer): eight boxes [16 k][16 Mside-cols] of 2 KB; element (k,c) of a box at
+//        k*128 + (((c>>1) ^ (k&7)) << 4) + (c&1)*8.
+//        MMA row g of m-block `mbl` (two per box) reads box column (g&1) + 8*((g>>1)&1) + 2*(g>>2) + 4*mbl,
+//        again 16 distinct bank pairs per half-warp.
+// The output rows follow the same permutations, so no data is ever shuffled.
+// B slab: [16 k][ldb] row-major, ldb == 4 (mod 8): lane (g,t) reads word (4s+t)*2*ldb + 2*(8*nb+g);
+// t*2*ldb mod 32 is {0,8,16,24} (or its mirror) -> conflict-free.
+#include "skinny_gemm.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <mutex>
+
+namespace corrla {
+
+namespace {
+
+constexpr uint32_t kAStageBytes = kTileM * kChunkK * 8;  // 16 KB
+
+__device__ __forceinline__ int rowperm(int g) { return 2 * (g & 3) + (g >> 2); }
+__device__ __forceinline__ int colperm(int g, int mbl) {
+  return (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2) + 4 * mbl;
+}
+
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+template <bool KC, int WM, int WN, int MI, int JW>
+__global__ void __launch_bounds__((WM * WN + 1) * 32, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
+  static_assert(WM * MI * 8 == kTileM, "tile rows");
+  static_assert(MI % 2 == 0, "MI even (box parity)");
+  constexpr int NCW = WM * WN;
+
+  if (p.cond_flag != nullptr && *p.cond_flag == 0) return;
+
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  unsigned char* smem = smem_raw + pad;
+  const uint32_t sA = raw_u32 + pad;
+  const uint32_t sB = sA + p.stages * kAStageBytes;
+  const uint32_t sBar = sB + p.stages * p.b_stage_bytes;     // full[stages], empty[stages]
+  unsigned char* smemB = smem + p.stages * kAStageBytes;
+  double* red = reinterpret_cast<double*>(smemB + p.stages * p.b_stage_bytes + 2 * 8 * 8);  // after 16 barriers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(sBar + 8 * s, 1);
+      mbar_init(sBar + 8 * (8 + s), NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int W = p.tilesM * p.splits;
+  uint32_t stage = 0, phase = 0;
+
+  if (warp == NCW) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane != 0) return;
+    tma_prefetch_desc(&tmA);
+    const uint32_t tx = kAStageBytes + p.b_stage_bytes;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+      const int split = w / p.tilesM, tile = w - split * p.tilesM;
+      const int64_t c0 = (int64_t)split * p.chunks_per_split;
+      const int64_t c1 = min(c0 + p.chunks_per_split, p.chunks_total);
+      const int m0 = tile * kTileM;
+      for (int64_t c = c0; c < c1; ++c) {
+        mbar_wait(sBar + 8 * (8 + stage), phase ^ 1u);
+        const uint32_t full = sBar + 8 * stage;
+        mbar_arrive_expect_tx(full, tx);
+        const int k0 = (int)(c * kChunkK);
+        const uint32_t dstA = sA + stage * kAStageBytes;
+        if (KC) {
+          tma_load_2d(dstA, &tmA, k0, m0, full);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
+        }
+        bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ DMMA consumers ------------------------------
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp % WM, wn = warp / WM;
+  const int jn = min(JW, p.nblk - wn * JW);   // valid n-blocks of this warp (may be <= 0)
+
+  // A-fragment byte offsets inside a stage
+  int a_base;          // KC: row part for i = 0;   MC: box part for i = 0
+  int a_xo[2][4];      // KC: [0][s];  MC: [i&1][s]
+  if (KC) {
+    const int rp = rowperm(g);
+    a_base = (wm * MI * 8 + rp) * 128;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      a_xo[0][s] = ((((s << 1) | (t >> 1)) ^ rp) << 4) + ((t & 1) << 3);
+      a_xo[1][s] = a_xo[0][s];
+    }
+  } else {
+    a_base = ((wm * MI) >> 1) * 2048;
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const int mc = colperm(g, par);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int kr = 4 * s + t;
+        a_xo[par][s] = kr * 128 + ((((mc >> 1) ^ (kr & 7))) << 4) + ((mc & 1) << 3);
+      }
+    }
+  }
+  const int b_off = t * p.ldb * 8 + (8 * wn * JW + g) * 8;
+  const int b_step = 4 * p.ldb * 8;
+
+  double alpha = 1.0;
+  if (p.alpha_sumsq != nullptr) alpha = rsqrt(*p.alpha_sumsq);
+
+  double acc[MI][JW][2];
+
+  for (int w = blockIdx.x; w < W; w += gridDim.x) {
+    const int split = w / p.tilesM, tile = w - split * p.tilesM;
+    const int64_t c0 = (int64_t)split * p.chunks_per_split;
+    const int64_t c1 = min(c0 + p.chunks_per_split, p.chunks_total);
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    for (int64_t c = c0; c < c1; ++c) {
+      mbar_wait(sBar + 8 * stage, phase);
+      const unsigned char* a = smem + stage * kAStageBytes + a_base;
+      const unsigned char* b = smemB + stage * p.b_stage_bytes + b_off;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        double af[MI], bf[JW];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int off = KC ? (i * 1024 + a_xo[0][s]) : ((i >> 1) * 2048 + a_xo[i & 1][s]);
+          af[i] = *reinterpret_cast<const double*>(a + off);
+        }
+#pragma unroll
+        for (int j = 0; j < JW; ++j)
+          if (j < jn) bf[j] = *reinterpret_cast<const double*>(b + s * b_step + j * 64);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < JW; ++j)
+            if (j < jn) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sBar + 8 * (8 + stage));
+      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+    }
+
+    // ------------------------------ epilogue ------------------------------
+    const int Lc = p.nblk * 8;
+    double ss = 0.0;
+    if (p.splits > 1) {
+      double* wsp = p.ws + (int64_t)w * kTileM * Lc;
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int tr = KC ? ((wm * MI + i) * 8 + rowperm(g)) : (16 * ((wm * MI + i) >> 1) + colperm(g, i & 1));
+#pragma unroll
+        for (int j = 0; j < JW; ++j)
+          if (j < jn) {
+            const int col = 8 * (wn * JW + j) + 2 * t;
+            *reinterpret_cast<double2*>(wsp + (int64_t)tr * Lc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+          }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int tr = KC ? ((wm * MI + i) * 8 + rowperm(g)) : (16 * ((wm * MI + i) >> 1) + colperm(g, i & 1));
+        const int64_t row = (int64_t)tile * kTileM + tr;
+        if (row < p.Mside) {
+#pragma unroll
+          for (int j = 0; j < JW; ++j)
+            if (j < jn) {
+              const int col = 8 * (wn * JW + j) + 2 * t;
+              const double v0 = acc[i][j][0] * alpha, v1 = acc[i][j][1] * alpha;
+              ss += v0 * v0 + v1 * v1;
+              double* o = p.out + row * p.out_rs + (int64_t)col * p.out_cs;
+              if (p.out_cs == 1 && (p.out_rs & 1) == 0 && col + 1 < p.ncols_out) {
+                *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+              } else {
+                if (col < p.ncols_out) o[0] = v0;
+                if (col + 1 < p.ncols_out) o[p.out_cs] = v1;
+              }
+            }
+        }
+      }
+      if (p.sumsq_partials != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        consumer_bar_sync(NCW * 32);
+        if (warp == 0 && lane == 0) {
+          double tot = 0.0;
+          for (int i = 0; i < NCW; ++i) tot += red[i];
+          p.sumsq_partials[w] = tot;
+        }
+        consumer_bar_sync(NCW * 32);
+      }
+    }
+  }
+}
+
+// out(r, c) = alpha * sum_s ws[s][tile(r)][r % 128][c]; one thread per column pair.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside,
+                     double* __restrict__ out, int64_t out_rs, int64_t out_cs, int ncols_out,
+                     const double* alpha_sumsq, double* sumsq_partials, const int* cond_flag) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  __shared__ double red[8];
+  const int half = Lc >> 1;
+  const int64_t total = Mside * half;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double alpha = 1.0;
+  if (alpha_sumsq != nullptr) alpha = rsqrt(*alpha_sumsq);
+  double ss = 0.0;
+  if (idx < total) {
+    const int64_t r = idx / half;
+    const int col = (int)(idx - r * half) * 2;
+    const int64_t tile = r / kTileM, rt = r - tile * kTileM;
+    const int64_t split_stride = (int64_t)tilesM * kTileM * Lc;
+    const double* src = ws + (tile * kTileM + rt) * Lc + col;
+    double s0 = 0.0, s1 = 0.0;
+    for (int s = 0; s < splits; ++s) {
+      const double2 v = *reinterpret_cast<const double2*>(src + s * split_stride);
+      s0 += v.x; s1 += v.y;
+    }
+    s0 *= alpha; s1 *= alpha;
+    ss = s0 * s0 + s1 * s1;
+    double* o = out + r * out_rs + (int64_t)col * out_cs;
+    if (col < ncols_out) o[0] = s0;
+    if (col + 1 < ncols_out) o[out_cs] = s1;
+  }
+  if (sumsq_partials != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+      sumsq_partials[blockIdx.x] = tot;
+    }
+  }
+}
+
+// *slot = sum(partials[0..n)) in a fixed order (bit-reproducible).
+__global__ void __launch_bounds__(1024)
+sumsq_finalize_kernel(const double* __restrict__ partials, int64_t n, double* slot, const int* cond_flag) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 32; ++i) tot += red[i];
+    *slot = tot;
+  }
+}
+
+// ----------------------------------- host side -----------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+bool encode_map(CUtensorMap* tm, const MatView& v, bool kc) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)v.inner, (cuuint64_t)v.outer};
+  cuuint64_t strides[1] = {(cuuint64_t)v.ld * 8};
+  cuuint32_t box[2] = {16, kc ? (cuuint32_t)kTileM : (cuuint32_t)kChunkK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(v.p), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "corrla: cuTensorMapEncodeTiled failed (%d) p=%p inner=%lld outer=%lld ld=%lld\n", (int)r,
+            (const void*)v.p, (long long)v.inner, (long long)v.outer, (long long)v.ld);
+    return false;
+  }
+  return true;
+}
+
+typedef void (*KernelFn)(const CUtensorMap, const GemmArgs);
+
+template <bool KC>
+KernelFn pick_kernel(int nblk, int* threads) {
+  *threads = 9 * 32;
+  switch (nblk) {
+    case 1: return skinny_gemm_kernel<KC, 8, 1, 2, 1>;
+    case 2: return skinny_gemm_kernel<KC, 8, 1, 2, 2>;
+    case 3: return skinny_gemm_kernel<KC, 8, 1, 2, 3>;
+    case 4: return skinny_gemm_kernel<KC, 8, 1, 2, 4>;
+    case 5: return skinny_gemm_kernel<KC, 8, 1, 2, 5>;
+    case 6: return skinny_gemm_kernel<KC, 8, 1, 2, 6>;
+    case 7: return skinny_gemm_kernel<KC, 8, 1, 2, 7>;
+    case 8: return skinny_gemm_kernel<KC, 4, 2, 4, 4>;
+    case 9: case 10: return skinny_gemm_kernel<KC, 4, 2, 4, 5>;
+    case 11: case 12: return skinny_gemm_kernel<KC, 4, 2, 4, 6>;
+    case 13: case 14: return skinny_gemm_kernel<KC, 4, 2, 4, 7>;
+    case 15: case 16: return skinny_gemm_kernel<KC, 4, 2, 4, 8>;
+    default: return nullptr;
+  }
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+constexpr size_t kWsCapBytes = (size_t)512 << 20;
+
+}  // namespace
+
+bool tma_compatible(const MatView& v) {
+  return (reinterpret_cast<uintptr_t>(v.p) % 16 == 0) && (v.ld % 2 == 0) && v.inner > 0 && v.outer > 0 &&
+         v.inner < ((int64_t)1 << 31) && v.outer < ((int64_t)1 << 31) && (v.ld * 8 < ((int64_t)1 << 40));
+}
+
+void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits, int* tilesM_out, int* splits_out,
+               int64_t* cps_out, size_t* ws_bytes, size_t* n_partials) {
+  const int Lc = nblk * 8;
+  const int64_t tilesM = (Mside + kTileM - 1) / kTileM;
+  const int64_t chunks = std::max<int64_t>(1, (K + kChunkK - 1) / kChunkK);
+  const double t_chunk = std::max(Lc * 0.016384, 0.37);  // us: DMMA time vs HBM time of one 16 KB A chunk
+  const size_t tile_bytes = (size_t)kTileM * Lc * 8;
+  int best_s = 1;
+  double best_t = 1e300;
+  const int64_t smax = force_splits > 0 ? force_splits : std::min<int64_t>(chunks, 1024);
+  for (int64_t s = force_splits > 0 ? force_splits : 1; s <= smax; ++s) {
+    const int64_t cps = (chunks + s - 1) / s;
+    if (s > 1 && force_splits == 0 && cps < 8) break;
+    if ((cps * (s - 1)) >= chunks && s > 1) continue;  // last split would be empty
+    const int64_t items = tilesM * s;
+    if (s > 1 && (size_t)items * tile_bytes > kWsCapBytes && force_splits == 0) break;
+    const int64_t per_cta = (items + num_sms - 1) / num_sms;
+    double t = per_cta * (cps + 3.0) * t_chunk;
+    if (s > 1) t += (double)items * tile_bytes * 2.0 / 4.0e6 + 4.0;
+    if (t < best_t * 0.999) { best_t = t; best_s = (int)s; }
+  }
+  const int64_t cps = (chunks + best_s - 1) / best_s;
+  *tilesM_out = (int)tilesM;
+  *splits_out = best_s;
+  *cps_out = cps;
+  *ws_bytes = best_s > 1 ? (size_t)tilesM * best_s * tile_bytes : 0;
+  const int64_t reduce_blocks = (Mside * (Lc / 2) + 255) / 256;
+  *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM;
+}
+
+cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t stream, int* launches) {
+  GemmArgs a{};
+  const bool kc = c.reduce_inner;
+  a.Mside = kc ? c.a.outer : c.a.inner;
+  a.K = kc ? c.a.inner : c.a.outer;
+  a.B = c.B; a.ldb = c.ldb; a.nblk = c.nblk;
+  a.out = c.out; a.out_rs = c.out_rs; a.out_cs = c.out_cs; a.ncols_out = c.ncols_out;
+  a.alpha_sumsq = c.alpha_sumsq;
+  a.cond_flag = c.cond_flag;
+  if (c.nblk < 1 || c.nblk > kMaxNblk || (c.ldb % 8) != 4 || c.ldb < c.nblk * 8) return cudaErrorInvalidValue;
+  if (!tma_compatible(c.a)) return cudaErrorInvalidValue;
+
+  size_t ws_bytes, n_partials;
+  gemm_plan(a.Mside, a.K, a.nblk, w.num_sms, c.force_splits, &a.tilesM, &a.splits, &a.chunks_per_split, &ws_bytes,
+            &n_partials);
+  a.chunks_total = std::max<int64_t>(1, (a.K + kChunkK - 1) / kChunkK);
+  if (ws_bytes > w.ws_bytes) return cudaErrorMemoryAllocation;
+  if (c.sumsq_slot != nullptr && n_partials > w.n_partials) return cudaErrorMemoryAllocation;
+  a.ws = w.ws;
+  a.sumsq_partials = (c.sumsq_slot != nullptr && a.splits == 1) ? w.sumsq_partials : nullptr;
+
+  a.b_stage_bytes = (uint32_t)(kChunkK * c.ldb * 8);
+  const size_t per_stage = kAStageBytes + a.b_stage_bytes;
+  const size_t fixed = 1024 + 16 * 8 + 16 * 8;  // alignment slack + barriers + reduction scratch
+  a.stages = (int)std::min<size_t>(8, (kMaxDynSmem - fixed) / per_stage);
+  if (a.stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = fixed + a.stages * per_stage;
+
+  CUtensorMap tm;
+  if (!encode_map(&tm, c.a, kc)) return cudaErrorInvalidValue;
+
+  int threads = 0;
+  KernelFn fn = kc ? pick_kernel<true>(a.nblk, &threads) : pick_kernel<false>(a.nblk, &threads);
+  if (fn == nullptr) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+
+  const int W = a.tilesM * a.splits;
+  const int grid = std::min(W, w.num_sms);
+  fn<<<grid, threads, smem, stream>>>(tm, a);
+  if (launches) ++*launches;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+
+  int64_t n_part_used = a.tilesM;
+  if (a.splits > 1) {
+    const int Lc = a.nblk * 8;
+    const int64_t total = a.Mside * (Lc / 2);
+    const int blocks = (int)((total + 255) / 256);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(w.ws, a.splits, a.tilesM, Lc, a.Mside, a.out, a.out_rs, a.out_cs,
+                                                     a.ncols_out, a.alpha_sumsq,
+                                                     c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    n_part_used = blocks;
+  }
+  if (c.sumsq_slot != nullptr) {
+    sumsq_finalize_kernel<<<1, 1024, 0, stream>>>(w.sumsq_partials, n_part_used, c.sumsq_slot, a.cond_flag);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace corrla

@@ -1,0 +1,73 @@
+// Skinny f64 GEMM on the FP64 tensor pipe (DMMA.8x8x4) fed by TMA, for the RSVD passes.
+//
+//   D[Mside x Lc] (+)= op(A)[Mside x K] * B[K x Lc],   Lc = 8*nblk <= 128
+//
+// A is any 2-D f64 array in global memory seen as `outer` rows of `inner` contiguous elements
+// (row pitch ld).  Two ways to contract it:
+//   reduce_inner : Mside = outer, K = inner  (e.g. Y = A*Omega for row-major A;  A^T*Y for column-major A)
+//   reduce_outer : Mside = inner, K = outer  (e.g. Z = A^T*Y for row-major A;  Gram Y^T*Y)
+// B, and every matrix the engine owns, is row-major with pitch ldb = Lc + 4 (== 4 mod 8), zero padded,
+// which makes the DMMA B-fragment loads bank-conflict free and lets a whole 16-row slab travel as
+// one cp.async.bulk.
+//
+// This replaces faer's matmul behind par_matmul_helper (reference src/lib_math_utils/mat_utils.rs:20-33)
+// at the call sites random_svd.rs:31, :42-51, :80, :92.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace corrla {
+
+constexpr int kTileM = 128;   // output rows per work item
+constexpr int kChunkK = 16;   // reduction elements per pipeline stage
+constexpr int kMaxNblk = 16;  // Lc <= 128
+
+struct MatView {            // element (o, i) at p[o*ld + i]
+  const double* p;
+  int64_t inner, outer, ld;
+};
+
+struct GemmArgs {
+  int64_t Mside, K;
+  const double* B; int ldb; int nblk;
+  // direct output (used when splits == 1) or final destination of the split-K reduction
+  double* out; int64_t out_rs, out_cs; int ncols_out;
+  // split-K
+  double* ws; int tilesM, splits; int64_t chunks_total, chunks_per_split;
+  // alpha = rsqrt(*alpha_sumsq) when non-null, else 1
+  const double* alpha_sumsq;
+  // per-work-item (splits==1) sum of squares of the scaled output, or null
+  double* sumsq_partials;
+  // when non-null and *cond_flag == 0 the kernel does nothing
+  const int* cond_flag;
+  int stages; uint32_t b_stage_bytes;
+};
+
+// Host-side description of one product; see gemm_launch().
+struct GemmCall {
+  MatView a; bool reduce_inner;
+  const double* B; int ldb; int nblk;
+  double* out; int64_t out_rs, out_cs; int ncols_out;
+  const double* alpha_sumsq = nullptr;
+  double* sumsq_slot = nullptr;     // if set: *sumsq_slot = sum of squares of the (scaled) output
+  const int* cond_flag = nullptr;
+  int force_splits = 0;             // testing hook: 0 = choose
+};
+
+struct GemmWorkspace {
+  double* ws = nullptr; size_t ws_bytes = 0;           // split-K partial tiles
+  double* sumsq_partials = nullptr; size_t n_partials = 0;
+  int num_sms = 148;
+};
+
+// Returns cudaSuccess or the first CUDA error; throws nothing.  All work is enqueued on `stream`.
+cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t stream, int* launches = nullptr);
+
+// Bytes of split-K workspace / partial slots a call will need (so plans can size buffers up front).
+void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits,
+               int* tilesM, int* splits, int64_t* chunks_per_split, size_t* ws_bytes, size_t* n_partials);
+
+bool tma_compatible(const MatView& v);
+
+}  // namespace corrla
