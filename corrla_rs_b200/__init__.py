@@ -1,0 +1,330 @@
+"""corrla_rs_b200 -- host-side mirror of CORRLA-RS's RSVD interface over libcorrla_b200.so.
+
+The functions here have the names, argument meaning and error behaviour of the reference's pyo3 module
+(`corrla_rs.rsvd`, src/lib_math_utils_py.rs:21-36) and of the Rust functions underneath it
+(`random_svd`, `power_iter`: src/lib_math_utils/random_svd.rs:15-110; `par_matmul_helper`,
+`random_mat_normal`: src/lib_math_utils/mat_utils.rs:20-33, :161-175).  All arithmetic runs in the
+CUDA library; this module only marshals pointers, strides and sizes.  There is no CPU fallback.
+
+Inputs may be numpy arrays (host path: the library copies A to the GPU and the results back) or
+torch CUDA tensors (device path: nothing crosses PCIe).  torch is imported lazily and only for the
+device path and for the multi-GPU communicator bootstrap.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
+
+__all__ = ["rsvd", "random_svd", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
+           "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings"]
+
+_SCHEDULES = {"reference": 0, "stabilised": 1, "stabilized": 1, 0: 0, 1: 1}
+_tls = threading.local()
+
+
+def version() -> str:
+    return _ffi.load().corrla_version().decode()
+
+
+def last_timings() -> dict | None:
+    """corrla_timings of the most recent call made by this thread (as a dict)."""
+    return getattr(_tls, "timings", None)
+
+
+# --------------------------------------------------------------------------------------------
+# contexts (persistent device buffers) and communicators
+# --------------------------------------------------------------------------------------------
+class Context:
+    """Per-GPU handle that keeps the engine's device buffers alive between calls."""
+
+    def __init__(self, device: int | None = None):
+        lib = _ffi.load()
+        h = C.c_void_p()
+        _ffi.check(lib.corrla_ctx_create(-1 if device is None else int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.load().corrla_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: dict[int, Context] = {}
+_ctx_lock = threading.Lock()
+
+
+def _context_for(device: int | None) -> Context:
+    key = -1 if device is None else int(device)
+    with _ctx_lock:
+        ctx = _default_ctx.get(key)
+        if ctx is None or ctx.handle is None:
+            ctx = Context(device)
+            _default_ctx[key] = ctx
+        return ctx
+
+
+class ShardComm:
+    """NCCL communicator over the ranks that each hold a block of rows of one tall matrix.
+    Bootstrapped through torch.distributed (any backend): rank 0 draws the ncclUniqueId and broadcasts it."""
+
+    def __init__(self, device: int | None = None, group=None):
+        import torch
+        import torch.distributed as dist
+        lib = _ffi.load()
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised before ShardComm()")
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        if device is None:
+            device = torch.cuda.current_device()
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _ffi.check(lib.corrla_comm_unique_id(buf))
+        # gloo and nccl both broadcast CPU/GPU tensors respectively; use an object broadcast to stay backend-neutral
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        h = C.c_void_p()
+        _ffi.check(lib.corrla_comm_init(box[0], self.rank, self.size, int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.load().corrla_comm_destroy(self._h)
+            self._h = None
+
+
+# --------------------------------------------------------------------------------------------
+# marshalling helpers
+# --------------------------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch" and hasattr(x, "data_ptr")
+
+
+class _Mat:
+    """(pointer, shape, element strides, residency) of a 2-D f64 array, numpy or torch."""
+
+    def __init__(self, x, name="a_mat"):
+        if _is_torch(x):
+            import torch
+            if x.dtype != torch.float64 or x.dim() != 2:
+                raise TypeError(f"{name} must be a 2-D float64 array")   # pyo3 extraction error
+            self.on_device = x.is_cuda
+            if not self.on_device:
+                x = x.numpy()
+            else:
+                self.keep = x
+                self.ptr = x.data_ptr()
+                self.shape = tuple(x.shape)
+                self.strides = tuple(x.stride())
+                self.device = x.device.index
+                return
+        if not isinstance(x, np.ndarray):
+            raise TypeError(f"{name} must be a numpy.ndarray or a torch tensor of dtype float64")
+        if x.dtype != np.float64 or x.ndim != 2:
+            raise TypeError(f"{name} must be a 2-D float64 array")       # pyo3: PyReadonlyArray2<f64>
+        self.on_device = False
+        self.keep = x
+        self.ptr = x.ctypes.data
+        self.shape = x.shape
+        self.strides = tuple(s // 8 for s in x.strides)
+        if any(s * 8 != b for s, b in zip(self.strides, x.strides)) or any(s < 0 for s in self.strides):
+            # exotic (negative / unaligned) strides: take a contiguous copy, as PyReadonlyArray would refuse them
+            x = np.ascontiguousarray(x)
+            self.keep = x
+            self.ptr = x.ctypes.data
+            self.strides = tuple(s // 8 for s in x.strides)
+        self.device = None
+
+
+def _make_opts(*, ctx, on_device, out_on_device, omega, seed, schedule, comm, global_rows, stream, device):
+    lib = _ffi.load()
+    o = _ffi.RsvdOpts()
+    lib.corrla_rsvd_opts_default(C.byref(o))
+    if schedule not in _SCHEDULES:
+        raise ValueError(f"schedule must be 'reference' or 'stabilised', got {schedule!r}")
+    o.schedule = _SCHEDULES[schedule]
+    o.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2**64 - 1)
+    o.a_on_device = 1 if on_device else 0
+    o.out_on_device = 1 if out_on_device else 0
+    o.device = -1 if device is None else int(device)
+    o.ctx = ctx.handle
+    keep = None
+    if omega is not None:
+        om = _Mat(omega, "omega")
+        o.omega = om.ptr
+        o.omega_rs, o.omega_cs = om.strides
+        o.omega_on_device = 1 if om.on_device else 0
+        keep = om
+    if comm is not None:
+        o.comm = comm.handle
+        o.global_rows = int(global_rows or 0)
+    if stream is not None:
+        o.stream = int(stream)
+    return o, keep
+
+
+def _current_stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _colmajor_empty_like(a: _Mat, rows: int, cols: int):
+    """Column-major rows x cols output living where `a` lives."""
+    if a.on_device:
+        import torch
+        return torch.empty((cols, rows), dtype=torch.float64, device=a.keep.device).t()
+    return np.empty((rows, cols), dtype=np.float64, order="F")
+
+
+def _ptr(x):
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+# --------------------------------------------------------------------------------------------
+# public API
+# --------------------------------------------------------------------------------------------
+def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, seed: int | None = None,
+         schedule="reference", ctx: Context | None = None, comm: ShardComm | None = None,
+         global_rows: int | None = None):
+    """Randomized SVD, drop-in for `corrla_rs.rsvd(a_mat, n_rank, n_iters, n_oversamples)`
+    (src/lib_math_utils_py.rs:21-36 -> random_svd, src/lib_math_utils/random_svd.rs:63-110).
+
+    Returns (ur, sr, vr) with shapes (nrows, n_rank), (n_rank, 1), (n_rank, ncols), like the reference.
+    Keyword extras (not in the reference): `omega` injects the Gaussian test matrix (ncols_thin x l),
+    `seed` makes the on-device Philox generator reproducible (the reference is unseeded),
+    `schedule="stabilised"` re-orthonormalises in every power iteration, `comm` runs row-sharded over
+    several GPUs (a_mat is then this rank's rows of the thin matrix)."""
+    for name, v in (("n_rank", n_rank), ("n_iters", n_iters), ("n_oversamples", n_oversamples)):
+        if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
+            raise TypeError(f"{name} must be an int")
+        if v < 0:
+            raise OverflowError(f"can't convert negative int to unsigned ({name})")   # pyo3 usize extraction
+    a = _Mat(a_mat)
+    lib = _ffi.load()
+    nrows, ncols = a.shape
+    device = a.device if a.on_device else (comm.device if comm is not None else None)
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if a.on_device else None
+    o, keep = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=omega, seed=seed,
+                         schedule=schedule, comm=comm, global_rows=global_rows, stream=stream, device=device)
+    k = int(n_rank)
+    u = _colmajor_empty_like(a, nrows, max(k, 1))
+    vt = _colmajor_empty_like(a, max(k, 1), ncols)
+    s = _colmajor_empty_like(a, max(k, 1), 1)
+    t = Timings()
+    st = lib.corrla_rsvd_f64(a.ptr, nrows, ncols, a.strides[0], a.strides[1], k, int(n_iters), int(n_oversamples),
+                             C.byref(o), _ptr(u), _ptr(s), _ptr(vt), C.byref(t))
+    del keep
+    _ffi.check(st)
+    _tls.timings = t.as_dict()
+    return u, s, vt
+
+
+random_svd = rsvd
+
+
+def power_iter(a_mat, omega_rank: int, n_iter: int, *, omega=None, seed: int | None = None, schedule="reference",
+               ctx: Context | None = None, comm: ShardComm | None = None, global_rows: int | None = None):
+    """Q = power_iter(a, omega_rank, n_iter) (random_svd.rs:15-59): orthonormal basis (nrows x omega_rank)."""
+    a = _Mat(a_mat)
+    lib = _ffi.load()
+    nrows, ncols = a.shape
+    device = a.device if a.on_device else (comm.device if comm is not None else None)
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if a.on_device else None
+    o, keep = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=omega, seed=seed,
+                         schedule=schedule, comm=comm, global_rows=global_rows, stream=stream, device=device)
+    q = _colmajor_empty_like(a, nrows, int(omega_rank))
+    t = Timings()
+    st = lib.corrla_power_iter_f64(a.ptr, nrows, ncols, a.strides[0], a.strides[1], int(omega_rank), int(n_iter),
+                                   C.byref(o), _ptr(q), C.byref(t))
+    del keep
+    _ffi.check(st)
+    _tls.timings = t.as_dict()
+    return q
+
+
+def par_matmul(lhs, rhs, beta: float = 1.0, *, ctx: Context | None = None):
+    """res = beta * lhs @ rhs with a skinny rhs (<= 128 columns): par_matmul_helper with alpha=None
+    (mat_utils.rs:20-33).  Returns a new array where the inputs live."""
+    a = _Mat(lhs, "lhs")
+    b = _Mat(rhs, "rhs")
+    if a.on_device != b.on_device:
+        raise ValueError("lhs and rhs must both be on the host or both on the device")
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"dimension mismatch: lhs is {a.shape}, rhs is {b.shape}")   # faer asserts
+    lib = _ffi.load()
+    device = a.device if a.on_device else None
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if a.on_device else None
+    o, _ = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=None, seed=0,
+                      schedule="reference", comm=None, global_rows=None, stream=stream, device=device)
+    res = _colmajor_empty_like(a, a.shape[0], b.shape[1])
+    st = lib.corrla_par_matmul_f64(_ptr(res), 1, a.shape[0], a.ptr, a.shape[0], a.shape[1], a.strides[0], a.strides[1],
+                                   b.ptr, b.shape[1], b.strides[0], b.strides[1], float(beta),
+                                   1 if a.on_device else 0, C.byref(o))
+    _ffi.check(st)
+    return res
+
+
+par_matmul_helper = par_matmul
+
+
+def random_mat_normal(n_rows: int, n_cols: int, seed: int | None = None, *, device: int | None = None,
+                      as_torch: bool = False, ctx: Context | None = None):
+    """n_rows x n_cols i.i.d. N(0,1) (mat_utils.rs:161-175), drawn on the GPU with Philox4x32-10."""
+    lib = _ffi.load()
+    ctx = ctx or _context_for(device)
+    o, _ = _make_opts(ctx=ctx, on_device=False, out_on_device=as_torch, omega=None, seed=seed, schedule="reference",
+                      comm=None, global_rows=None, stream=None, device=device)
+    if as_torch:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        out = torch.empty((n_cols, n_rows), dtype=torch.float64, device=dev).t()
+        torch.cuda.synchronize(dev)
+    else:
+        out = np.empty((n_rows, n_cols), dtype=np.float64, order="F")
+    st = lib.corrla_random_mat_normal_f64(o.seed, int(n_rows), int(n_cols), _ptr(out), 1 if as_torch else 0, C.byref(o))
+    _ffi.check(st)
+    return out
+
+
+def thin_q(a_mat, *, ctx: Context | None = None, comm: ShardComm | None = None, global_rows: int | None = None,
+           return_rank: bool = False):
+    """Thin Q of a tall matrix with <= 128 columns by adaptive CholeskyQR2/3: the engine's stand-in for faer's
+    `qr().compute_thin_q()` (random_svd.rs:38, :57).  Rank-deficient columns come back as exact zeros."""
+    a = _Mat(a_mat)
+    lib = _ffi.load()
+    device = a.device if a.on_device else (comm.device if comm is not None else None)
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if a.on_device else None
+    o, _ = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=None, seed=0,
+                      schedule="reference", comm=comm, global_rows=global_rows, stream=stream, device=device)
+    q = _colmajor_empty_like(a, a.shape[0], a.shape[1])
+    rank = C.c_int(0)
+    st = lib.corrla_thin_q_f64(a.ptr, a.shape[0], a.shape[1], a.strides[0], a.strides[1], 1 if a.on_device else 0,
+                               C.byref(o), _ptr(q), C.byref(rank))
+    _ffi.check(st)
+    return (q, rank.value) if return_rank else q

@@ -1,0 +1,48 @@
+// Small single-CTA / elementwise kernels around the skinny GEMM: Philox test matrix, Cholesky + triangular
+// inverse for CholeskyQR, one-sided Jacobi SVD of the l x l core, strided repack.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace corrla {
+
+// Omega ~ N(0,1), rows x cols, row-major with pitch ld (pad untouched).  Replaces random_mat_normal
+// (reference src/lib_math_utils/mat_utils.rs:161-175) with a counter-based generator so every GPU
+// regenerates the same matrix without a broadcast.  oracle/ref_rsvd.py:philox_normal restates it.
+cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld, uint64_t seed, cudaStream_t s);
+
+enum CholMode { kCholAuto = 0, kCholPlain = 1 };
+
+// Upper Cholesky G = R^T R of the l x l Gram matrix (row-major, pitch ldg) in shared memory, then the
+// "deflated" inverse T = R^-1 (columns whose pivot vanished are zero, so Q = Y*T has exact zero columns there).
+// T is written as Lrows x ldt (zero outside the upper triangle).  kCholAuto: if the smallest pivot ratio
+// falls under 1e-10 the factorisation is redone on G + shift*I (shifted CholeskyQR3, Fukaya et al. 2020)
+// and *flag3 = 1 (a third pass is needed), else *flag3 = 0.
+// info[0] = live columns, info[1] = shifted?, dinfo[0] = smallest pivot ratio.
+// Together with the Gram/apply GEMMs this replaces faer's qr().compute_thin_q() at random_svd.rs:38 and :57.
+// deadmask (optional, l ints) receives 1 for deflated columns and *flag_dead = (any deflated column).
+cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, int mode,
+                            double global_rows, int* flag3, int* info, double* dinfo, int* deadmask, int* flag_dead,
+                            const int* cond_flag, cudaStream_t s);
+
+// X[i][j] = N(0,1) for every column j with deadmask[j] != 0 (rows x l, pitch ld); draw number
+// ((stream_id << 40) + i) * 128 + j of Philox4x32-10 keyed by seed.  Runs only if *cond_flag != 0.
+cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const int* deadmask, uint64_t seed,
+                               uint64_t stream_id, const int* cond_flag, cudaStream_t s);
+
+// One-sided (Hestenes) Jacobi SVD of the l x l matrix W (row-major, pitch ldw): W = Ur * diag(sigma) * Vr^T,
+// sigma sorted descending.  Ur, Vr are written as Lrows x ldo row-major, zero padded (ready to be a GEMM B
+// operand).  scratch: 2*l*(l|1) doubles of global memory, used when the matrices do not fit in shared memory.
+// Replaces faer's svd() at random_svd.rs:89 (after the QR preconditioning done by the caller).
+cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
+                              int ldo, double* scratch, int* info, cudaStream_t s);
+
+// dst[i*ldd + j] = scale * src[i*rs + j*cs] for i < rows, j < cols (any strides, device pointers).
+cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double* dst,
+                          int64_t ldd, cudaStream_t s, double scale = 1.0);
+
+// dst[i*drs + j*dcs] = src[i*ld + j]  (scatter a padded row-major matrix to arbitrary output strides)
+cudaError_t scatter_launch(const double* src, int64_t rows, int64_t cols, int64_t ld, double* dst, int64_t drs,
+                           int64_t dcs, cudaStream_t s);
+
+}  // namespace corrla

@@ -1,0 +1,136 @@
+/* libcorrla_b200.so -- C ABI of the B200-native randomized-SVD engine.
+ *
+ * Drop-in boundary for the one hot path of wgurecky/CORRLA_RS.  The reference has no FFI of its own; the
+ * entry points below are what a Rust `-sys` crate / the pyo3 module would bind in place of the pure-Rust
+ * bodies (paths relative to the reference checkout):
+ *
+ *   corrla_rsvd_f64               <- random_svd<T>()        src/lib_math_utils/random_svd.rs:63-110
+ *                                    and the pyo3 rsvd()    src/lib_math_utils_py.rs:21-36
+ *   corrla_power_iter_f64         <- power_iter<T>()        src/lib_math_utils/random_svd.rs:15-59
+ *   corrla_par_matmul_f64         <- par_matmul_helper<T>() src/lib_math_utils/mat_utils.rs:20-33
+ *   corrla_random_mat_normal_f64  <- random_mat_normal<T>() src/lib_math_utils/mat_utils.rs:161-175
+ *
+ * Conventions: plain pointers and sizes only; every function returns CORRLA_OK (0) or a negative
+ * corrla_status and never unwinds.  Matrices are described like a faer MatRef: (ptr, nrows, ncols,
+ * row_stride, col_stride) with strides in ELEMENTS; inputs are borrowed and never modified.  Outputs are
+ * written column-major (faer `Mat` layout) into caller-owned buffers.  All arithmetic is IEEE f64 on the GPU
+ * (DMMA tensor pipe); there is no CPU fallback: without a usable CUDA device the calls fail with
+ * CORRLA_ERR_NO_DEVICE.
+ */
+#ifndef CORRLA_B200_H
+#define CORRLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CORRLA_API __attribute__((visibility("default")))
+#else
+#define CORRLA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum corrla_status {
+  CORRLA_OK = 0,
+  CORRLA_ERR_INVALID = -1,      /* bad argument (null pointer, zero-sized matrix, bad strides) */
+  CORRLA_ERR_RANK = -2,         /* n_rank > min(n_rank + n_oversamples, ncols(thin a)): the reference panics here
+                                   (out-of-range get at random_svd.rs:98-107) */
+  CORRLA_ERR_CUDA = -3,         /* a CUDA call failed; see corrla_last_error() */
+  CORRLA_ERR_UNSUPPORTED = -4,  /* n_rank + n_oversamples > 128 (round-1 limit of the register-tiled kernels) */
+  CORRLA_ERR_ALLOC = -5,        /* device or host allocation failed */
+  CORRLA_ERR_COMM = -6,         /* NCCL failure or libnccl not loadable */
+  CORRLA_ERR_NO_DEVICE = -7     /* no CUDA device / driver */
+} corrla_status;
+
+/* Opaque per-GPU context: stream, cached device buffers (grow-only), split-K workspace. Thread-safe per ctx. */
+typedef struct corrla_ctx corrla_ctx;
+/* Opaque communicator over the GPUs that hold the row shards of one tall matrix (one process per GPU). */
+typedef struct corrla_comm corrla_comm;
+
+typedef struct corrla_rsvd_opts {
+  uint64_t seed;           /* Philox key for Omega when `omega` is NULL */
+  const double* omega;     /* NULL => Omega = Philox4x32-10 N(0,1); else the injected test matrix,
+                              ncols(thin a) x l with element strides (omega_rs, omega_cs) */
+  int64_t omega_rs, omega_cs;
+  int omega_on_device;     /* 0: host pointer, 1: device pointer */
+  int schedule;            /* 0 = reference (QR only when i > 2, Frobenius scaling each trip; random_svd.rs:35-56)
+                              1 = stabilised (re-orthonormalise before every A^T*Y) */
+  int a_on_device;         /* 0: `a` is a host pointer (copied in, counted in timings.h2d_ms); 1: device pointer */
+  int out_on_device;       /* 0: outputs are host pointers; 1: device pointers */
+  int device;              /* CUDA ordinal, or -1 for the current device */
+  void* stream;            /* cudaStream_t to enqueue on, or NULL for the context's own stream */
+  corrla_ctx* ctx;         /* reuse buffers across calls; NULL => a temporary context per call */
+  corrla_comm* comm;       /* NULL => single GPU.  Else `a` is this rank's block of rows of the thin matrix */
+  int64_t global_rows;     /* with comm: total rows over all ranks (0 => computed with an all-reduce) */
+} corrla_rsvd_opts;
+
+typedef struct corrla_timings {
+  double total_ms;         /* whole call, host clock */
+  double h2d_ms;           /* host->device copy of A (0 when a_on_device) */
+  double device_ms;        /* CUDA-event time of everything enqueued after A is resident */
+  double d2h_ms;           /* device->host copy of the results */
+  int gpu_launches;        /* kernels of this library launched by the call */
+  int passes_over_a;       /* 2 + 2*n_iter */
+  int qr_third_passes;     /* how many CholeskyQR calls needed the shifted third pass */
+  int qr_refills;          /* how many CholeskyQR calls replaced numerically dependent columns by random vectors */
+  int jacobi_sweeps;
+  int live_columns;        /* numerical rank kept by the last CholeskyQR (<= l) */
+} corrla_timings;
+
+CORRLA_API void corrla_rsvd_opts_default(corrla_rsvd_opts* opts);
+
+/* (U, S, Vt) = random_svd(a, n_rank, n_iter, n_oversamples).
+ *   u  : nrows x n_rank, column-major      s : n_rank      vt : n_rank x ncols, column-major
+ * For nrows < ncols the routine works on the transposed view exactly like random_svd.rs:69-74,96-102.
+ * With opts->comm the caller passes its local rows of the THIN matrix (nrows = local rows >= 1, all ranks
+ * the same ncols); u receives the matching local rows, s and vt are replicated. */
+CORRLA_API int corrla_rsvd_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                    size_t n_rank, size_t n_iter, size_t n_oversamples, const corrla_rsvd_opts* opts,
+                    double* u, double* s, double* vt, corrla_timings* timings);
+
+/* q (nrows x omega_rank, column-major) = power_iter(a, omega_rank, n_iter); `a` is used as given (no fat/thin
+ * swap, as in the reference). */
+CORRLA_API int corrla_power_iter_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                          size_t omega_rank, size_t n_iter, const corrla_rsvd_opts* opts, double* q,
+                          corrla_timings* timings);
+
+/* res = beta * lhs * rhs (alpha = None: the destination is overwritten), rhs_cols <= 128.
+ * lhs is m x kk, rhs is kk x rhs_cols, res is m x rhs_cols; all strided, all on the host or all on the device
+ * (on_device).  opts may be NULL (defaults) -- only device/stream/ctx are read. */
+CORRLA_API int corrla_par_matmul_f64(double* res, int64_t res_rs, int64_t res_cs,
+                          const double* lhs, int64_t lhs_rows, int64_t lhs_cols, int64_t lhs_rs, int64_t lhs_cs,
+                          const double* rhs, int64_t rhs_cols, int64_t rhs_rs, int64_t rhs_cs,
+                          double beta, int on_device, const corrla_rsvd_opts* opts);
+
+/* out (n_rows x n_cols, column-major like faer Mat::from_fn) = i.i.d. N(0,1) from Philox4x32-10 keyed by seed.
+ * Element (i, j) is draw number i*n_cols + j. */
+CORRLA_API int corrla_random_mat_normal_f64(uint64_t seed, int64_t n_rows, int64_t n_cols, double* out, int out_on_device,
+                                 const corrla_rsvd_opts* opts);
+
+/* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
+ * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 128.  rank_out (optional) = live columns. */
+CORRLA_API int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                      int on_device, const corrla_rsvd_opts* opts, double* q, int* rank_out);
+
+/* contexts */
+CORRLA_API int corrla_ctx_create(int device, corrla_ctx** out);
+CORRLA_API void corrla_ctx_destroy(corrla_ctx* ctx);
+
+/* communicator (NCCL, loaded with dlopen("libnccl.so.2")); id is the 128-byte ncclUniqueId from rank 0 */
+CORRLA_API int corrla_comm_unique_id(unsigned char id[128]);
+CORRLA_API int corrla_comm_init(const unsigned char id[128], int rank, int nranks, int device, corrla_comm** out);
+CORRLA_API void corrla_comm_destroy(corrla_comm* comm);
+CORRLA_API int corrla_comm_rank(const corrla_comm* comm);
+CORRLA_API int corrla_comm_size(const corrla_comm* comm);
+
+CORRLA_API const char* corrla_status_str(int status);
+CORRLA_API const char* corrla_last_error(void);   /* thread-local text of the last failure */
+CORRLA_API const char* corrla_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORRLA_B200_H */

@@ -1,0 +1,181 @@
+"""CPU model of the B200 engine's *algorithm* (not of the reference) -- TEST INFRASTRUCTURE ONLY.
+
+corrla_rs_b200/csrc/engine.cu reorganises random_svd.rs:15-110 so that it maps onto skinny GEMMs and
+small replicated factors: CholeskyQR2/3 with a deflated triangular inverse instead of Householder QR,
+R^-1 folded into the small side, the Frobenius scaling deferred into the next product, QR-preconditioned
+one-sided Jacobi for the SVD of B, and row sharding with all-reduces of Z = A^T Y and of the Gram matrices.
+This file restates that reorganisation in numpy so that
+
+  * its equivalence with the reference restatement (oracle/ref_rsvd.py) can be checked on the CPU, and
+  * the multi-rank data flow can be exercised with torch.distributed/gloo (tests/test_sharded_gloo.py)
+    by plugging an all-reduce callable in.
+
+Only tests/ import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPS = np.finfo(np.float64).eps
+TOL_DEAD_PER_COL = 8.0 * EPS
+TAU_SHIFT = 1e-10
+
+
+def _identity_allreduce(x: np.ndarray) -> np.ndarray:
+    return x
+
+
+def chol_factor(g: np.ndarray, d0: np.ndarray, shifted: bool, tol_dead: float):
+    """Upper Cholesky with per-column deflation; mirrors chol_factor() in small_kernels.cu."""
+    l = g.shape[0]
+    s = np.array(g, dtype=np.float64, copy=True)
+    dead = np.zeros(l, dtype=bool)
+    minratio = np.inf
+    for j in range(l):
+        piv, dj = s[j, j], d0[j]
+        if shifted:
+            is_dead = (not dj > 0.0) or (not piv > 0.0)
+        else:
+            is_dead = (not dj > 0.0) or (not piv > tol_dead * dj)
+        ratio = piv / dj if (dj > 0.0 and piv > 0.0) else 0.0
+        minratio = min(minratio, ratio)
+        dead[j] = is_dead
+        if is_dead:
+            s[j, j:] = 0.0
+            continue
+        rjj = np.sqrt(piv)
+        s[j, j + 1:] /= rjj
+        s[j, j] = rjj
+        r = s[j, j + 1:]
+        s[j + 1:, j + 1:] -= np.outer(r, r)
+    return np.triu(s), dead, minratio
+
+
+def chol_inv(g: np.ndarray, mode_auto: bool, global_rows: float):
+    """Returns (T, shifted, live): T = deflated inverse of the Cholesky factor of g."""
+    l = g.shape[0]
+    d0 = np.diag(g).copy()
+    tol_dead = TOL_DEAD_PER_COL * l
+    r, dead, minratio = chol_factor(g, d0, False, tol_dead)
+    shifted = False
+    if mode_auto and minratio < TAU_SHIFT:
+        trace = float(np.sum(d0[d0 > 0.0]))
+        shift = 11.0 * (global_rows * l + l * (l + 1.0)) * (0.5 * EPS) * trace
+        gs = np.array(g, copy=True)
+        idx = np.arange(l)
+        pos = d0 > 0.0
+        gs[idx[pos], idx[pos]] += shift
+        r, dead, minratio = chol_factor(gs, d0, True, tol_dead)
+        shifted = True
+    rt = r.copy()
+    rt[dead, dead] = 1.0
+    t = np.linalg.solve(rt, np.eye(l)) if l else rt
+    t = np.triu(t)
+    t[:, dead] = 0.0
+    return t, shifted, dead
+
+
+def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None):
+    """Adaptive CholeskyQR2/3 with refill of numerically dependent columns (they are replaced by fresh
+    Gaussian vectors and re-orthonormalised, which is what a Householder QR's arbitrary completion amounts to).
+    Returns (x_last, t_fold, shifted, live): the orthonormal factor is x_last @ t_fold."""
+    g = distributed_allreduce(x.T @ x)
+    t1, shifted, _ = chol_inv(g, True, global_rows)
+    x = x @ t1
+    g = distributed_allreduce(x.T @ x)
+    tf, _, dead = chol_inv(g, False, global_rows)
+    if shifted:
+        x = x @ tf
+        g = distributed_allreduce(x.T @ x)
+        tf, _, dead = chol_inv(g, False, global_rows)
+    if dead.any():
+        rng = refill_rng or np.random.default_rng(12345)
+        x = x @ tf
+        x[:, dead] = rng.standard_normal((x.shape[0], int(dead.sum())))
+        g = distributed_allreduce(x.T @ x)
+        t1, _, _ = chol_inv(g, False, global_rows)
+        x = x @ t1
+        g = distributed_allreduce(x.T @ x)
+        tf, _, dead = chol_inv(g, False, global_rows)
+    return x, tf, shifted, int(np.sum(~dead))
+
+
+def jacobi_svd(w: np.ndarray, max_sweeps: int = 60):
+    """One-sided Hestenes Jacobi with the round-robin ordering of jacobi_svd_kernel.
+    Returns (ur, sigma, vr) with w = ur diag(sigma) vr^T, sigma descending."""
+    l = w.shape[0]
+    wc = np.array(w, dtype=np.float64, copy=True)
+    vc = np.eye(l)
+    h = (l + 1) // 2
+    top = list(range(h))
+    bot = list(range(h, 2 * h))
+    tol = np.sqrt(l) * EPS
+    for _ in range(max_sweeps):
+        rotations = 0
+        for _step in range(max(2 * h - 1, 1)):
+            for p, q in zip(top, bot):
+                if p > q:
+                    p, q = q, p
+                if q >= l:
+                    continue
+                x, y = wc[:, p], wc[:, q]
+                a, b, c = x @ x, y @ y, x @ y
+                if c != 0.0 and abs(c) > tol * np.sqrt(a) * np.sqrt(b):
+                    zeta = (b - a) / (2.0 * c)
+                    t = np.copysign(1.0, zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta))
+                    cs = 1.0 / np.sqrt(1.0 + t * t)
+                    sn = cs * t
+                    wc[:, p], wc[:, q] = cs * x - sn * y, sn * x + cs * y
+                    vx, vy = vc[:, p].copy(), vc[:, q].copy()
+                    vc[:, p], vc[:, q] = cs * vx - sn * vy, sn * vx + cs * vy
+                    rotations += 1
+            if h > 1:
+                t_last = top[h - 1]
+                top = [top[0], bot[0]] + top[1:h - 1]
+                bot = bot[1:] + [t_last]
+        if rotations == 0:
+            break
+    sig = np.sqrt(np.sum(wc * wc, axis=0))
+    order = np.argsort(-sig, kind="stable")
+    ur = np.zeros_like(wc)
+    nz = sig > 0.0
+    ur[:, nz] = wc[:, nz] / sig[nz]
+    return ur[:, order], sig[order], vc[:, order]
+
+
+def engine_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: int, omega: np.ndarray,
+                allreduce=_identity_allreduce, global_rows: float | None = None, schedule: int = 0,
+                use_numpy_svd_for_core: bool = False):
+    """The engine's algorithm on one row shard of a THIN matrix.  `allreduce(x)` must return the
+    element-wise sum of x over all ranks.  Returns (u_local m x k, s k x 1, vt k x n)."""
+    a = np.asarray(a_local, dtype=np.float64)
+    m, n = a.shape
+    l = min(n_rank + n_oversamples, n)
+    if n_rank > l:
+        raise IndexError("n_rank exceeds l")
+    grows = float(m if global_rows is None else global_rows)
+    y = a @ omega
+    nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
+    for i in range(n_iter):
+        if schedule == 1 or i > 2:
+            y, tf, _, _ = qr_fold(y, allreduce, grows)
+            z = allreduce(a.T @ y) @ tf
+            y = a @ z
+        else:
+            z = allreduce(a.T @ y)
+            y = (a @ z) * (1.0 / np.sqrt(nu2))
+        nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
+    y, tf, _, _ = qr_fold(y, allreduce, grows)
+    zb = allreduce(a.T @ y) @ tf                      # B^T, replicated
+    qz, tzf, _, _ = qr_fold(zb.copy(), _identity_allreduce, float(n))
+    qz = qz @ tzf
+    w = qz.T @ zb
+    if use_numpy_svd_for_core:
+        ur, sig, vrt = np.linalg.svd(w)
+        vr = vrt.T
+    else:
+        ur, sig, vr = jacobi_svd(w)
+    k = n_rank
+    u = y @ (tf @ vr[:, :k])
+    v = qz @ ur[:, :k]
+    return u, sig[:k].reshape(k, 1).copy(), v.T.copy()

@@ -1,0 +1,84 @@
+"""CPU suite: the C-ABI shared library loads and exports exactly what include/corrla_b200.h declares; the host
+logic (argument checks, error mapping) behaves like the reference binding; and the product path fails loudly
+(never falls back to the CPU) when no GPU is present."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "corrla_b200.h").read_text()
+    return sorted(set(re.findall(r"CORRLA_API[^;]*?\b(corrla_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(built_lib):
+    from corrla_rs_b200 import _ffi
+    names = declared_symbols()
+    assert len(names) >= 16
+    assert sorted(_ffi.SYMBOLS) == names            # the ctypes table binds the header 1:1
+    for n in names:
+        assert getattr(built_lib, n) is not None
+
+
+def test_status_strings_and_version(built_lib):
+    assert built_lib.corrla_status_str(0) == b"ok"
+    assert b"panics" in built_lib.corrla_status_str(-2) or b"n_rank" in built_lib.corrla_status_str(-2)
+    assert b"sm_100a" in built_lib.corrla_version()
+
+
+def test_struct_layout_matches_header(built_lib):
+    """opts_default() must leave device = -1 and everything else zero: catches field-order drift between the
+    ctypes mirror and the C struct."""
+    import ctypes as C
+    from corrla_rs_b200 import _ffi
+    o = _ffi.RsvdOpts()
+    C.memset(C.byref(o), 0xFF, C.sizeof(o))
+    built_lib.corrla_rsvd_opts_default(C.byref(o))
+    assert o.device == -1 and o.seed == 0 and o.omega is None and o.schedule == 0
+    assert o.a_on_device == 0 and o.out_on_device == 0 and o.ctx is None and o.comm is None and o.global_rows == 0
+    assert C.sizeof(o) == 88
+
+
+def test_type_errors_like_pyo3(built_lib):
+    import corrla_rs
+    with pytest.raises(TypeError):
+        corrla_rs.rsvd(np.zeros((4, 4), dtype=np.float32), 1, 1, 1)       # PyReadonlyArray2<f64>
+    with pytest.raises(TypeError):
+        corrla_rs.rsvd(np.zeros(4), 1, 1, 1)
+    with pytest.raises(TypeError):
+        corrla_rs.rsvd([[1.0, 2.0]], 1, 1, 1)
+    with pytest.raises(OverflowError):
+        corrla_rs.rsvd(np.zeros((4, 4)), -1, 1, 1)                        # usize extraction
+    with pytest.raises(NotImplementedError):
+        corrla_rs.rpca
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    """On a box without a GPU every compute entry point must fail with CORRLA_ERR_NO_DEVICE."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    import corrla_rs_b200 as cb
+    a = np.random.default_rng(0).standard_normal((32, 8))
+    for call in (lambda: cb.rsvd(a, 2, 2, 2), lambda: cb.power_iter(a, 3, 2), lambda: cb.par_matmul(a, a.T.copy()[:, :4]),
+                 lambda: cb.random_mat_normal(4, 4, 1), lambda: cb.thin_q(a)):
+        with pytest.raises(cb.CorrlaError) as ei:
+            call()
+        assert ei.value.status == -7
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under corrla_rs_b200/ or corrla_rs/ may reference it."""
+    pat = re.compile(r"^\s*(import\s+oracle|from\s+oracle|#\s*include.*oracle)|oracle\.\w+\(|dlopen\([^)]*oracle", re.M)
+    for pkg in ("corrla_rs_b200", "corrla_rs"):
+        for f in (ROOT / pkg).rglob("*"):
+            if f.suffix in (".py", ".cu", ".cuh", ".cpp", ".h"):
+                assert pat.search(f.read_text()) is None, f

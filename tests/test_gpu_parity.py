@@ -1,0 +1,331 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs and the same injected Omega.  Tolerances are the north-star ones: singular values within 1e-10 relative,
+sine of the largest principal angle under 1e-8 -- on inputs where the oracle agrees with itself 10x tighter
+(tests/test_oracle.py::test_oracle_self_consistency_defines_parity_class)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref_rsvd
+
+pytestmark = pytest.mark.gpu
+
+TOL_SIGMA = 1e-10     # relative, per singular value
+TOL_ANGLE = 1e-8      # sine of the largest principal angle
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import corrla_rs_b200
+    corrla_rs_b200._ffi.load()
+    return corrla_rs_b200
+
+
+def lowrank_noise(rng, m, n, r, noise):
+    u, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    return (u * (10.0 * 0.95 ** np.arange(r))) @ v.T + noise * rng.standard_normal((m, n))
+
+
+def assert_parity(out, ref, k, tol_sigma=TOL_SIGMA, tol_angle=TOL_ANGLE):
+    u, s, vt = (np.asarray(x) for x in out)
+    u0, s0, vt0 = ref
+    assert u.shape == u0.shape and s.shape == s0.shape == (k, 1) and vt.shape == vt0.shape
+    es = ref_rsvd.sigma_rel_err(s0, s)
+    eu = ref_rsvd.subspace_sine(u0, u)
+    ev = ref_rsvd.subspace_sine(vt0.T, vt.T)
+    assert es < tol_sigma, f"sigma rel err {es:.3e}"
+    assert eu < tol_angle, f"sin(U angle) {eu:.3e}"
+    assert ev < tol_angle, f"sin(V angle) {ev:.3e}"
+    assert np.max(np.abs(u.T @ u - np.eye(k))) < 1e-12
+    assert np.max(np.abs(vt @ vt.T - np.eye(k))) < 1e-12
+    return es, eu, ev
+
+
+# ------------------------------------------------------------------ fixed vectors
+def test_known_answer_lowrank_5x5(cb):
+    """The reference's only known-answer test (random_svd.rs:153-196): rank-3 5x5 matrix, l = min(15, 5) = 5, so Y is
+    rank deficient at every QR (the CholeskyQR deflation + refill path)."""
+    g = np.load(GOLD / "known_answer_5x5.npz")
+    a, sigma = g["a"], g["sigma"]
+    u, s, vt = cb.rsvd(a, 5, 12, 10, seed=1)
+    assert u.shape == (5, 5) and s.shape == (5, 1) and vt.shape == (5, 5)
+    assert np.max(np.abs(s.ravel() - sigma)) < 1e-3                 # the reference's own tolerance (:182)
+    assert np.max(np.abs(s.ravel()[:3] - np.array([3.0, np.sqrt(5.0), 2.0]))) < 1e-12
+    assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - a)) < 1e-12
+    u, s, vt = cb.rsvd(a, 3, 12, 10, seed=2)
+    assert s.shape == (3, 1)
+    assert np.max(np.abs(s.ravel() - sigma[:3])) < 1e-3             # :195
+    assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - a)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["c1", "tall", "fat", "clamp"])
+def test_committed_oracle_vectors(cb, name):
+    g = np.load(GOLD / "oracle_cases.npz")
+    a, omega = g[f"{name}_a"], g[f"{name}_omega"]
+    k, q, p = (int(x) for x in g[f"{name}_kqp"])
+    out = cb.rsvd(a, k, q, p, omega=omega)
+    assert_parity(out, (g[f"{name}_u"], g[f"{name}_s"], g[f"{name}_vt"]), k)
+
+
+@pytest.mark.parametrize("name", ["tall", "fat"])
+def test_reference_python_statement_vectors(cb, name):
+    """Outputs of the reference's own examples/benchmark_rsvd.py:16-54 (no in-loop QR, no scaling: same subspace
+    in exact arithmetic, so the tolerance is the oracle-vs-statement one, tests/test_oracle.py)."""
+    g = np.load(GOLD / f"ref_examples_rsvd_{name}.npz")
+    k, p, q = int(g["k"]), int(g["p"]), int(g["q"])
+    u, s, vt = cb.rsvd(g["a"], k, q, p, omega=g["omega"])
+    assert ref_rsvd.sigma_rel_err(g["s"], s) < 1e-9
+    assert ref_rsvd.subspace_sine(g["u"], u) < 1e-7
+    assert ref_rsvd.subspace_sine(g["vt"].T, vt.T) < 1e-7
+
+
+# ------------------------------------------------------------------ seeded parity, every layout the callers produce
+CASES = [
+    # name, m, n, (k, q, p), generator
+    ("readme_100x100", 100, 100, (10, 12, 8), "gauss"),
+    ("tall_gauss", 4096, 512, (20, 4, 10), "gauss"),
+    ("tall_l110", 6000, 700, (100, 4, 10), "gauss"),
+    ("pca_like_q20", 3000, 12, (4, 20, 10), "gauss"),          # pca_rsvd.rs:65-66 (q = 20, p = min(n, 10))
+    ("lowrank_noise", 5000, 640, (30, 4, 10), "lowrank"),
+    ("active_ss_like", 20000, 64, (8, 8, 10), "gauss"),        # active_subspaces.rs:241-243
+    ("ragged", 1037, 131, (17, 5, 6), "gauss"),
+]
+
+
+def make(case, rng):
+    name, m, n, kqp, gen = case
+    a = rng.standard_normal((m, n)) if gen == "gauss" else lowrank_noise(rng, m, n, 60, 1e-2)
+    k, q, p = kqp
+    omega = rng.standard_normal((n, min(k + p, n)))
+    return a, omega, kqp
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_parity_row_major_host(cb, case):
+    a, omega, (k, q, p) = make(case, np.random.default_rng(100))
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    assert_parity(cb.rsvd(a, k, q, p, omega=omega), ref, k)
+
+
+@pytest.mark.parametrize("case", CASES[1:5], ids=[c[0] for c in CASES[1:5]])
+def test_parity_column_major_host(cb, case):
+    """faer Mat / numpy F-order: unit row stride (the layout POD and the Rust callers hand in)."""
+    a, omega, (k, q, p) = make(case, np.random.default_rng(101))
+    af = np.asfortranarray(a)
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    assert_parity(cb.rsvd(af, k, q, p, omega=np.asfortranarray(omega)), ref, k)
+
+
+def test_parity_fat_pod_like(cb):
+    """pod_rom.rs:56: snapshots x space (fat) => the path runs on the transposed view."""
+    rng = np.random.default_rng(102)
+    a = rng.standard_normal((20, 5000))
+    k, q, p = 8, 10, 10
+    omega = rng.standard_normal((20, 18))
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    out = cb.rsvd(a, k, q, p, omega=omega)
+    assert out[0].shape == (20, 8) and out[2].shape == (8, 5000)
+    assert_parity(out, ref, k)
+
+
+def test_parity_dmd_like_subviews(cb):
+    """dmd_rom.rs:149-162: _X = all rows, cols 0..N-1 and _Y = first nx rows, cols 1..N of one column-major buffer
+    with an odd column stride (unaligned for TMA => repack / pitched-copy path)."""
+    rng = np.random.default_rng(103)
+    nx, nu, nt = 3001, 2, 41
+    buf = np.asfortranarray(rng.standard_normal((nx + nu, nt)))
+    x = buf[:, : nt - 1]
+    y = buf[:nx, 1:]
+    assert x.strides == (8, 8 * (nx + nu)) and (nx + nu) % 2 == 1
+    for view in (x, y):
+        k, q, p = 14, 6, 12
+        omega = rng.standard_normal((view.shape[1], min(k + p, view.shape[1])))
+        ref = ref_rsvd.random_svd(view, k, q, p, omega=omega)
+        assert_parity(cb.rsvd(view, k, q, p, omega=omega), ref, k)
+
+
+def test_parity_device_resident_torch(cb):
+    """Device path: torch CUDA tensors in, torch CUDA tensors out, row-major, transposed view and odd-offset slice."""
+    import torch
+    rng = np.random.default_rng(104)
+    m, n, k, q, p = 8192, 384, 24, 4, 10
+    a = rng.standard_normal((m, n))
+    omega = rng.standard_normal((n, k + p))
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    ad = torch.from_numpy(a).cuda()
+    od = torch.from_numpy(omega).cuda()
+    out = cb.rsvd(ad, k, q, p, omega=od)
+    assert all(t.is_cuda for t in out)
+    torch.cuda.synchronize()
+    assert_parity([t.cpu().numpy() for t in out], ref, k)
+    # column-major device view of the same matrix
+    adt = torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+    assert adt.stride() == (1, m)
+    out = cb.rsvd(adt, k, q, p, omega=od)
+    torch.cuda.synchronize()
+    assert_parity([t.cpu().numpy() for t in out], ref, k)
+    # slice with an odd element offset and odd pitch: not TMA-compatible => device repack
+    big = torch.zeros((m, n + 3), dtype=torch.float64, device="cuda")
+    big[:, 1:n + 1] = ad
+    out = cb.rsvd(big[:, 1:n + 1], k, q, p, omega=od)
+    torch.cuda.synchronize()
+    assert_parity([t.cpu().numpy() for t in out], ref, k)
+
+
+def test_schedules_agree_on_benign_input(cb):
+    rng = np.random.default_rng(105)
+    a = rng.standard_normal((3000, 200))
+    omega = rng.standard_normal((200, 30))
+    r = cb.rsvd(a, 20, 5, 10, omega=omega, schedule="reference")
+    s = cb.rsvd(a, 20, 5, 10, omega=omega, schedule="stabilised")
+    assert ref_rsvd.sigma_rel_err(r[1], s[1]) < 1e-10
+    assert ref_rsvd.subspace_sine(np.asarray(r[0]), np.asarray(s[0])) < 1e-8
+
+
+def test_power_iter_parity(cb):
+    rng = np.random.default_rng(106)
+    a = rng.standard_normal((2500, 150))
+    omega = rng.standard_normal((150, 22))
+    q0 = ref_rsvd.power_iter(a, 22, 5, omega=omega)
+    q = cb.power_iter(a, 22, 5, omega=omega)
+    assert q.shape == (2500, 22)
+    assert np.max(np.abs(q.T @ q - np.eye(22))) < 1e-12
+    assert ref_rsvd.subspace_sine(q0, q) < TOL_ANGLE
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_rank_panic_and_limits(cb):
+    a = np.random.default_rng(107).standard_normal((64, 9))
+    with pytest.raises(IndexError):                      # k > l = min(k + p, 9): the reference panics
+        cb.rsvd(a, 10, 2, 10)
+    out = cb.rsvd(a, 6, 5, 10, seed=3)                   # l clamps to 9
+    assert out[0].shape == (64, 6) and out[2].shape == (6, 9)
+    with pytest.raises(cb.CorrlaError) as ei:            # round-1 limit
+        cb.rsvd(np.zeros((400, 300)), 120, 1, 10)
+    assert ei.value.status == -4
+
+
+def test_input_is_not_modified_and_deterministic(cb):
+    rng = np.random.default_rng(108)
+    a = rng.standard_normal((2000, 100))
+    keep = a.copy()
+    o1 = cb.rsvd(a, 10, 4, 10, seed=77)
+    o2 = cb.rsvd(a, 10, 4, 10, seed=77)
+    o3 = cb.rsvd(a, 10, 4, 10, seed=78)
+    assert np.array_equal(a, keep)
+    for x, y in zip(o1, o2):
+        assert np.array_equal(np.asarray(x), np.asarray(y))     # bit-reproducible (no atomics on the data path)
+    assert not np.array_equal(np.asarray(o1[0]), np.asarray(o3[0]))
+    assert ref_rsvd.sigma_rel_err(o1[1], o3[1]) < 5e-2           # different Omega, same (flat) spectrum estimate
+
+
+# ------------------------------------------------------------------ the other drop-in rows
+@pytest.mark.parametrize("shape,cols,beta", [((300, 200), 110, 1.0), ((257, 129), 7, -0.5), ((64, 1000), 128, 2.0),
+                                              ((5, 5), 3, 1.0), ((4000, 18), 18, 1.0)])
+def test_par_matmul(cb, shape, cols, beta):
+    """par_matmul_helper (mat_utils.rs:20-33): res = beta * lhs * rhs, every layout, 1e-13 relative."""
+    rng = np.random.default_rng(109)
+    lhs = rng.standard_normal(shape)
+    rhs = rng.standard_normal((shape[1], cols))
+    ref = beta * (lhs @ rhs)
+    scale = np.max(np.abs(ref))
+    for l_, r_ in ((lhs, rhs), (np.asfortranarray(lhs), rhs), (lhs, np.asfortranarray(rhs)),
+                   (np.ascontiguousarray(lhs.T).T, rhs)):
+        res = cb.par_matmul(l_, r_, beta)
+        assert res.shape == ref.shape
+        assert np.max(np.abs(res - ref)) < 1e-13 * scale * np.sqrt(shape[1])
+
+
+def test_par_matmul_transposed_operand_on_device(cb):
+    import torch
+    rng = np.random.default_rng(110)
+    a = rng.standard_normal((5000, 300))
+    y = rng.standard_normal((5000, 40))
+    ad, yd = torch.from_numpy(a).cuda(), torch.from_numpy(y).cuda()
+    z = cb.par_matmul(ad.t(), yd)                      # A^T * Y: random_svd.rs:42-46
+    torch.cuda.synchronize()
+    ref = a.T @ y
+    assert np.max(np.abs(z.cpu().numpy() - ref)) < 1e-12 * np.max(np.abs(ref))
+
+
+def test_random_mat_normal_matches_philox_restatement(cb):
+    for rows, cols, seed in ((1024, 110, 42), (7, 3, 1), (1, 1, 5), (333, 18, 2**40 + 17)):
+        z = cb.random_mat_normal(rows, cols, seed)
+        z0 = ref_rsvd.philox_normal(rows, cols, seed)
+        assert z.shape == (rows, cols)
+        assert np.max(np.abs(z - z0)) < 1e-13
+    assert np.array_equal(cb.random_mat_normal(64, 8, 9), cb.random_mat_normal(64, 8, 9))
+    assert not np.array_equal(cb.random_mat_normal(64, 8, 9), cb.random_mat_normal(64, 8, 10))
+
+
+def test_rsvd_with_engine_omega_equals_injected(cb):
+    """seed path == injecting the same Omega fetched from the generator."""
+    rng = np.random.default_rng(111)
+    a = rng.standard_normal((1500, 90))
+    omega = cb.random_mat_normal(90, 22, 1234)
+    o1 = cb.rsvd(a, 12, 4, 10, seed=1234)
+    o2 = cb.rsvd(a, 12, 4, 10, omega=omega)
+    for x, y in zip(o1, o2):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert_parity(o1, ref_rsvd.random_svd(a, 12, 4, 10, omega=omega), 12)
+
+
+# ------------------------------------------------------------------ CholeskyQR (thin Q) robustness
+def test_thin_q_well_conditioned(cb):
+    rng = np.random.default_rng(112)
+    a = rng.standard_normal((5000, 110))
+    q, rank = cb.thin_q(a, return_rank=True)
+    assert rank == 110
+    assert np.max(np.abs(q.T @ q - np.eye(110))) < 1e-13
+    assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-12 * np.linalg.norm(a)
+    q0, _ = np.linalg.qr(a)
+    assert ref_rsvd.subspace_sine(q0, q) < 1e-12
+
+
+@pytest.mark.parametrize("kappa", [1e4, 1e8, 1e12])
+def test_thin_q_ill_conditioned(cb, kappa):
+    """cond up to 1e12: the shifted third pass must kick in and still deliver orthonormality at machine precision."""
+    rng = np.random.default_rng(113)
+    m, l = 4000, 40
+    u, _ = np.linalg.qr(rng.standard_normal((m, l)))
+    v, _ = np.linalg.qr(rng.standard_normal((l, l)))
+    a = (u * np.logspace(0, -np.log10(kappa), l)) @ v.T
+    q = cb.thin_q(a)
+    assert np.max(np.abs(q.T @ q - np.eye(l))) < 1e-12
+    assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-11 * np.linalg.norm(a)
+
+
+def test_thin_q_rank_deficient_is_completed(cb):
+    rng = np.random.default_rng(114)
+    base = rng.standard_normal((3000, 10))
+    a = np.hstack([base, base @ rng.standard_normal((10, 6)), np.zeros((3000, 2))])     # rank 10 of 18 columns
+    q, rank = cb.thin_q(a, return_rank=True)
+    assert np.max(np.abs(q.T @ q - np.eye(18))) < 1e-12        # completed like a Householder QR would
+    assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-11 * np.linalg.norm(a)
+
+
+# ------------------------------------------------------------------ size-independent properties at larger sizes
+def test_large_device_properties(cb):
+    """1M x 1024 (8 GB) generated on the device: orthonormality, A^T U = V S, and agreement with a planted spectrum."""
+    import torch
+    torch.manual_seed(0)
+    m, n, r, k, q, p = 1 << 20, 1024, 56, 48, 4, 10     # rank 56 <= l = 58: exact recovery, 2 dependent columns
+    u0, _ = torch.linalg.qr(torch.randn(m, r, dtype=torch.float64, device="cuda"))
+    v0, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device="cuda"))
+    sig = 100.0 * 0.97 ** torch.arange(r, dtype=torch.float64, device="cuda")
+    a = (u0 * sig) @ v0.T
+    u, s, vt = cb.rsvd(a, k, q, p, seed=5)
+    torch.cuda.synchronize()
+    t = cb.last_timings()
+    assert t["passes_over_a"] == 10 and t["gpu_launches"] > 0
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float((u.T @ u - eye).abs().max()) < 1e-12
+    assert float((vt @ vt.T - eye).abs().max()) < 1e-12
+    assert float(((s.ravel() - sig[:k]).abs() / sig[:k]).max()) < 1e-10      # planted singular values
+    resid = a.T @ u - vt.T * s.ravel()
+    assert float(resid.abs().max()) < 1e-9 * float(sig[0])
+    pu = u0[:, :k] - u @ (u.T @ u0[:, :k])
+    assert float(torch.linalg.matrix_norm(pu, 2)) < 1e-8

@@ -1,0 +1,138 @@
+"""CPU suite: the oracle (numpy restatement of random_svd.rs:15-110) against every fixed vector available:
+the reference's known-answer test, outputs of the reference's own numpy statement of the algorithm
+(examples/benchmark_rsvd.py, fixtures made by tools/make_golden.py), Philox known answers, and the
+engine-algorithm model against the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import engine_model, ref_rsvd
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def test_known_answer_lowrank_5x5():
+    """test_rsvd_lowrank, random_svd.rs:153-196: sigma = {3, 2.2360679, 2, 0, 0}, abs tol 1e-3 (:182, :195)."""
+    g = np.load(GOLD / "known_answer_5x5.npz")
+    a, sigma, tol = g["a"], g["sigma"], float(g["tol"])
+    rng = np.random.default_rng(0)
+    u, s, vt = ref_rsvd.random_svd(a, 5, 12, 10, rng=rng)
+    assert u.shape == (5, 5) and s.shape == (5, 1) and vt.shape == (5, 5)
+    assert np.max(np.abs(s.ravel() - sigma)) < tol
+    u, s, vt = ref_rsvd.random_svd(a, 3, 12, 10, rng=rng)
+    assert s.shape == (3, 1)
+    assert np.max(np.abs(s.ravel() - sigma[:3])) < tol
+    assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - a)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tall", "fat"])
+def test_against_reference_python_statement(name):
+    """examples/benchmark_rsvd.py:16-54 differs from random_svd.rs only by having no in-loop QR and no scaling,
+    which changes nothing in exact arithmetic: same shapes, same fat handling, same sigma and subspaces on
+    a well-conditioned input."""
+    g = np.load(GOLD / f"ref_examples_rsvd_{name}.npz")
+    a, omega, k, p, q = g["a"], g["omega"], int(g["k"]), int(g["p"]), int(g["q"])
+    u, s, vt = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    assert u.shape == g["u"].shape and vt.shape == g["vt"].shape and s.shape == (k, 1)
+    assert ref_rsvd.sigma_rel_err(g["s"], s) < 1e-9
+    assert ref_rsvd.subspace_sine(g["u"], u) < 1e-7
+    assert ref_rsvd.subspace_sine(g["vt"].T, vt.T) < 1e-7
+
+
+def test_shapes_and_clamp_and_panic():
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((64, 9))
+    u, s, vt = ref_rsvd.random_svd(a, 6, 5, 10, rng=rng)     # l = min(16, 9) = 9  (random_svd.rs:77)
+    assert u.shape == (64, 6) and s.shape == (6, 1) and vt.shape == (6, 9)
+    with pytest.raises(IndexError):                            # k > l: out-of-range get (:98-107)
+        ref_rsvd.random_svd(a, 10, 5, 10, rng=rng)
+    with pytest.raises(TypeError):
+        ref_rsvd.random_svd(np.zeros(5), 1, 1, 1)
+    ut, st, vtt = ref_rsvd.random_svd(a.T.copy(), 6, 5, 10, rng=np.random.default_rng(4))
+    assert ut.shape == (9, 6) and vtt.shape == (6, 64)
+
+
+def test_par_matmul_semantics():
+    """test_par_matmul_mat_vec / mat_mat (mat_utils.rs:642-684): overwrite with beta * lhs * rhs."""
+    eye = np.eye(2)
+    v = np.array([[1.0], [2.0]])
+    assert np.allclose(ref_rsvd.par_matmul_helper(eye, v, 1.0), v, atol=1e-6)
+    b = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.allclose(ref_rsvd.par_matmul_helper(eye, b, 1.0), b, atol=1e-6)
+    assert np.allclose(ref_rsvd.par_matmul_helper(b, b, 0.5), 0.5 * b @ b)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    w = ref_rsvd.philox4x32_10(np.array([0]), 0)[0]
+    assert [int(x) for x in w] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    # counter = ffffffff ffffffff 0 0 with key ffffffff ffffffff is not a published vector (counter words 2,3 are
+    # zero here), so pin the second property instead: distinct counters/keys give distinct streams
+    a = ref_rsvd.philox4x32_10(np.arange(1000), 1)
+    b = ref_rsvd.philox4x32_10(np.arange(1000), 2)
+    assert len({tuple(r) for r in a}) == 1000 and not np.array_equal(a, b)
+
+
+def test_philox_normal_moments_and_layout():
+    z = ref_rsvd.philox_normal(2000, 110, 42)
+    assert z.shape == (2000, 110)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs(np.mean(z ** 4) - 3.0) < 0.1
+    z2 = ref_rsvd.philox_normal(7, 3, 42)          # odd element count: last pair half used
+    assert np.array_equal(z2.ravel(), ref_rsvd.philox_normal(21, 1, 42).ravel())
+
+
+def test_oracle_self_consistency_defines_parity_class():
+    """the reference schedule is only reproducible at 1e-10 / 1e-8 on well-conditioned inputs.
+    Re-running the oracle with the GEMM summation order changed (columns of A permuted together with the rows
+    of Omega) must agree 10x tighter than the GPU tolerance on the classes the GPU tests gate on."""
+    rng = np.random.default_rng(5)
+    m, n, k, q, p = 1200, 160, 12, 4, 10
+    perm = rng.permutation(n)
+    for a in (rng.standard_normal((m, n)), _lowrank_noise(rng, m, n, 40, 1e-2)):
+        omega = rng.standard_normal((n, k + p))
+        u0, s0, v0 = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+        u1, s1, v1 = ref_rsvd.random_svd(a[:, perm], k, q, p, omega=omega[perm])
+        assert ref_rsvd.sigma_rel_err(s0, s1) < 1e-11
+        assert ref_rsvd.subspace_sine(u0, u1) < 1e-9
+
+
+def _lowrank_noise(rng, m, n, r, noise):
+    u, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    return (u * (10.0 * 0.95 ** np.arange(r))) @ v.T + noise * rng.standard_normal((m, n))
+
+
+@pytest.mark.parametrize("shape,kqp", [((100, 100), (10, 12, 8)), ((900, 130), (20, 4, 10)), ((700, 64), (8, 8, 10))])
+def test_engine_algorithm_model_matches_oracle(shape, kqp):
+    """The reorganised algorithm the CUDA engine runs (CholeskyQR2/3, folded R^-1, deferred scaling, QR-preconditioned
+    Jacobi) is equivalent to the reference schedule at the GPU tolerance."""
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal(shape)
+    k, q, p = kqp
+    omega = rng.standard_normal((shape[1], min(k + p, shape[1])))
+    u0, s0, v0 = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    u1, s1, v1 = engine_model.engine_rsvd(a, k, q, p, omega)
+    assert ref_rsvd.sigma_rel_err(s0, s1) < 1e-11
+    assert ref_rsvd.subspace_sine(u0, u1) < 1e-9
+    assert ref_rsvd.subspace_sine(v0.T, v1.T) < 1e-9
+    assert np.max(np.abs(u1.T @ u1 - np.eye(k))) < 1e-12
+
+
+def test_engine_model_rank_deficient_refill():
+    g = np.load(GOLD / "known_answer_5x5.npz")
+    omega = np.random.default_rng(8).standard_normal((5, 5))
+    u, s, vt = engine_model.engine_rsvd(g["a"], 5, 12, 10, omega)
+    assert np.max(np.abs(s.ravel() - g["sigma"])) < 1e-3
+    assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - g["a"])) < 1e-12
+
+
+def test_engine_model_jacobi_svd():
+    rng = np.random.default_rng(9)
+    w = np.triu(rng.standard_normal((37, 37))) * (0.8 ** np.arange(37))[None, :]
+    ur, sig, vr = engine_model.jacobi_svd(w)
+    s_ref = np.linalg.svd(w, compute_uv=False)
+    assert np.max(np.abs(sig - s_ref)) < 1e-14 * s_ref[0]
+    assert np.max(np.abs(sig - s_ref) / s_ref) < 1e-9          # high relative accuracy even at kappa = 1e10
+    assert np.max(np.abs(ur @ np.diag(sig) @ vr.T - w)) < 1e-13
