@@ -42,6 +42,9 @@ class Timings(C.Structure):
         ("qr_refills", C.c_int),
         ("jacobi_sweeps", C.c_int),
         ("live_columns", C.c_int),
+        ("pass_launches", C.c_int),
+        ("pass_ms", C.c_double),
+        ("pass_flops", C.c_double),
     ]
 
     def as_dict(self):

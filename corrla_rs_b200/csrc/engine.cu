@@ -28,6 +28,15 @@ struct corrla_ctx {
   struct Buf { void* p = nullptr; size_t bytes = 0; };
   std::map<std::string, Buf> pool;
   void* pinned = nullptr; size_t pinned_bytes = 0;
+  std::vector<cudaEvent_t> events;   // reusable timing events
+  cudaEvent_t event(size_t i) {
+    while (events.size() <= i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      events.push_back(e);
+    }
+    return events[i];
+  }
 
   // grow-only device buffer
   void* get(const char* name, size_t bytes) {
@@ -50,6 +59,7 @@ struct corrla_ctx {
   }
   ~corrla_ctx() {
     for (auto& kv : pool) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto e : events) cudaEventDestroy(e);
     if (pinned) cudaFreeHost(pinned);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
@@ -187,9 +197,18 @@ struct Core {
     return CORRLA_OK;
   }
 
+  bool profile_passes = false;
+  int n_pass_events = 0;    // pairs recorded so far: events 2i, 2i+1 (offset by 2 for the whole-call pair)
+
   int mm(const MatView& a, bool reduce_inner, const double* B, double* out, int64_t ors, int64_t ocs, int ncols_out,
-         const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0) {
+         const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0,
+         bool is_pass = false) {
     GemmCall c{};
+    if (is_pass && profile_passes) {
+      c.ev_begin = ctx->event(2 + 2 * (size_t)n_pass_events);
+      c.ev_end = ctx->event(3 + 2 * (size_t)n_pass_events);
+      if (c.ev_begin && c.ev_end) ++n_pass_events;
+    }
     c.a = a; c.reduce_inner = reduce_inner; c.B = B; c.ldb = ld; c.nblk = nblk;
     c.out = out; c.out_rs = ors; c.out_cs = ocs; c.ncols_out = ncols_out;
     c.alpha_sumsq = alpha; c.sumsq_slot = sumsq; c.cond_flag = cond; c.force_splits = force_splits;
@@ -207,10 +226,12 @@ struct Core {
 
   // Y[m x Lc] = alpha * A * X        (X: n16 x ld)
   int mm_AX(const double* X, double* Yout, const double* alpha, double* sumsq) {
-    return mm(av, a_rowmajor, X, Yout, ld, 1, Lc, alpha, sumsq);
+    return mm(av, a_rowmajor, X, Yout, ld, 1, Lc, alpha, sumsq, nullptr, 0, true);
   }
   // Z[n x Lc] = A^T * Yin            (Yin: m16 x ld)
-  int mm_AtY(const double* Yin, double* Zout) { return mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc); }
+  int mm_AtY(const double* Yin, double* Zout) {
+    return mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true);
+  }
 
   int allreduce(double* buf, size_t count) {
     if (comm == nullptr || comm->nranks <= 1) return CORRLA_OK;
@@ -476,7 +497,12 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   }
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (tm) { CU_TRY(cudaEventCreate(&ev0)); CU_TRY(cudaEventCreate(&ev1)); CU_TRY(cudaEventRecord(ev0, sc.st)); }
+  if (tm) {
+    ev0 = sc.ctx->event(0); ev1 = sc.ctx->event(1);
+    if (!ev0 || !ev1) { set_last_error("cudaEventCreate failed"); return CORRLA_ERR_CUDA; }
+    c.profile_passes = true;
+    CU_TRY(cudaEventRecord(ev0, sc.st));
+  }
 
   const double* omega_packed = nullptr;
   if (o.omega != nullptr) {
@@ -545,7 +571,13 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     CU_TRY(cudaStreamSynchronize(sc.st));
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    double pass_ms = 0.0;
+    for (int i = 0; i < c.n_pass_events; ++i) {
+      float pm = 0.f;
+      if (cudaEventElapsedTime(&pm, sc.ctx->event(2 + 2 * (size_t)i), sc.ctx->event(3 + 2 * (size_t)i)) == cudaSuccess) pass_ms += pm;
+      else cudaGetLastError();
+    }
+    tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l;
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
     tm->qr_third_passes = hflags[8]; tm->qr_refills = hflags[9]; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1];

@@ -421,7 +421,9 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
 
   const int W = a.tilesM * a.splits;
   const int grid = std::min(W, w.num_sms);
+  if (c.ev_begin) cudaEventRecord(c.ev_begin, stream);
   fn<<<grid, threads, smem, stream>>>(tm, a);
+  if (c.ev_end) cudaEventRecord(c.ev_end, stream);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

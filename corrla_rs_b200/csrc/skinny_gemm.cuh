@@ -53,6 +53,7 @@ struct GemmCall {
   double* sumsq_slot = nullptr;     // if set: *sumsq_slot = sum of squares of the (scaled) output
   const int* cond_flag = nullptr;
   int force_splits = 0;             // testing hook: 0 = choose
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;   // optional: recorded around the DMMA kernel only
 };
 
 struct GemmWorkspace {

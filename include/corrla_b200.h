@@ -78,6 +78,9 @@ typedef struct corrla_timings {
   int qr_refills;          /* how many CholeskyQR calls replaced numerically dependent columns by random vectors */
   int jacobi_sweeps;
   int live_columns;        /* numerical rank kept by the last CholeskyQR (<= l) */
+  int pass_launches;       /* launches of the DMMA GEMM kernel that stream A (== passes_over_a) */
+  double pass_ms;          /* summed CUDA-event duration of those launches (the dominant kernel) */
+  double pass_flops;       /* algorithmic flops of one such launch on this GPU: 2 * local_rows * ncols * l */
 } corrla_timings;
 
 CORRLA_API void corrla_rsvd_opts_default(corrla_rsvd_opts* opts);
