@@ -1,0 +1,81 @@
+//! Raw FFI surface of `libcorrla_b200.so`; mirrors `include/corrla_b200.h` field for field.
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+pub const CORRLA_OK: c_int = 0;
+pub const CORRLA_ERR_INVALID: c_int = -1;
+pub const CORRLA_ERR_RANK: c_int = -2;
+pub const CORRLA_ERR_CUDA: c_int = -3;
+pub const CORRLA_ERR_UNSUPPORTED: c_int = -4;
+pub const CORRLA_ERR_ALLOC: c_int = -5;
+pub const CORRLA_ERR_COMM: c_int = -6;
+pub const CORRLA_ERR_NO_DEVICE: c_int = -7;
+
+#[repr(C)]
+pub struct corrla_ctx { _private: [u8; 0] }
+#[repr(C)]
+pub struct corrla_comm { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct corrla_rsvd_opts {
+    pub seed: u64,
+    pub omega: *const f64,
+    pub omega_rs: i64,
+    pub omega_cs: i64,
+    pub omega_on_device: c_int,
+    pub schedule: c_int,
+    pub a_on_device: c_int,
+    pub out_on_device: c_int,
+    pub device: c_int,
+    pub stream: *mut c_void,
+    pub ctx: *mut corrla_ctx,
+    pub comm: *mut corrla_comm,
+    pub global_rows: i64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct corrla_timings {
+    pub total_ms: f64,
+    pub h2d_ms: f64,
+    pub device_ms: f64,
+    pub d2h_ms: f64,
+    pub gpu_launches: c_int,
+    pub passes_over_a: c_int,
+    pub qr_third_passes: c_int,
+    pub qr_refills: c_int,
+    pub jacobi_sweeps: c_int,
+    pub live_columns: c_int,
+    pub pass_launches: c_int,
+    pub pass_ms: f64,
+    pub pass_flops: f64,
+}
+
+extern "C" {
+    pub fn corrla_rsvd_opts_default(opts: *mut corrla_rsvd_opts);
+    pub fn corrla_rsvd_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
+                           n_rank: usize, n_iter: usize, n_oversamples: usize, opts: *const corrla_rsvd_opts,
+                           u: *mut f64, s: *mut f64, vt: *mut f64, timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_power_iter_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
+                                 omega_rank: usize, n_iter: usize, opts: *const corrla_rsvd_opts, q: *mut f64,
+                                 timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_par_matmul_f64(res: *mut f64, res_rs: i64, res_cs: i64, lhs: *const f64, lhs_rows: i64,
+                                 lhs_cols: i64, lhs_rs: i64, lhs_cs: i64, rhs: *const f64, rhs_cols: i64,
+                                 rhs_rs: i64, rhs_cs: i64, beta: f64, on_device: c_int,
+                                 opts: *const corrla_rsvd_opts) -> c_int;
+    pub fn corrla_random_mat_normal_f64(seed: u64, n_rows: i64, n_cols: i64, out: *mut f64, out_on_device: c_int,
+                                        opts: *const corrla_rsvd_opts) -> c_int;
+    pub fn corrla_thin_q_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
+                             on_device: c_int, opts: *const corrla_rsvd_opts, q: *mut f64, rank_out: *mut c_int) -> c_int;
+    pub fn corrla_ctx_create(device: c_int, out: *mut *mut corrla_ctx) -> c_int;
+    pub fn corrla_ctx_destroy(ctx: *mut corrla_ctx);
+    pub fn corrla_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn corrla_comm_init(id: *const u8, rank: c_int, nranks: c_int, device: c_int, out: *mut *mut corrla_comm) -> c_int;
+    pub fn corrla_comm_destroy(comm: *mut corrla_comm);
+    pub fn corrla_comm_rank(comm: *const corrla_comm) -> c_int;
+    pub fn corrla_comm_size(comm: *const corrla_comm) -> c_int;
+    pub fn corrla_status_str(status: c_int) -> *const c_char;
+    pub fn corrla_last_error() -> *const c_char;
+    pub fn corrla_version() -> *const c_char;
+}
