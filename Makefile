@@ -5,7 +5,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisi
 CSRC      := corrla_rs_b200/csrc
 OBJDIR    := build
 LIB       := corrla_rs_b200/lib/libcorrla_b200.so
-OBJS      := $(OBJDIR)/skinny_gemm.o $(OBJDIR)/small_kernels.o $(OBJDIR)/engine.o $(OBJDIR)/comm.o
+OBJS      := $(OBJDIR)/skinny_gemm.o $(OBJDIR)/small_kernels.o $(OBJDIR)/engine.o $(OBJDIR)/comm.o $(OBJDIR)/hostcopy.o
 
 all: $(LIB)
 
@@ -15,7 +15,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/corrla_b200.h
 
 $(LIB): $(OBJS)
 	@mkdir -p $(dir $(LIB))
-	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS) -ldl
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS) -ldl -lpthread
 
 tools: tools/test_gemm tools/peaks2
 tools/test_gemm: tools/test_gemm.cu $(CSRC)/skinny_gemm.cu $(CSRC)/skinny_gemm.cuh $(CSRC)/ptx.cuh

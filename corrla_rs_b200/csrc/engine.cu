@@ -12,6 +12,7 @@
 
 #include "../../include/corrla_b200.h"
 #include "comm.cuh"
+#include "hostcopy.cuh"
 #include "skinny_gemm.cuh"
 #include "small_kernels.cuh"
 
@@ -28,6 +29,7 @@ struct corrla_ctx {
   struct Buf { void* p = nullptr; size_t bytes = 0; };
   std::map<std::string, Buf> pool;
   void* pinned = nullptr; size_t pinned_bytes = 0;
+  BounceBuffers bounce;
   std::vector<cudaEvent_t> events;   // reusable timing events
   cudaEvent_t event(size_t i) {
     while (events.size() <= i) {
@@ -61,6 +63,7 @@ struct corrla_ctx {
     for (auto& kv : pool) if (kv.second.p) cudaFree(kv.second.p);
     for (auto e : events) cudaEventDestroy(e);
     if (pinned) cudaFreeHost(pinned);
+    bounce.release();
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 };
@@ -376,8 +379,7 @@ int stage_matrix(corrla_ctx* ctx, cudaStream_t st, const char* bufname, const do
     const int64_t ldd = round_up(inner, 2);
     double* buf = static_cast<double*>(ctx->get(bufname, (size_t)outer * ldd * 8));
     if (!buf) { set_last_error("device allocation for A failed (%lld x %lld)", (long long)rows, (long long)cols); return CORRLA_ERR_ALLOC; }
-    CU_TRY(cudaMemcpy2DAsync(buf, ldd * 8, a, src_ld * 8, inner * 8, outer, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(copy_h2d_2d(ctx->bounce, st, buf, ldd * 8, a, src_ld * 8, inner * 8, outer));
     *view = MatView{buf, inner, outer, ldd};
     *rowmajor = rowmajor_like;
   } else {
@@ -521,7 +523,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
     if (!out_dev) {
       CU_TRY(cudaStreamSynchronize(sc.st));
-      Timer t; CU_TRY(cudaMemcpy(q_out, qd, (size_t)m * l * 8, cudaMemcpyDeviceToHost)); d2h_ms = t.ms();
+      Timer t; CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, q_out, (size_t)m * l * 8, qd, (size_t)m * l * 8, (size_t)m * l * 8, 1)); d2h_ms = t.ms();
     }
   } else {
     // B^T = Z_B = (A^T Y) Tf                                       random_svd.rs:80
@@ -559,8 +561,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     if (!out_dev) {
       CU_TRY(cudaStreamSynchronize(sc.st));
       Timer t;
-      CU_TRY(cudaMemcpy(u, ud, (size_t)nrows * kk * 8, cudaMemcpyDeviceToHost));
-      CU_TRY(cudaMemcpy(vt, vd, (size_t)ncols * kk * 8, cudaMemcpyDeviceToHost));
+      CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, u, (size_t)nrows * kk * 8, ud, (size_t)nrows * kk * 8, (size_t)nrows * kk * 8, 1));
+      CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, vt, (size_t)ncols * kk * 8, vd, (size_t)ncols * kk * 8, (size_t)ncols * kk * 8, 1));
       CU_TRY(cudaMemcpy(s, sd, (size_t)kk * 8, cudaMemcpyDeviceToHost));
       d2h_ms = t.ms();
     }

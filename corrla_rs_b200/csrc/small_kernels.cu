@@ -55,11 +55,13 @@ philox_normal_kernel(double* __restrict__ out, int64_t rows, int cols, int64_t l
 constexpr double kTolDeadPerCol = 8.0 * DBL_EPSILON;  // times l
 constexpr double kTauShift = 1e-10;
 
-// Factor S (upper triangle, pitch lp) in place. Returns the smallest pivot ratio (valid in thread 0's
-// view through *minratio_s).  dead[j] = 1 where the pivot vanished; that row of R is zero.
-__device__ void chol_factor(double* S, int lp, int l, const double* d0, int* dead, bool shifted, double tol_dead,
-                            double* minratio_s) {
+// Factor S (upper triangle, pitch lp) in place; the diagonal of R goes to diag[] (S[j][j] keeps the pivot), so no
+// thread overwrites what another still reads and a step needs two barriers.  Smallest pivot ratio -> *minratio_s.
+// dead[j] = 1 where the pivot vanished; that row of R is zero.
+__device__ void chol_factor(double* S, int lp, int l, const double* d0, double* diag, int* dead, bool shifted,
+                            double tol_dead, double* minratio_s) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
   if (tid == 0) *minratio_s = DBL_MAX;
   __syncthreads();
   for (int j = 0; j < l; ++j) {
@@ -68,26 +70,26 @@ __device__ void chol_factor(double* S, int lp, int l, const double* d0, int* dea
     bool is_dead;
     if (shifted) is_dead = !(dj > 0.0) || !(piv > 0.0);
     else is_dead = !(dj > 0.0) || !(piv > tol_dead * dj);
-    __syncthreads();   // everyone has read the pivot before it is overwritten
     if (tid == 0) {
       const double ratio = (dj > 0.0 && piv > 0.0) ? piv / dj : 0.0;
       if (ratio < *minratio_s) *minratio_s = ratio;
       dead[j] = is_dead ? 1 : 0;
+      diag[j] = is_dead ? 0.0 : sqrt(piv);
     }
     if (!is_dead) {
-      const double rjj = sqrt(piv), inv = 1.0 / rjj;
+      const double inv = 1.0 / sqrt(piv);
       for (int k = j + 1 + tid; k < l; k += nt) S[j * lp + k] *= inv;
-      if (tid == 0) S[j * lp + j] = rjj;
     } else {
-      for (int k = j + tid; k < l; k += nt) S[j * lp + k] = 0.0;
+      for (int k = j + 1 + tid; k < l; k += nt) S[j * lp + k] = 0.0;
     }
     __syncthreads();
     if (!is_dead) {
-      const int n1 = l - j - 1;
-      const double* rj = S + j * lp + j + 1;
-      for (int idx = tid; idx < n1 * n1; idx += nt) {
-        const int ii = idx / n1, kk = idx - ii * n1;
-        if (kk >= ii) S[(j + 1 + ii) * lp + j + 1 + kk] -= rj[ii] * rj[kk];
+      const double* rj = S + j * lp;
+      for (int i = j + 1 + ty; i < l; i += nty) {
+        const double ri = rj[i];
+        double* si = S + i * lp;
+        for (int k = (i & ~31) + tx; k < l; k += 32)
+          if (k >= i) si[k] -= ri * rj[k];
       }
     }
     __syncthreads();
@@ -104,7 +106,8 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
   double* S = sm;                 // l x lp
   double* d0 = S + l * lp;        // l
   double* v = d0 + l;             // l
-  double* scal = v + l;           // [0] minratio, [1] trace
+  double* diag = v + l;           // l: diagonal of R
+  double* scal = diag + l;        // [0] minratio, [1] trace
   int* dead = reinterpret_cast<int*>(scal + 2);
   const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const double tol_dead = kTolDeadPerCol * l;
@@ -122,7 +125,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
   }
   __syncthreads();
 
-  chol_factor(S, lp, l, d0, dead, false, tol_dead, &scal[0]);
+  chol_factor(S, lp, l, d0, diag, dead, false, tol_dead, &scal[0]);
   int shifted = 0;
   if (mode == kCholAuto) {
     const double mr = scal[0];
@@ -137,7 +140,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
         S[i * lp + j] = g;
       }
       __syncthreads();
-      chol_factor(S, lp, l, d0, dead, true, tol_dead, &scal[0]);
+      chol_factor(S, lp, l, d0, diag, dead, true, tol_dead, &scal[0]);
       shifted = 1;
     }
     if (tid == 0 && flag3 != nullptr) *flag3 = shifted;
@@ -146,7 +149,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
   // In-place inverse of the upper-triangular factor (dead diagonal entries act as 1), column by column:
   // T[0:j, j] = -T[0:j,0:j] * R[0:j, j] * T[j][j]
   for (int j = 0; j < l; ++j) {
-    const double tjj = dead[j] ? 1.0 : 1.0 / S[j * lp + j];
+    const double tjj = dead[j] ? 1.0 : 1.0 / diag[j];
     for (int k = tid; k < j; k += nt) v[k] = S[k * lp + j];
     __syncthreads();
     for (int i = warp; i < j; i += nw) {
@@ -197,108 +200,114 @@ refill_dead_kernel(double* __restrict__ X, int64_t rows, int l, int64_t ld, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// One-sided Jacobi SVD, one CTA of 32 warps, round-robin pair ordering, one warp per column pair
+// One-sided (Hestenes) Jacobi SVD, one CTA.  Each half-warp owns one column pair of the current round of
+// a round-robin tournament (closed-form schedule, no shared ordering state), so a round of up to 64 disjoint pairs
+// costs one barrier.  Column norms are carried along and refreshed exactly at the start of every sweep, which
+// leaves a single dot product per pair.  The matrix handed in is nearly upper triangular (an R factor); following
+// Drmac & Veselic the rotations are applied to its transpose, which converges in fewer sweeps.
 // ------------------------------------------------------------------------------------------------
 constexpr int kJacobiMaxSweeps = 60;
 
 __global__ void __launch_bounds__(1024)
 jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                   double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, double* gscratch,
-                  int w_smem, int v_smem, int* info) {
+                  int w_smem, int v_smem, int transpose, int* info) {
   extern __shared__ double sm[];
   const int lp = l | 1;
-  const int h = (l + 1) >> 1;
-  double* Wc = w_smem ? sm : gscratch;
-  double* Vc = v_smem ? (sm + (w_smem ? l * lp : 0)) : (gscratch + l * lp);
-  double* sig = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);
-  int* top = reinterpret_cast<int*>(sig + l);
-  int* bot = top + h;
-  int* rnk = bot + h;
-  int* cnt = rnk + l;
-  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int h = (l + 1) >> 1;          // pairs per round; N = 2h players, player index >= l is a bye
+  const int N1 = 2 * h - 1;
+  double* Xc = w_smem ? sm : gscratch;                                   // working columns (become U*Sigma)
+  double* Vc = v_smem ? (sm + (w_smem ? l * lp : 0)) : (gscratch + l * lp);   // accumulated rotations
+  double* nrm = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);      // squared column norms
+  int* rnk = reinterpret_cast<int*>(nrm + l);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int hw = tid >> 4, sub = tid & 15, nhw = nt >> 4;
+  const unsigned hmask = 0xffffu << (tid & 16);
 
   for (int idx = tid; idx < l * l; idx += nt) {
     const int i = idx / l, j = idx - i * l;
-    Wc[j * lp + i] = Win[(int64_t)i * ldw + j];
+    const double w = Win[(int64_t)i * ldw + j];
+    if (transpose) Xc[i * lp + j] = w; else Xc[j * lp + i] = w;
     Vc[j * lp + i] = (i == j) ? 1.0 : 0.0;
   }
-  for (int i = tid; i < h; i += nt) { top[i] = i; bot[i] = i + h; }
   for (int idx = tid; idx < Lrows * ldo; idx += nt) { Vr_out[idx] = 0.0; Ur_out[idx] = 0.0; }
   __syncthreads();
 
   const double tol = sqrt((double)l) * DBL_EPSILON;
   int sweeps = 0, converged = 0;
   for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
-    if (tid == 0) *cnt = 0;
-    __syncthreads();
-    const int steps = (2 * h - 1 > 0) ? 2 * h - 1 : 1;
-    for (int step = 0; step < steps; ++step) {
-      for (int pi = warp; pi < h; pi += nw) {
-        int p = top[pi], q = bot[pi];
-        if (p > q) { const int tmp = p; p = q; q = tmp; }
-        if (q >= l) continue;
-        double* wp = Wc + p * lp; double* wq = Wc + q * lp;
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int i = lane; i < l; i += 32) {
-          const double x = wp[i], y = wq[i];
-          a += x * x; b += y * y; c += x * y;
-        }
+    // exact norms
+    for (int j = hw; j < l; j += nhw) {
+      double a = 0.0;
+      for (int i = sub; i < l; i += 16) { const double x = Xc[j * lp + i]; a += x * x; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); c += __shfl_xor_sync(kFull, c, o);
-        }
-        a = __shfl_sync(kFull, a, 0); b = __shfl_sync(kFull, b, 0); c = __shfl_sync(kFull, c, 0);
+      for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(hmask, a, o);
+      if (sub == 0) nrm[j] = a;
+    }
+    __syncthreads();
+    int any = 0;
+    for (int r = 0; r < N1; ++r) {
+      int rotated = 0;
+      for (int pi = hw; pi < h; pi += nhw) {
+        int p, q;
+        if (pi == 0) { p = N1; q = r; }
+        else { p = r + pi; if (p >= N1) p -= N1; q = r - pi; if (q < 0) q += N1; }
+        if (p > q) { const int tmp = p; p = q; q = tmp; }
+        if (q >= l) continue;                                     // bye
+        double* xp = Xc + p * lp; double* xq = Xc + q * lp;
+        double c = 0.0;
+        for (int i = sub; i < l; i += 16) c += xp[i] * xq[i];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(hmask, c, o);
+        c = __shfl_sync(hmask, c, tid & 16);                      // identical bits in all 16 lanes
+        const double a = nrm[p], b = nrm[q];
         if (c != 0.0 && fabs(c) > tol * sqrt(a) * sqrt(b)) {
           const double zeta = (b - a) / (2.0 * c);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
           double* vp = Vc + p * lp; double* vq = Vc + q * lp;
-          for (int i = lane; i < l; i += 32) {
-            const double x = wp[i], y = wq[i];
-            wp[i] = cs * x - sn * y; wq[i] = sn * x + cs * y;
+          for (int i = sub; i < l; i += 16) {
+            const double x = xp[i], y = xq[i];
+            xp[i] = cs * x - sn * y; xq[i] = sn * x + cs * y;
             const double vx = vp[i], vy = vq[i];
             vp[i] = cs * vx - sn * vy; vq[i] = sn * vx + cs * vy;
           }
-          if (lane == 0) atomicAdd(cnt, 1);
+          if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; }
+          rotated = 1;
         }
       }
-      __syncthreads();
-      if (tid == 0 && h > 1) {
-        const int t_last = top[h - 1];
-        for (int i = h - 1; i >= 2; --i) top[i] = top[i - 1];
-        top[1] = bot[0];
-        for (int i = 0; i < h - 1; ++i) bot[i] = bot[i + 1];
-        bot[h - 1] = t_last;
-      }
-      __syncthreads();
+      any |= __syncthreads_or(rotated);
     }
-    const int rotations = *cnt;
-    __syncthreads();
-    if (rotations == 0) { converged = 1; ++sweeps; break; }
+    if (!any) { converged = 1; ++sweeps; break; }
   }
 
-  for (int j = warp; j < l; j += nw) {
+  // singular values, ranks (descending), outputs
+  for (int j = hw; j < l; j += nhw) {
     double a = 0.0;
-    for (int i = lane; i < l; i += 32) { const double x = Wc[j * lp + i]; a += x * x; }
+    for (int i = sub; i < l; i += 16) { const double x = Xc[j * lp + i]; a += x * x; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
-    if (lane == 0) sig[j] = sqrt(a);
+    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(hmask, a, o);
+    if (sub == 0) nrm[j] = sqrt(a);
   }
   __syncthreads();
   for (int j = tid; j < l; j += nt) {
-    const double sj = sig[j];
+    const double sj = nrm[j];
     int r = 0;
-    for (int i = 0; i < l; ++i) r += (sig[i] > sj || (sig[i] == sj && i < j)) ? 1 : 0;
+    for (int i = 0; i < l; ++i) r += (nrm[i] > sj || (nrm[i] == sj && i < j)) ? 1 : 0;
     rnk[j] = r;
     sigma_out[r] = sj;
   }
   __syncthreads();
+  // X = Win or Win^T;  X * Vacc = Ux * Sigma.   Win   = Ux S Vacc^T  (no transpose): Ur = Ux, Vr = Vacc
+  //                                              Win^T = Ux S Vacc^T  (transpose)  : Ur = Vacc, Vr = Ux
+  double* out_ux = transpose ? Vr_out : Ur_out;
+  double* out_va = transpose ? Ur_out : Vr_out;
   for (int idx = tid; idx < l * l; idx += nt) {
     const int j = idx / l, i = idx - j * l;
     const int r = rnk[j];
-    const double sj = sig[j];
-    Ur_out[(int64_t)i * ldo + r] = sj > 0.0 ? Wc[j * lp + i] / sj : 0.0;
-    Vr_out[(int64_t)i * ldo + r] = Vc[j * lp + i];
+    const double sj = nrm[j];
+    out_ux[(int64_t)i * ldo + r] = sj > 0.0 ? Xc[j * lp + i] / sj : 0.0;
+    out_va[(int64_t)i * ldo + r] = Vc[j * lp + i];
   }
   if (tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = converged; }
 }
@@ -346,7 +355,7 @@ cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld
 cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, int mode,
                             double global_rows, int* flag3, int* info, double* dinfo, int* deadmask, int* flag_dead,
                             const int* cond_flag, cudaStream_t s) {
-  const size_t smem = ((size_t)l * (l + 1) + 2 * (size_t)l + 2) * 8 + (size_t)l * 4;
+  const size_t smem = ((size_t)l * (l + 1) + 3 * (size_t)l + 2) * 8 + (size_t)l * 4;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
@@ -368,10 +377,10 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 }
 
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
-                              int ldo, double* scratch, int* info, cudaStream_t s) {
-  const int lp = l | 1, h = (l + 1) / 2;
+                              int ldo, double* scratch, int* info, cudaStream_t s, int transpose) {
+  const int lp = l | 1;
   const size_t mat = (size_t)l * lp * 8;
-  const size_t small = (size_t)l * 8 + (size_t)(2 * h + l + 2) * 4 + 16;
+  const size_t small = (size_t)l * 8 + (size_t)(l + 2) * 4 + 16;
   const size_t cap = 227 * 1024;
   int w_smem = 0, v_smem = 0;
   if (2 * mat + small <= cap) { w_smem = 1; v_smem = 1; }
@@ -383,7 +392,7 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  jacobi_svd_kernel<<<1, 1024, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, info);
+  jacobi_svd_kernel<<<1, 1024, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, transpose, info);
   return cudaGetLastError();
 }
 

@@ -35,7 +35,7 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 // operand).  scratch: 2*l*(l|1) doubles of global memory, used when the matrices do not fit in shared memory.
 // Replaces faer's svd() at random_svd.rs:89 (after the QR preconditioning done by the caller).
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
-                              int ldo, double* scratch, int* info, cudaStream_t s);
+                              int ldo, double* scratch, int* info, cudaStream_t s, int transpose = 1);
 
 // dst[i*ldd + j] = scale * src[i*rs + j*cs] for i < rows, j < cols (any strides, device pointers).
 cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double* dst,

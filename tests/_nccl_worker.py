@@ -1,0 +1,82 @@
+"""Worker for tests/test_gpu_multi.py: one rank (one GPU) of a row-sharded rsvd over NCCL, checked against the oracle."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import corrla_rs_b200 as cb  # noqa: E402
+from oracle import ref_rsvd  # noqa: E402
+
+
+def main():
+    out_dir = Path(sys.argv[1])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    comm = cb.ShardComm(device=local)
+    results = {}
+    cases = {"gauss_rowmajor": (20011, 512, 30, 5, 10, "C"), "lowrank_colmajor": (16384, 300, 20, 4, 10, "F"),
+             "tiny_rank_deficient": (64, 16, 8, 12, 8, "C")}
+    for name, (m, n, k, q, p, order) in cases.items():
+        rng = np.random.default_rng(77)
+        if name.startswith("lowrank"):
+            u0, _ = np.linalg.qr(rng.standard_normal((m, 40)))
+            v0, _ = np.linalg.qr(rng.standard_normal((n, 40)))
+            a = (u0 * (10.0 * 0.95 ** np.arange(40))) @ v0.T + 1e-2 * rng.standard_normal((m, n))
+        elif name.startswith("tiny"):
+            a = rng.standard_normal((m, 5)) @ rng.standard_normal((5, n))          # rank 5 < l = 16
+        else:
+            a = rng.standard_normal((m, n))
+        l = min(k + p, n)
+        omega = rng.standard_normal((n, l))
+        per = (m + world - 1) // world
+        r0, r1 = rank * per, min(m, (rank + 1) * per)
+        shard = np.asfortranarray(a[r0:r1]) if order == "F" else np.ascontiguousarray(a[r0:r1])
+        # host path and device path
+        u_loc, s, vt = cb.rsvd(shard, k, q, p, omega=omega, comm=comm, global_rows=m)
+        ud, sd, vd = cb.rsvd(torch.from_numpy(shard).cuda(), k, q, p, omega=torch.from_numpy(omega).cuda(), comm=comm)
+        torch.cuda.synchronize()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (r0, r1, np.asarray(u_loc), ud.cpu().numpy()))
+        if rank == 0:
+            u = np.zeros((m, k)); u2 = np.zeros((m, k))
+            for g0, g1, blk, blk2 in gathered:
+                u[g0:g1] = blk; u2[g0:g1] = blk2
+            uo, so, vo = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+            nz = so.ravel() > 1e-9 * so.ravel()[0]
+            kk = int(nz.sum())
+            results[name] = {
+                "sigma_rel": float(np.max(np.abs(so.ravel()[:kk] - s.ravel()[:kk]) / so.ravel()[:kk])),
+                "sigma_tail_abs": float(np.max(np.abs(s.ravel()[kk:])) if kk < k else 0.0),
+                "sin_u": ref_rsvd.subspace_sine(uo[:, :kk], u[:, :kk]), "sin_v": ref_rsvd.subspace_sine(vo[:kk].T, vt[:kk].T),
+                "orth_u": float(np.max(np.abs(u.T @ u - np.eye(k)))),
+                "device_vs_host_sigma": float(np.max(np.abs(sd.cpu().numpy() - s))),
+                "device_vs_host_u": float(np.max(np.abs(u2 - u))), "k_checked": kk}
+    # thin_q sharded
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((9000, 48))
+    per = (9000 + world - 1) // world
+    r0, r1 = rank * per, min(9000, (rank + 1) * per)
+    q_loc = cb.thin_q(a[r0:r1].copy(), comm=comm, global_rows=9000)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (r0, r1, np.asarray(q_loc)))
+    if rank == 0:
+        qf = np.zeros((9000, 48))
+        for g0, g1, blk in gathered:
+            qf[g0:g1] = blk
+        results["thin_q"] = {"orth": float(np.max(np.abs(qf.T @ qf - np.eye(48)))),
+                             "span": float(np.linalg.norm(a - qf @ (qf.T @ a)) / np.linalg.norm(a))}
+        (out_dir / "result.json").write_text(json.dumps(results))
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

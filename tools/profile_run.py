@@ -17,4 +17,4 @@ for i in range(2):
     u, s, vt = cb.rsvd(a, k, q, p, seed=3)
     torch.cuda.synchronize()
     t = cb.last_timings()
-    print(i, "device_ms", t["device_ms"], "pass_ms", t["pass_ms"], "launches", t["gpu_launches"], "sigma0", float(s[0, 0]))
+    print(i, "device_ms", t["device_ms"], "pass_ms", t["pass_ms"], "launches", t["gpu_launches"], "sweeps", t["jacobi_sweeps"], "sigma0", float(s[0, 0]))
