@@ -36,72 +36,20 @@ __device__ __forceinline__ void consumer_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-template <bool KC, int WM, int WN, int MI, int JW>
-__global__ void __launch_bounds__((WM * WN + 1) * 32, 1)
-skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
-  static_assert(WM * MI * 8 == kTileM, "tile rows");
-  static_assert(MI % 2 == 0, "MI even (box parity)");
+// Register budget: 12 warps are launched (two consumer warpgroups + one producer warpgroup); the producer group gives
+// its registers back (setmaxnreg.dec) and the consumers grow to 232, which holds 112 accumulator registers plus two
+// sets of fragments without spilling.
+constexpr int kConsumerRegs = 232;
+constexpr int kProducerRegs = 40;
+constexpr int kThreads = 12 * 32;
+
+// One consumer warp, all work items of this CTA.  FULL: every n-block of the warp is valid (no predicates on the DMMAs).
+template <bool KC, int WM, int WN, int MI, int JW, bool FULL>
+__device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* smem, unsigned char* smemB, uint32_t sBar,
+                                              double* red, int warp, int lane, int jn) {
   constexpr int NCW = WM * WN;
-
-  if (p.cond_flag != nullptr && *p.cond_flag == 0) return;
-
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw_u32 = smem_u32(smem_raw);
-  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
-  unsigned char* smem = smem_raw + pad;
-  const uint32_t sA = raw_u32 + pad;
-  const uint32_t sB = sA + p.stages * kAStageBytes;
-  const uint32_t sBar = sB + p.stages * p.b_stage_bytes;     // full[stages], empty[stages]
-  unsigned char* smemB = smem + p.stages * kAStageBytes;
-  double* red = reinterpret_cast<double*>(smemB + p.stages * p.b_stage_bytes + 2 * 8 * 8);  // after 16 barriers
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(sBar + 8 * s, 1);
-      mbar_init(sBar + 8 * (8 + s), NCW);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const int W = p.tilesM * p.splits;
-  uint32_t stage = 0, phase = 0;
-
-  if (warp == NCW) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane != 0) return;
-    tma_prefetch_desc(&tmA);
-    const uint32_t tx = kAStageBytes + p.b_stage_bytes;
-    for (int w = blockIdx.x; w < W; w += gridDim.x) {
-      const int split = w / p.tilesM, tile = w - split * p.tilesM;
-      const int64_t c0 = (int64_t)split * p.chunks_per_split;
-      const int64_t c1 = min(c0 + p.chunks_per_split, p.chunks_total);
-      const int m0 = tile * kTileM;
-      for (int64_t c = c0; c < c1; ++c) {
-        mbar_wait(sBar + 8 * (8 + stage), phase ^ 1u);
-        const uint32_t full = sBar + 8 * stage;
-        mbar_arrive_expect_tx(full, tx);
-        const int k0 = (int)(c * kChunkK);
-        const uint32_t dstA = sA + stage * kAStageBytes;
-        if (KC) {
-          tma_load_2d(dstA, &tmA, k0, m0, full);
-        } else {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
-        }
-        bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
-        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
-      }
-    }
-    return;
-  }
-
-  // ------------------------------ DMMA consumers ------------------------------
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp % WM, wn = warp / WM;
-  const int jn = min(JW, p.nblk - wn * JW);   // valid n-blocks of this warp (may be <= 0)
 
   // A-fragment byte offsets inside a stage
   int a_base;          // KC: row part for i = 0;   MC: box part for i = 0
@@ -132,7 +80,21 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
   double alpha = 1.0;
   if (p.alpha_sumsq != nullptr) alpha = rsqrt(*p.alpha_sumsq);
 
+  auto load_frags = [&](double (&af)[MI], double (&bf)[JW], const unsigned char* a, const unsigned char* b, int s) {
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int off = KC ? (i * 1024 + a_xo[0][s]) : ((i >> 1) * 2048 + a_xo[i & 1][s]);
+      af[i] = *reinterpret_cast<const double*>(a + off);
+    }
+#pragma unroll
+    for (int j = 0; j < JW; ++j)
+      if (FULL || j < jn) bf[j] = *reinterpret_cast<const double*>(b + s * b_step + j * 64);
+  };
+
+  const int W = p.tilesM * p.splits;
+  uint32_t stage = 0, phase = 0;
   double acc[MI][JW][2];
+  double af[2][MI], bf[2][JW];
 
   for (int w = blockIdx.x; w < W; w += gridDim.x) {
     const int split = w / p.tilesM, tile = w - split * p.tilesM;
@@ -143,30 +105,33 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
 #pragma unroll
       for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    for (int64_t c = c0; c < c1; ++c) {
+    if (c0 < c1) {
       mbar_wait(sBar + 8 * stage, phase);
+      load_frags(af[0], bf[0], smem + stage * kAStageBytes + a_base, smemB + stage * p.b_stage_bytes + b_off, 0);
+    }
+    for (int64_t c = c0; c < c1; ++c) {
       const unsigned char* a = smem + stage * kAStageBytes + a_base;
       const unsigned char* b = smemB + stage * p.b_stage_bytes + b_off;
+      uint32_t nstage = stage + 1, nphase = phase;
+      if (nstage == (uint32_t)p.stages) { nstage = 0; nphase ^= 1u; }
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        double af[MI], bf[JW];
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          const int off = KC ? (i * 1024 + a_xo[0][s]) : ((i >> 1) * 2048 + a_xo[i & 1][s]);
-          af[i] = *reinterpret_cast<const double*>(a + off);
+        if (s < 3) {
+          load_frags(af[(s + 1) & 1], bf[(s + 1) & 1], a, b, s + 1);
+        } else if (c + 1 < c1) {
+          // fragments of the next chunk's first step are fetched before this chunk's last DMMAs are issued
+          mbar_wait(sBar + 8 * nstage, nphase);
+          load_frags(af[0], bf[0], smem + nstage * kAStageBytes + a_base, smemB + nstage * p.b_stage_bytes + b_off, 0);
         }
-#pragma unroll
-        for (int j = 0; j < JW; ++j)
-          if (j < jn) bf[j] = *reinterpret_cast<const double*>(b + s * b_step + j * 64);
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < JW; ++j)
-            if (j < jn) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            if (FULL || j < jn) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[s & 1][i], bf[s & 1][j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sBar + 8 * (8 + stage));
-      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      stage = nstage; phase = nphase;
     }
 
     // ------------------------------ epilogue ------------------------------
@@ -179,7 +144,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
         const int tr = KC ? ((wm * MI + i) * 8 + rowperm(g)) : (16 * ((wm * MI + i) >> 1) + colperm(g, i & 1));
 #pragma unroll
         for (int j = 0; j < JW; ++j)
-          if (j < jn) {
+          if (FULL || j < jn) {
             const int col = 8 * (wn * JW + j) + 2 * t;
             *reinterpret_cast<double2*>(wsp + (int64_t)tr * Lc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
           }
@@ -192,7 +157,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
         if (row < p.Mside) {
 #pragma unroll
           for (int j = 0; j < JW; ++j)
-            if (j < jn) {
+            if (FULL || j < jn) {
               const int col = 8 * (wn * JW + j) + 2 * t;
               const double v0 = acc[i][j][0] * alpha, v1 = acc[i][j][1] * alpha;
               ss += v0 * v0 + v1 * v1;
@@ -220,6 +185,76 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
       }
     }
   }
+}
+
+template <bool KC, int WM, int WN, int MI, int JW>
+__global__ void __launch_bounds__(kThreads, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
+  static_assert(WM * MI * 8 == kTileM, "tile rows");
+  static_assert(MI % 2 == 0, "MI even (box parity)");
+  static_assert(WM * WN == 8, "two consumer warpgroups");
+  constexpr int NCW = WM * WN;
+
+  if (p.cond_flag != nullptr && *p.cond_flag == 0) return;
+
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  unsigned char* smem = smem_raw + pad;
+  const uint32_t sA = raw_u32 + pad;
+  const uint32_t sB = sA + p.stages * kAStageBytes;
+  const uint32_t sBar = sB + p.stages * p.b_stage_bytes;     // full[stages], empty[stages]
+  unsigned char* smemB = smem + p.stages * kAStageBytes;
+  double* red = reinterpret_cast<double*>(smemB + p.stages * p.b_stage_bytes + 2 * 8 * 8);  // after 16 barriers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(sBar + 8 * s, 1);
+      mbar_init(sBar + 8 * (8 + s), NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp >= NCW) {
+    // ------------------------------ TMA producer warpgroup ------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+    if (warp != NCW || lane != 0) return;
+    tma_prefetch_desc(&tmA);
+    const int W = p.tilesM * p.splits;
+    uint32_t stage = 0, phase = 0;
+    const uint32_t tx = kAStageBytes + p.b_stage_bytes;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+      const int split = w / p.tilesM, tile = w - split * p.tilesM;
+      const int64_t c0 = (int64_t)split * p.chunks_per_split;
+      const int64_t c1 = min(c0 + p.chunks_per_split, p.chunks_total);
+      const int m0 = tile * kTileM;
+      for (int64_t c = c0; c < c1; ++c) {
+        mbar_wait(sBar + 8 * (8 + stage), phase ^ 1u);
+        const uint32_t full = sBar + 8 * stage;
+        mbar_arrive_expect_tx(full, tx);
+        const int k0 = (int)(c * kChunkK);
+        const uint32_t dstA = sA + stage * kAStageBytes;
+        if (KC) {
+          tma_load_2d(dstA, &tmA, k0, m0, full);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
+        }
+        bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ DMMA consumer warpgroups ------------------------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+  const int jn = min(JW, p.nblk - (warp / WM) * JW);   // valid n-blocks of this warp (may be <= 0)
+  if (jn == JW) consumer_loop<KC, WM, WN, MI, JW, true>(p, smem, smemB, sBar, red, warp, lane, jn);
+  else consumer_loop<KC, WM, WN, MI, JW, false>(p, smem, smemB, sBar, red, warp, lane, jn);
 }
 
 // out(r, c) = alpha * sum_s ws[s][tile(r)][r % 128][c]; one thread per column pair.
@@ -323,7 +358,7 @@ typedef void (*KernelFn)(const CUtensorMap, const GemmArgs);
 
 template <bool KC>
 KernelFn pick_kernel(int nblk, int* threads) {
-  *threads = 9 * 32;
+  *threads = kThreads;
   switch (nblk) {
     case 1: return skinny_gemm_kernel<KC, 8, 1, 2, 1>;
     case 2: return skinny_gemm_kernel<KC, 8, 1, 2, 2>;

@@ -40,8 +40,8 @@ def main():
         r0, r1 = rank * per, min(m, (rank + 1) * per)
         shard = np.asfortranarray(a[r0:r1]) if order == "F" else np.ascontiguousarray(a[r0:r1])
         # host path and device path
-        u_loc, s, vt = cb.rsvd(shard, k, q, p, omega=omega, comm=comm, global_rows=m)
-        ud, sd, vd = cb.rsvd(torch.from_numpy(shard).cuda(), k, q, p, omega=torch.from_numpy(omega).cuda(), comm=comm)
+        u_loc, s, vt = cb.rsvd(shard, k, q, p, omega=omega, comm=comm, global_rows=m, seed=9)
+        ud, sd, vd = cb.rsvd(torch.from_numpy(shard).cuda(), k, q, p, omega=torch.from_numpy(omega).cuda(), comm=comm, seed=9)
         torch.cuda.synchronize()
         gathered = [None] * world
         dist.all_gather_object(gathered, (r0, r1, np.asarray(u_loc), ud.cpu().numpy()))
