@@ -8,8 +8,6 @@ namespace corrla {
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
-
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) + Box-Muller
 // ------------------------------------------------------------------------------------------------
@@ -55,128 +53,154 @@ philox_normal_kernel(double* __restrict__ out, int64_t rows, int cols, int64_t l
 constexpr double kTolDeadPerCol = 8.0 * DBL_EPSILON;  // times l
 constexpr double kTauShift = 1e-10;
 
-// Factor S (upper triangle, pitch lp) in place; the diagonal of R goes to diag[] (S[j][j] keeps the pivot), so no
-// thread overwrites what another still reads and a step needs two barriers.  Smallest pivot ratio -> *minratio_s.
-// dead[j] = 1 where the pivot vanished; that row of R is zero.
-__device__ void chol_factor(double* S, int lp, int l, const double* d0, double* diag, int* dead, bool shifted,
-                            double tol_dead, double* minratio_s) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
-  if (tid == 0) *minratio_s = DBL_MAX;
-  __syncthreads();
+// One CTA of 16x32 threads; thread (ty, tx) keeps the entries (i, k), i = ty + 16a (a < 8), k = tx + 32b (b < 4), so
+// l <= 128, of ONE packed matrix M in registers: for k >= i it is the working copy of G that becomes R (right-looking
+// Cholesky G = R^T R), for k < i it is W = L^-1 (L = R^T), obtained by running the same elimination on an identity
+// matrix.  T = R^-1 = W^T therefore falls out of the factorisation; there is no separate triangular inversion.
+// Only pivot row j travels through shared memory (double buffered: one barrier per step).
+// Deflation: a pivot under tol_dead * (original diagonal) marks column j dead: row j of R is zero, no update is made,
+// and column j of T is zeroed on output, so Q = Y*T has an exact zero column there.
+struct CholState {
+  double m[8][4];
+  double minratio;
+};
+
+__device__ __forceinline__ void chol_load(CholState& st, const double* __restrict__ G, int ldg, int l, double shift,
+                                          int ty, int tx) {
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, k = tx + 32 * b;
+      double g = (i < l && k < l && k >= i) ? G[(int64_t)i * ldg + k] : 0.0;     // strictly-lower part: W starts at 0
+      if (i == k && g > 0.0) g += shift;
+      st.m[a][b] = g;
+    }
+  st.minratio = DBL_MAX;
+}
+
+__device__ __forceinline__ void chol_eliminate(CholState& st, int l, const double* d0, double (*rowbuf)[128],
+                                               double* tdiag, int* dead_s, bool shifted, double tol_dead, int ty,
+                                               int tx) {
   for (int j = 0; j < l; ++j) {
-    const double piv = S[j * lp + j];
-    const double dj = d0[j];
+    const int buf = j & 1;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      if (ty + 16 * a == j) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) rowbuf[buf][tx + 32 * b] = st.m[a][b];
+      }
+    __syncthreads();
+    const double piv = rowbuf[buf][j], dj = d0[j];
     bool is_dead;
     if (shifted) is_dead = !(dj > 0.0) || !(piv > 0.0);
     else is_dead = !(dj > 0.0) || !(piv > tol_dead * dj);
-    if (tid == 0) {
-      const double ratio = (dj > 0.0 && piv > 0.0) ? piv / dj : 0.0;
-      if (ratio < *minratio_s) *minratio_s = ratio;
-      dead[j] = is_dead ? 1 : 0;
-      diag[j] = is_dead ? 0.0 : sqrt(piv);
+    const double ratio = (dj > 0.0 && piv > 0.0) ? piv / dj : 0.0;
+    if (ratio < st.minratio) st.minratio = ratio;
+    if (ty == 0 && tx == 0) dead_s[j] = is_dead ? 1 : 0;
+    if (is_dead) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (ty + 16 * a == j) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) if (tx + 32 * b >= j) st.m[a][b] = 0.0;
+        }
+      if (ty == 0 && tx == 0) tdiag[j] = 0.0;
+      continue;
     }
-    if (!is_dead) {
-      const double inv = 1.0 / sqrt(piv);
-      for (int k = j + 1 + tid; k < l; k += nt) S[j * lp + k] *= inv;
-    } else {
-      for (int k = j + 1 + tid; k < l; k += nt) S[j * lp + k] = 0.0;
+    const double inv = rsqrt(piv);
+    if (ty == 0 && tx == 0) tdiag[j] = inv;
+    if (ty + 112 < j) continue;                         // every row this warp owns is already finished
+    double ck[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int k = tx + 32 * b;
+      ck[b] = (k == j) ? inv : rowbuf[buf][k] * inv;   // k > j: r_jk;  k < j: W[j][k] * inv;  k == j: W[j][j] * inv
     }
-    __syncthreads();
-    if (!is_dead) {
-      const double* rj = S + j * lp;
-      for (int i = j + 1 + ty; i < l; i += nty) {
-        const double ri = rj[i];
-        double* si = S + i * lp;
-        for (int k = (i & ~31) + tx; k < l; k += 32)
-          if (k >= i) si[k] -= ri * rj[k];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int i = ty + 16 * a;
+      if (i > j) {
+        const double ri = rowbuf[buf][i] * inv;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int k = tx + 32 * b;
+          if (k >= i || k <= j) st.m[a][b] -= ri * ck[b];
+        }
+      } else if (i == j) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int k = tx + 32 * b;
+          st.m[a][b] = (k == j) ? piv * inv : ck[b];   // R[j][j] = sqrt(piv); R[j][k>j]; scaled W[j][k<j]
+        }
       }
     }
-    __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 1)
 chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict__ T, int Lrows, int ldt, int mode,
                 double global_rows, int* flag3, int* info, double* dinfo, int* deadmask, int* flag_dead,
                 const int* cond_flag) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
   extern __shared__ double sm[];
+  __shared__ double rowbuf[2][128], d0[128], tdiag[128];
+  __shared__ int dead_s[128];
+  __shared__ double trace_s;
   const int lp = l + 1;
-  double* S = sm;                 // l x lp
-  double* d0 = S + l * lp;        // l
-  double* v = d0 + l;             // l
-  double* diag = v + l;           // l: diagonal of R
-  double* scal = diag + l;        // [0] minratio, [1] trace
-  int* dead = reinterpret_cast<int*>(scal + 2);
-  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  double* Wsm = sm;               // l x lp staging of the packed matrix for the transposed write
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 31, ty = tid >> 5;
   const double tol_dead = kTolDeadPerCol * l;
 
-  for (int idx = tid; idx < l * l; idx += nt) {
-    const int i = idx / l, j = idx - i * l;
-    S[i * lp + j] = G[(int64_t)i * ldg + j];
-  }
-  for (int j = tid; j < l; j += nt) d0[j] = G[(int64_t)j * ldg + j];
+  for (int j = tid; j < 128; j += nt) d0[j] = (j < l) ? G[(int64_t)j * ldg + j] : 0.0;
   __syncthreads();
   if (tid == 0) {
     double tr = 0.0;
     for (int j = 0; j < l; ++j) tr += d0[j] > 0.0 ? d0[j] : 0.0;
-    scal[1] = tr;
+    trace_s = tr;
   }
+  CholState st;
+  chol_load(st, G, ldg, l, 0.0, ty, tx);
   __syncthreads();
-
-  chol_factor(S, lp, l, d0, diag, dead, false, tol_dead, &scal[0]);
+  chol_eliminate(st, l, d0, rowbuf, tdiag, dead_s, false, tol_dead, ty, tx);
   int shifted = 0;
   if (mode == kCholAuto) {
-    const double mr = scal[0];
-    __syncthreads();
-    if (mr < kTauShift) {
+    if (st.minratio < kTauShift) {      // uniform: every thread tracked the same pivots
       // shifted CholeskyQR: G + s I with s = 11 (m l + l (l+1)) u ||Y||_2^2, ||Y||_2^2 <= trace(G)
-      const double shift = 11.0 * (global_rows * l + (double)l * (l + 1)) * (0.5 * DBL_EPSILON) * scal[1];
-      for (int idx = tid; idx < l * l; idx += nt) {
-        const int i = idx / l, j = idx - i * l;
-        double g = G[(int64_t)i * ldg + j];
-        if (i == j && g > 0.0) g += shift;
-        S[i * lp + j] = g;
-      }
+      const double shift = 11.0 * (global_rows * l + (double)l * (l + 1)) * (0.5 * DBL_EPSILON) * trace_s;
       __syncthreads();
-      chol_factor(S, lp, l, d0, diag, dead, true, tol_dead, &scal[0]);
+      chol_load(st, G, ldg, l, shift, ty, tx);
+      chol_eliminate(st, l, d0, rowbuf, tdiag, dead_s, true, tol_dead, ty, tx);
       shifted = 1;
     }
     if (tid == 0 && flag3 != nullptr) *flag3 = shifted;
   }
-
-  // In-place inverse of the upper-triangular factor (dead diagonal entries act as 1), column by column:
-  // T[0:j, j] = -T[0:j,0:j] * R[0:j, j] * T[j][j]
-  for (int j = 0; j < l; ++j) {
-    const double tjj = dead[j] ? 1.0 : 1.0 / diag[j];
-    for (int k = tid; k < j; k += nt) v[k] = S[k * lp + j];
-    __syncthreads();
-    for (int i = warp; i < j; i += nw) {
-      double dot = 0.0;
-      for (int k = i + lane; k < j; k += 32) dot += S[i * lp + k] * v[k];
+  __syncthreads();
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(kFull, dot, o);
-      if (lane == 0) S[i * lp + j] = -dot * tjj;
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, k = tx + 32 * b;
+      if (i < l && k < l) Wsm[i * lp + k] = st.m[a][b];
     }
-    if (tid == 0) S[j * lp + j] = tjj;
-    __syncthreads();
-  }
+  __syncthreads();
   for (int idx = tid; idx < Lrows * ldt; idx += nt) {
-    const int i = idx / ldt, c = idx - i * ldt;
+    const int r = idx / ldt, c = idx - r * ldt;
     double val = 0.0;
-    if (i < l && c < l && c >= i && !dead[c]) val = S[i * lp + c];
+    if (r < l && c < l && c >= r && !dead_s[c])
+      val = (c == r) ? tdiag[c] : Wsm[c * lp + r];     // T = W^T, W = L^-1
     T[idx] = val;
   }
   if (tid == 0) {
     int live = 0;
-    for (int j = 0; j < l; ++j) live += dead[j] ? 0 : 1;
+    for (int j = 0; j < l; ++j) live += dead_s[j] ? 0 : 1;
     if (info != nullptr) { info[0] = live; info[1] = shifted; }
-    if (dinfo != nullptr) dinfo[0] = scal[0];
+    if (dinfo != nullptr) dinfo[0] = st.minratio;
     if (flag_dead != nullptr) *flag_dead = (live < l) ? 1 : 0;
   }
   if (deadmask != nullptr)
-    for (int j = tid; j < l; j += nt) deadmask[j] = dead[j];
+    for (int j = tid; j < l; j += nt) deadmask[j] = dead_s[j];
 }
 
 __global__ void __launch_bounds__(256)
@@ -207,8 +231,10 @@ refill_dead_kernel(double* __restrict__ X, int64_t rows, int l, int64_t ld, cons
 // Drmac & Veselic the rotations are applied to its transpose, which converges in fewer sweeps.
 // ------------------------------------------------------------------------------------------------
 constexpr int kJacobiMaxSweeps = 60;
+constexpr int kJacobiLanes = 8;          // lanes per column pair (a quarter warp)
+constexpr int kJacobiThreads = 512;      // 64 quarter warps >= 64 pairs (l <= 128); larger l loops
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kJacobiThreads)
 jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                   double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, double* gscratch,
                   int w_smem, int v_smem, int transpose, int* info) {
@@ -221,34 +247,56 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
   double* nrm = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);      // squared column norms
   int* rnk = reinterpret_cast<int*>(nrm + l);
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int hw = tid >> 4, sub = tid & 15, nhw = nt >> 4;
-  const unsigned hmask = 0xffffu << (tid & 16);
+  constexpr int LP = kJacobiLanes;
+  const int grp = tid / LP, sub = tid % LP, ngrp = nt / LP;
+  const unsigned gmask = ((1u << LP) - 1u) << ((tid & 31) & ~(LP - 1));
+  const int glead = (tid & 31) & ~(LP - 1);
 
-  for (int idx = tid; idx < l * l; idx += nt) {
-    const int i = idx / l, j = idx - i * l;
-    const double w = Win[(int64_t)i * ldw + j];
-    if (transpose) Xc[i * lp + j] = w; else Xc[j * lp + i] = w;
-    Vc[j * lp + i] = (i == j) ? 1.0 : 0.0;
+  // squared norms of the columns of X (= rows of Win when transposed), then their descending rank: the columns are
+  // laid out sorted by norm, which shortens the sweep count (de Rijk ordering)
+  for (int j = grp; j < l; j += ngrp) {
+    double a = 0.0;
+    for (int i = sub; i < l; i += LP) {
+      const double x = transpose ? Win[(int64_t)j * ldw + i] : Win[(int64_t)i * ldw + j];
+      a += x * x;
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
+    if (sub == 0) nrm[j] = a;
   }
   for (int idx = tid; idx < Lrows * ldo; idx += nt) { Vr_out[idx] = 0.0; Ur_out[idx] = 0.0; }
   __syncthreads();
+  for (int j = tid; j < l; j += nt) {
+    const double sj = nrm[j];
+    int r = 0;
+    for (int i = 0; i < l; ++i) r += (nrm[i] > sj || (nrm[i] == sj && i < j)) ? 1 : 0;
+    rnk[j] = r;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < l * l; idx += nt) {
+    const int j = idx / l, i = idx - j * l;                      // source column j, row i
+    const int c = rnk[j];
+    Xc[c * lp + i] = transpose ? Win[(int64_t)j * ldw + i] : Win[(int64_t)i * ldw + j];
+    Vc[c * lp + i] = (i == j) ? 1.0 : 0.0;                       // V starts as the permutation
+  }
+  __syncthreads();
 
   const double tol = sqrt((double)l) * DBL_EPSILON;
+  const double tol2 = tol * tol;
   int sweeps = 0, converged = 0;
   for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
-    // exact norms
-    for (int j = hw; j < l; j += nhw) {
+    for (int j = grp; j < l; j += ngrp) {                         // exact norms once per sweep
       double a = 0.0;
-      for (int i = sub; i < l; i += 16) { const double x = Xc[j * lp + i]; a += x * x; }
+      for (int i = sub; i < l; i += LP) { const double x = Xc[j * lp + i]; a += x * x; }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(hmask, a, o);
+      for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
       if (sub == 0) nrm[j] = a;
     }
     __syncthreads();
     int any = 0;
     for (int r = 0; r < N1; ++r) {
       int rotated = 0;
-      for (int pi = hw; pi < h; pi += nhw) {
+      for (int pi = grp; pi < h; pi += ngrp) {
         int p, q;
         if (pi == 0) { p = N1; q = r; }
         else { p = r + pi; if (p >= N1) p -= N1; q = r - pi; if (q < 0) q += N1; }
@@ -256,17 +304,20 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
         if (q >= l) continue;                                     // bye
         double* xp = Xc + p * lp; double* xq = Xc + q * lp;
         double c = 0.0;
-        for (int i = sub; i < l; i += 16) c += xp[i] * xq[i];
+#pragma unroll 4
+        for (int i = sub; i < l; i += LP) c += xp[i] * xq[i];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(hmask, c, o);
-        c = __shfl_sync(hmask, c, tid & 16);                      // identical bits in all 16 lanes
+        for (int o = LP / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
+        c = __shfl_sync(gmask, c, glead);                         // identical bits in all lanes of the group
         const double a = nrm[p], b = nrm[q];
-        if (c != 0.0 && fabs(c) > tol * sqrt(a) * sqrt(b)) {
-          const double zeta = (b - a) / (2.0 * c);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        if (c * c > tol2 * a * b) {
+          // t = sign(d) * 2c / (|d| + sqrt(d^2 + 4c^2)), d = b - a  (== sign(zeta)/(|zeta| + sqrt(1 + zeta^2)))
+          const double d = b - a;
+          const double t = copysign(2.0 * c, d * c) / (fabs(d) + sqrt(d * d + 4.0 * c * c));
+          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
           double* vp = Vc + p * lp; double* vq = Vc + q * lp;
-          for (int i = sub; i < l; i += 16) {
+#pragma unroll 4
+          for (int i = sub; i < l; i += LP) {
             const double x = xp[i], y = xq[i];
             xp[i] = cs * x - sn * y; xq[i] = sn * x + cs * y;
             const double vx = vp[i], vy = vq[i];
@@ -282,11 +333,11 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
   }
 
   // singular values, ranks (descending), outputs
-  for (int j = hw; j < l; j += nhw) {
+  for (int j = grp; j < l; j += ngrp) {
     double a = 0.0;
-    for (int i = sub; i < l; i += 16) { const double x = Xc[j * lp + i]; a += x * x; }
+    for (int i = sub; i < l; i += LP) { const double x = Xc[j * lp + i]; a += x * x; }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(hmask, a, o);
+    for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
     if (sub == 0) nrm[j] = sqrt(a);
   }
   __syncthreads();
@@ -355,8 +406,8 @@ cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld
 cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, int mode,
                             double global_rows, int* flag3, int* info, double* dinfo, int* deadmask, int* flag_dead,
                             const int* cond_flag, cudaStream_t s) {
-  const size_t smem = ((size_t)l * (l + 1) + 3 * (size_t)l + 2) * 8 + (size_t)l * 4;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (l > 128) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)l * (l + 1) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -392,7 +443,7 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  jacobi_svd_kernel<<<1, 1024, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, transpose, info);
+  jacobi_svd_kernel<<<1, kJacobiThreads, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, transpose, info);
   return cudaGetLastError();
 }
 
