@@ -21,7 +21,7 @@ import numpy as np
 from . import _ffi
 from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 
-__all__ = ["rsvd", "random_svd", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
+__all__ = ["rsvd", "random_svd", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
            "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings"]
 
 _SCHEDULES = {"reference": 0, "stabilised": 1, "stabilized": 1, 0: 0, 1: 1}
@@ -158,7 +158,8 @@ class _Mat:
         self.device = None
 
 
-def _make_opts(*, ctx, on_device, out_on_device, omega, seed, schedule, comm, global_rows, stream, device):
+def _make_opts(*, ctx, on_device, out_on_device, omega, seed, schedule, comm, global_rows, stream, device,
+               center=False):
     lib = _ffi.load()
     o = _ffi.RsvdOpts()
     lib.corrla_rsvd_opts_default(C.byref(o))
@@ -182,6 +183,7 @@ def _make_opts(*, ctx, on_device, out_on_device, omega, seed, schedule, comm, gl
         o.global_rows = int(global_rows or 0)
     if stream is not None:
         o.stream = int(stream)
+    o.center = 1 if center else 0
     return o, keep
 
 
@@ -207,7 +209,7 @@ def _ptr(x):
 # --------------------------------------------------------------------------------------------
 def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, seed: int | None = None,
          schedule="reference", ctx: Context | None = None, comm: ShardComm | None = None,
-         global_rows: int | None = None):
+         global_rows: int | None = None, center: bool = False):
     """Randomized SVD, drop-in for `corrla_rs.rsvd(a_mat, n_rank, n_iters, n_oversamples)`
     (src/lib_math_utils_py.rs:21-36 -> random_svd, src/lib_math_utils/random_svd.rs:63-110).
 
@@ -215,7 +217,8 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
     Keyword extras (not in the reference): `omega` injects the Gaussian test matrix (ncols_thin x l),
     `seed` makes the on-device Philox generator reproducible (the reference is unseeded),
     `schedule="stabilised"` re-orthonormalises in every power iteration, `comm` runs row-sharded over
-    several GPUs (a_mat is then this rank's rows of the thin matrix)."""
+    several GPUs (a_mat is then this rank's rows of the thin matrix), `center=True` decomposes a_mat minus its
+    column means (center_mat_col, mat_utils.rs:482-502) without forming the centred copy when a_mat is tall."""
     for name, v in (("n_rank", n_rank), ("n_iters", n_iters), ("n_oversamples", n_oversamples)):
         if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
             raise TypeError(f"{name} must be an int")
@@ -228,7 +231,8 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
     ctx = ctx or _context_for(device)
     stream = _current_stream(device) if a.on_device else None
     o, keep = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=omega, seed=seed,
-                         schedule=schedule, comm=comm, global_rows=global_rows, stream=stream, device=device)
+                         schedule=schedule, comm=comm, global_rows=global_rows, stream=stream, device=device,
+                         center=center)
     k = int(n_rank)
     u = _colmajor_empty_like(a, nrows, max(k, 1))
     vt = _colmajor_empty_like(a, max(k, 1), ncols)
@@ -243,6 +247,35 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
 
 
 random_svd = rsvd
+
+
+def rpca(a_mat, n_rank: int, n_iters: int = 0, n_oversamples: int = 0, *, omega=None, seed: int | None = None,
+         ctx: Context | None = None, comm: ShardComm | None = None, global_rows: int | None = None,
+         return_means: bool = False):
+    """PCA by RSVD, drop-in for `corrla_rs.rpca(a_mat, n_rank, n_iters, n_oversamples)` (lib_math_utils_py.rs:38-55 ->
+    PcaRsvd::new, pca_rsvd.rs:56-82).  Returns (singular_vals (n_rank, 1), components (n_rank, n_dim)).
+    Like the reference, `n_iters` and `n_oversamples` are accepted and IGNORED: PcaRsvd hard-codes 20 power
+    iterations and min(n_dim, 10) oversamples (pca_rsvd.rs:65-66).  The centred copy of a tall a_mat is never formed."""
+    a = _Mat(a_mat)
+    lib = _ffi.load()
+    nrows, ncols = a.shape
+    device = a.device if a.on_device else (comm.device if comm is not None else None)
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if a.on_device else None
+    o, keep = _make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=omega, seed=seed,
+                         schedule="reference", comm=comm, global_rows=global_rows, stream=stream, device=device,
+                         center=True)
+    k = int(n_rank)
+    s = _colmajor_empty_like(a, max(k, 1), 1)
+    comps = _colmajor_empty_like(a, max(k, 1), ncols)
+    means = _colmajor_empty_like(a, 1, ncols)
+    t = Timings()
+    st = lib.corrla_rpca_f64(a.ptr, nrows, ncols, a.strides[0], a.strides[1], k, C.byref(o), _ptr(s), _ptr(comps),
+                             _ptr(means), C.byref(t))
+    del keep
+    _ffi.check(st)
+    _tls.timings = t.as_dict()
+    return (s, comps, means) if return_means else (s, comps)
 
 
 def power_iter(a_mat, omega_rank: int, n_iter: int, *, omega=None, seed: int | None = None, schedule="reference",

@@ -27,6 +27,7 @@ class RsvdOpts(C.Structure):
         ("ctx", C.c_void_p),
         ("comm", C.c_void_p),
         ("global_rows", C.c_int64),
+        ("center", C.c_int),
     ]
 
 
@@ -59,6 +60,8 @@ SYMBOLS = {
                                   C.POINTER(Timings)]),
     "corrla_power_iter_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
                                         C.c_size_t, C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(Timings)]),
+    "corrla_rpca_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
+                                  C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
     "corrla_par_matmul_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_double, C.c_int, C.POINTER(RsvdOpts)]),

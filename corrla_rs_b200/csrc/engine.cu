@@ -141,6 +141,10 @@ struct Core {
   //        [4..5] jacobi info, [8] third-pass counter, [9] refill counter, [12..15] scratch info of refill-phase chol
   int* flags = nullptr;
   int* deadmask = nullptr;  // l ints
+  // on-the-fly centring (thin matrix is C = A - 1*mu^T): mu (n), bvec = X^T mu (Lc), column sums of Y live right
+  // behind the Z buffers (so one all-reduce carries both), sum_partials is scratch of the column-sum kernels
+  int center = 0;
+  double *mu = nullptr, *bvec = nullptr, *sum_partials = nullptr;
   uint64_t refill_seed = 0x5eedu; uint64_t refill_stream = 0; int qr_calls = 0;
   int launches = 0;
 
@@ -190,7 +194,12 @@ struct Core {
     deadmask = reinterpret_cast<int*>(getz("deadmask", (size_t)L16));
     bool ok = Y && G && T1 && Tf && scal && flags && deadmask;
     if (need_z) {
-      Za = getz("Za", (size_t)n16 * ld); Zb = getz("Zb", (size_t)n16 * ld); Qz = getz("Qz", (size_t)n16 * ld);
+      Za = getz("Za", (size_t)n16 * ld + 128); Zb = getz("Zb", (size_t)n16 * ld + 128); Qz = getz("Qz", (size_t)n16 * ld);
+      if (center) {
+        mu = getz("mu", (size_t)n16 + 128); bvec = getz("bvec", 256);
+        sum_partials = getz("sum_partials", (size_t)sum_blocks(m) * (size_t)std::max<int64_t>(n, Lc) + 128);
+        if (!mu || !bvec || !sum_partials) { set_last_error("device allocation failed (centring buffers)"); return CORRLA_ERR_ALLOC; }
+      }
       Tzf = getz("Tzf", small_elems()); Wm = getz("Wm", small_elems()); Vr = getz("Vr", small_elems());
       Ur = getz("Ur", small_elems()); M1 = getz("M1", small_elems()); sig = getz("sig", (size_t)L16);
       jscratch = getz("jscratch", 2 * (size_t)l * (l | 1) + 8);
@@ -205,8 +214,9 @@ struct Core {
 
   int mm(const MatView& a, bool reduce_inner, const double* B, double* out, int64_t ors, int64_t ocs, int ncols_out,
          const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0,
-         bool is_pass = false) {
+         bool is_pass = false, const double* col_bias = nullptr) {
     GemmCall c{};
+    c.col_bias = col_bias;
     if (is_pass && profile_passes) {
       c.ev_begin = ctx->event(2 + 2 * (size_t)n_pass_events);
       c.ev_end = ctx->event(3 + 2 * (size_t)n_pass_events);
@@ -227,13 +237,46 @@ struct Core {
 
   MatView view_rows(const double* p, int64_t rows) const { return MatView{p, (int64_t)Lc, rows, (int64_t)ld}; }
 
-  // Y[m x Lc] = alpha * A * X        (X: n16 x ld)
+  // Y[m x Lc] = alpha * C * X, C = A or A - 1*mu^T        (X: n16 x ld)
   int mm_AX(const double* X, double* Yout, const double* alpha, double* sumsq) {
-    return mm(av, a_rowmajor, X, Yout, ld, 1, Lc, alpha, sumsq, nullptr, 0, true);
+    const double* bias = nullptr;
+    if (center) {
+      cudaError_t e = gemv_t_launch(X, n, Lc, ld, mu, bvec, st);     // b = X^T mu: (1 mu^T) X = 1 b^T
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("gemv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      bias = bvec;
+    }
+    return mm(av, a_rowmajor, X, Yout, ld, 1, Lc, alpha, sumsq, nullptr, 0, true, bias);
   }
-  // Z[n x Lc] = A^T * Yin            (Yin: m16 x ld)
+  // Z[n x Lc] = C^T * Yin, summed over the ranks    (Yin: m16 x ld).  With centring: A^T Y - mu * (1^T Y).
   int mm_AtY(const double* Yin, double* Zout) {
-    return mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true);
+    ST_TRY(mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
+    double* colsum = Zout + (size_t)n16 * ld;            // contiguous with Z: one all-reduce for both
+    if (center) {
+      cudaError_t e = sum_over_outer_launch(Yin, Lc, m, ld, sum_partials, colsum, st);
+      launches += 2;
+      if (e != cudaSuccess) { set_last_error("column-sum launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    }
+    ST_TRY(allreduce(Zout, (size_t)n16 * ld + (center ? (size_t)Lc : 0)));
+    if (center) {
+      cudaError_t e = rank1_sub_launch(Zout, n, Lc, ld, mu, colsum, st);
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("rank-1 launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    }
+    return CORRLA_OK;
+  }
+
+  // mu = column means of the thin matrix (all ranks), for the fused centring
+  int compute_means_thin_cols() {
+    cudaError_t e = a_rowmajor ? sum_over_outer_launch(av.p, n, m, av.ld, sum_partials, mu, st)
+                               : sum_over_inner_launch(av.p, m, n, av.ld, mu, st);
+    launches += 2;
+    if (e != cudaSuccess) { set_last_error("mean launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    ST_TRY(allreduce(mu, (size_t)n));
+    e = scale_vec_launch(mu, n, 1.0 / grows, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("scale launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    return CORRLA_OK;
   }
 
   int allreduce(double* buf, size_t count) {
@@ -307,13 +350,11 @@ struct Core {
       const bool do_qr = (schedule == 1) || (i > 2);          // :37
       if (do_qr) {
         ST_TRY(qr_inplace(Y, m, true, grows, Tf));            // :38
-        ST_TRY(mm_AtY(Y, Zb));                                // :42-46 (on the pre-fold iterate)
-        ST_TRY(allreduce(Zb, (size_t)n * ld));
+        ST_TRY(mm_AtY(Y, Zb));                                // :42-46 (on the pre-fold iterate), all-reduced
         ST_TRY(mm(view_rows(Zb, n), true, Tf, Za, ld, 1, Lc)); // fold R^-1 into the small side
         ST_TRY(mm_AX(Za, Y, nullptr, nu2));                   // :47-51
       } else {
         ST_TRY(mm_AtY(Y, Zb));
-        ST_TRY(allreduce(Zb, (size_t)n * ld));
         ST_TRY(mm_AX(Zb, Y, nu2, nu2));                       // :47-51 with the deferred :53-55 scaling
       }
       ST_TRY(allreduce(nu2, 1));
@@ -444,13 +485,13 @@ corrla_rsvd_opts default_opts() {
 
 int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t cs, size_t n_rank, size_t n_iter,
               size_t n_oversamples, const corrla_rsvd_opts* opts_in, double* u, double* s, double* vt,
-              corrla_timings* tm, bool power_only, double* q_out) {
+              corrla_timings* tm, bool power_only, double* q_out, bool u_optional = false, double* means_out = nullptr) {
   Timer total;
   corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
   if (tm) memset(tm, 0, sizeof(*tm));
   if (a == nullptr || nrows <= 0 || ncols <= 0) { set_last_error("empty or null input matrix"); return CORRLA_ERR_INVALID; }
   if (power_only) { if (q_out == nullptr) { set_last_error("null output"); return CORRLA_ERR_INVALID; } }
-  else if (u == nullptr || s == nullptr || vt == nullptr) { set_last_error("null output"); return CORRLA_ERR_INVALID; }
+  else if ((u == nullptr && !u_optional) || s == nullptr || vt == nullptr) { set_last_error("null output"); return CORRLA_ERR_INVALID; }
 
   // thin orientation (random_svd.rs:69-74).  With a communicator the caller passes thin row blocks already.
   bool fat = false;
@@ -482,6 +523,9 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   ST_TRY(stage_matrix(sc.ctx, sc.st, "A", a, m, n, trs, tcs, o.a_on_device != 0, &c.av, &c.a_rowmajor, &h2d_ms, &c.launches));
   if (tm) tm->h2d_ms = h2d_ms;
 
+  const bool want_center = (o.center != 0) && !power_only;
+  if (want_center && fat && o.comm != nullptr) { set_last_error("centring of a fat matrix is not supported with a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  c.center = (want_center && !fat) ? 1 : 0;       // tall: rank-1 corrections inside the passes
   ST_TRY(c.alloc_workspace(true));
   ST_TRY(c.alloc_buffers(true));
 
@@ -496,6 +540,30 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       CU_TRY(cudaStreamSynchronize(sc.st));
       c.grows = hm;
     }
+  }
+
+  if (c.center) ST_TRY(c.compute_means_thin_cols());
+  if (want_center && fat) {
+    // thin = a^T: the column means of `a` are per-ROW constants of the thin matrix.  Fat matrices are small on their
+    // long side only (n <= m_thin rows of means): take the explicit centred copy the reference takes (center_mat_col).
+    double* mu_rows = static_cast<double*>(sc.ctx->get("mu", ((size_t)m + 128) * 8));
+    double* part = static_cast<double*>(sc.ctx->get("sum_partials", ((size_t)sum_blocks(n) * (size_t)m + 128) * 8));
+    double* cent = static_cast<double*>(sc.ctx->get("Acent", (size_t)c.av.outer * c.av.ld * 8));
+    if (!mu_rows || !part || !cent) { set_last_error("device allocation failed (centred copy)"); return CORRLA_ERR_ALLOC; }
+    // row sums of the thin matrix: a_rowmajor view = (inner n, outer m) -> sum over inner; else (inner m, outer n) -> over outer
+    cudaError_t e = c.a_rowmajor ? sum_over_inner_launch(c.av.p, n, m, c.av.ld, mu_rows, sc.st)
+                                 : sum_over_outer_launch(c.av.p, m, n, c.av.ld, part, mu_rows, sc.st);
+    if (e == cudaSuccess) e = scale_vec_launch(mu_rows, m, 1.0 / (double)n, sc.st);
+    if (e == cudaSuccess) e = center_copy_launch(c.av.p, c.av.inner, c.av.outer, c.av.ld, cent, c.av.ld, mu_rows,
+                                                 c.a_rowmajor ? 0 : 1, sc.st);
+    c.launches += 4;
+    if (e != cudaSuccess) { set_last_error("centring launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    c.av.p = cent;
+    c.mu = mu_rows;
+  }
+  if (means_out != nullptr && want_center) {
+    const int64_t cnt = fat ? m : n;                 // == ncols of the matrix as passed
+    CU_TRY(cudaMemcpyAsync(means_out, c.mu, (size_t)cnt * 8, o.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sc.st));
   }
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -528,7 +596,6 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   } else {
     // B^T = Z_B = (A^T Y) Tf                                       random_svd.rs:80
     ST_TRY(c.mm_AtY(c.Y, c.Zb));
-    ST_TRY(c.allreduce(c.Zb, (size_t)n * c.ld));
     ST_TRY(c.mm(c.view_rows(c.Zb, n), true, c.Tf, c.Za, c.ld, 1, c.Lc));
     // SVD of B (:89): QR-precondition Z_B, Jacobi on the l x l core W = Qz^T Z_B
     CU_TRY(cudaMemcpyAsync(c.Qz, c.Za, (size_t)c.n16 * c.ld * 8, cudaMemcpyDeviceToDevice, sc.st));
@@ -546,22 +613,23 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     // output placement (:96-109): thin-U is m x k, thin-V is n x k
     //   tall input : u <- U (col-major m x k),  vt <- V^T (col-major k x n  == V row-major n x k)
     //   fat input  : u <- V (col-major n x k),  vt <- U^T (col-major k x m  == U row-major m x k)
-    double* ud = out_dev ? u : static_cast<double*>(sc.ctx->get("Uout", (size_t)nrows * kk * 8));
+    const bool want_u = (u != nullptr);
+    double* ud = !want_u ? nullptr : (out_dev ? u : static_cast<double*>(sc.ctx->get("Uout", (size_t)nrows * kk * 8)));
     double* vd = out_dev ? vt : static_cast<double*>(sc.ctx->get("Vout", (size_t)ncols * kk * 8));
     double* sd = out_dev ? s : c.sig;
-    if (!ud || !vd) { set_last_error("device allocation of outputs failed"); return CORRLA_ERR_ALLOC; }
+    if ((want_u && !ud) || !vd) { set_last_error("device allocation of outputs failed"); return CORRLA_ERR_ALLOC; }
     double* Uthin_dst = fat ? vd : ud;
     double* Vthin_dst = fat ? ud : vd;
     const int64_t u_rs = fat ? kk : 1, u_cs = fat ? 1 : m;
     const int64_t v_rs = fat ? 1 : kk, v_cs = fat ? n : 1;
-    ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.M1, Uthin_dst, u_rs, u_cs, kk));
-    ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Ur, Vthin_dst, v_rs, v_cs, kk));
+    if (Uthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.M1, Uthin_dst, u_rs, u_cs, kk));
+    if (Vthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Ur, Vthin_dst, v_rs, v_cs, kk));
     if (out_dev) CU_TRY(cudaMemcpyAsync(s, c.sig, (size_t)kk * 8, cudaMemcpyDeviceToDevice, sc.st));
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
     if (!out_dev) {
       CU_TRY(cudaStreamSynchronize(sc.st));
       Timer t;
-      CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, u, (size_t)nrows * kk * 8, ud, (size_t)nrows * kk * 8, (size_t)nrows * kk * 8, 1));
+      if (want_u) CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, u, (size_t)nrows * kk * 8, ud, (size_t)nrows * kk * 8, (size_t)nrows * kk * 8, 1));
       CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, vt, (size_t)ncols * kk * 8, vd, (size_t)ncols * kk * 8, (size_t)ncols * kk * 8, 1));
       CU_TRY(cudaMemcpy(s, sd, (size_t)kk * 8, cudaMemcpyDeviceToHost));
       d2h_ms = t.ms();
@@ -615,6 +683,19 @@ int corrla_power_iter_f64(const double* a, int64_t nrows, int64_t ncols, int64_t
   try {
     return rsvd_impl(a, nrows, ncols, row_stride, col_stride, omega_rank, n_iter, 0, opts, nullptr, nullptr, nullptr,
                      timings, true, q);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+int corrla_rpca_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride, size_t n_rank,
+                    const corrla_rsvd_opts* opts, double* s, double* components, double* means, corrla_timings* timings) {
+  try {
+    corrla_rsvd_opts o = opts ? *opts : default_opts();
+    o.center = 1;
+    // PcaRsvd::new (pca_rsvd.rs:65-66): 20 power iterations, min(n_dim, 10) oversamples, U discarded
+    const size_t n_over = (size_t)std::min<int64_t>(ncols, 10);
+    return rsvd_impl(a, nrows, ncols, row_stride, col_stride, n_rank, 20, n_over, &o, nullptr, s, components, timings,
+                     false, nullptr, true, means);
   } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
   catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
 }

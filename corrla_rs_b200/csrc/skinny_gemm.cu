@@ -159,7 +159,9 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
           for (int j = 0; j < JW; ++j)
             if (FULL || j < jn) {
               const int col = 8 * (wn * JW + j) + 2 * t;
-              const double v0 = acc[i][j][0] * alpha, v1 = acc[i][j][1] * alpha;
+              double v0 = acc[i][j][0], v1 = acc[i][j][1];
+              if (p.col_bias != nullptr) { v0 -= p.col_bias[col]; v1 -= p.col_bias[col + 1]; }
+              v0 *= alpha; v1 *= alpha;
               ss += v0 * v0 + v1 * v1;
               double* o = p.out + row * p.out_rs + (int64_t)col * p.out_cs;
               if (p.out_cs == 1 && (p.out_rs & 1) == 0 && col + 1 < p.ncols_out) {
@@ -261,7 +263,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside,
                      double* __restrict__ out, int64_t out_rs, int64_t out_cs, int ncols_out,
-                     const double* alpha_sumsq, double* sumsq_partials, const int* cond_flag) {
+                     const double* alpha_sumsq, const double* col_bias, double* sumsq_partials, const int* cond_flag) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
   __shared__ double red[8];
   const int half = Lc >> 1;
@@ -281,6 +283,7 @@ splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int 
       const double2 v = *reinterpret_cast<const double2*>(src + s * split_stride);
       s0 += v.x; s1 += v.y;
     }
+    if (col_bias != nullptr) { s0 -= col_bias[col]; s1 -= col_bias[col + 1]; }
     s0 *= alpha; s1 *= alpha;
     ss = s0 * s0 + s1 * s1;
     double* o = out + r * out_rs + (int64_t)col * out_cs;
@@ -424,6 +427,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   a.B = c.B; a.ldb = c.ldb; a.nblk = c.nblk;
   a.out = c.out; a.out_rs = c.out_rs; a.out_cs = c.out_cs; a.ncols_out = c.ncols_out;
   a.alpha_sumsq = c.alpha_sumsq;
+  a.col_bias = c.col_bias;
   a.cond_flag = c.cond_flag;
   if (c.nblk < 1 || c.nblk > kMaxNblk || (c.ldb % 8) != 4 || c.ldb < c.nblk * 8) return cudaErrorInvalidValue;
   if (!tma_compatible(c.a)) return cudaErrorInvalidValue;
@@ -469,7 +473,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
     const int64_t total = a.Mside * (Lc / 2);
     const int blocks = (int)((total + 255) / 256);
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(w.ws, a.splits, a.tilesM, Lc, a.Mside, a.out, a.out_rs, a.out_cs,
-                                                     a.ncols_out, a.alpha_sumsq,
+                                                     a.ncols_out, a.alpha_sumsq, a.col_bias,
                                                      c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag);
     if (launches) ++*launches;
     e = cudaGetLastError();

@@ -37,6 +37,8 @@ struct GemmArgs {
   double* ws; int tilesM, splits; int64_t chunks_total, chunks_per_split;
   // alpha = rsqrt(*alpha_sumsq) when non-null, else 1
   const double* alpha_sumsq;
+  // out = alpha * (acc - col_bias[col]) when non-null (rank-1 centring correction: 1 * (mu^T X))
+  const double* col_bias;
   // per-work-item (splits==1) sum of squares of the scaled output, or null
   double* sumsq_partials;
   // when non-null and *cond_flag == 0 the kernel does nothing
@@ -50,6 +52,7 @@ struct GemmCall {
   const double* B; int ldb; int nblk;
   double* out; int64_t out_rs, out_cs; int ncols_out;
   const double* alpha_sumsq = nullptr;
+  const double* col_bias = nullptr;
   double* sumsq_slot = nullptr;     // if set: *sumsq_slot = sum of squares of the (scaled) output
   const int* cond_flag = nullptr;
   int force_splits = 0;             // testing hook: 0 = choose

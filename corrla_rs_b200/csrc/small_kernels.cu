@@ -234,6 +234,9 @@ constexpr int kJacobiMaxSweeps = 60;
 constexpr int kJacobiLanes = 8;          // lanes per column pair (a quarter warp)
 constexpr int kJacobiThreads = 512;      // 64 quarter warps >= 64 pairs (l <= 128); larger l loops
 
+// kAllSmem: both matrices live in shared memory (l <= 118) and every access compiles to LDS/STS; otherwise the
+// generic-pointer version runs with one or both matrices in global scratch.
+template <bool kAllSmem>
 __global__ void __launch_bounds__(kJacobiThreads)
 jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                   double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, double* gscratch,
@@ -242,10 +245,17 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
   const int lp = l | 1;
   const int h = (l + 1) >> 1;          // pairs per round; N = 2h players, player index >= l is a bye
   const int N1 = 2 * h - 1;
-  double* Xc = w_smem ? sm : gscratch;                                   // working columns (become U*Sigma)
-  double* Vc = v_smem ? (sm + (w_smem ? l * lp : 0)) : (gscratch + l * lp);   // accumulated rotations
-  double* nrm = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);      // squared column norms
+  double* Xc;                          // working columns (become U*Sigma)
+  double* Vc;                          // accumulated rotations
+  double* nrm;                         // squared column norms
+  if (kAllSmem) { Xc = sm; Vc = sm + l * lp; nrm = sm + 2 * l * lp; }
+  else {
+    Xc = w_smem ? sm : gscratch;
+    Vc = v_smem ? (sm + (w_smem ? l * lp : 0)) : (gscratch + l * lp);
+    nrm = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);
+  }
   int* rnk = reinterpret_cast<int*>(nrm + l);
+  int* anyflag = rnk + l;
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int LP = kJacobiLanes;
   const int grp = tid / LP, sub = tid % LP, ngrp = nt / LP;
@@ -293,9 +303,8 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
       if (sub == 0) nrm[j] = a;
     }
     __syncthreads();
-    int any = 0;
+    if (tid == 0) *anyflag = 0;
     for (int r = 0; r < N1; ++r) {
-      int rotated = 0;
       for (int pi = grp; pi < h; pi += ngrp) {
         int p, q;
         if (pi == 0) { p = N1; q = r; }
@@ -323,12 +332,13 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
             const double vx = vp[i], vy = vq[i];
             vp[i] = cs * vx - sn * vy; vq[i] = sn * vx + cs * vy;
           }
-          if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; }
-          rotated = 1;
+          if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; *anyflag = 1; }
         }
       }
-      any |= __syncthreads_or(rotated);
+      __syncthreads();
     }
+    const int any = *anyflag;
+    __syncthreads();
     if (!any) { converged = 1; ++sweeps; break; }
   }
 
@@ -393,7 +403,144 @@ repack_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// column statistics / rank-1 corrections
+// ------------------------------------------------------------------------------------------------
+constexpr int kSumRowsPerBlock = 4096;
+
+// block (bx over inner tiles of 128, by over row chunks): partial[by][i] = sum of rows of the chunk
+__global__ void __launch_bounds__(1024)
+sum_over_outer_kernel(const double* __restrict__ p, int64_t inner, int64_t outer, int64_t ld, double* __restrict__ partials) {
+  __shared__ double red[8][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;       // 128 columns x 8 row lanes
+  const int64_t i = (int64_t)blockIdx.x * 128 + tx;
+  const int64_t o0 = (int64_t)blockIdx.y * kSumRowsPerBlock, o1 = min(outer, o0 + kSumRowsPerBlock);
+  double a = 0.0;
+  if (i < inner)
+    for (int64_t o = o0 + ty; o < o1; o += 8) a += p[o * ld + i];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && i < inner) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][tx];
+    partials[(int64_t)blockIdx.y * inner + i] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const double* __restrict__ partials, int64_t inner, int nblocks, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inner) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partials[(int64_t)b * inner + i];
+  out[i] = t;
+}
+// one block per outer index: sum of a contiguous row
+__global__ void __launch_bounds__(256)
+sum_over_inner_kernel(const double* __restrict__ p, int64_t inner, int64_t outer, int64_t ld, double* __restrict__ out) {
+  __shared__ double red[8];
+  for (int64_t o = blockIdx.x; o < outer; o += gridDim.x) {
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < inner; i += blockDim.x) a += p[o * ld + i];
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) a += __shfl_xor_sync(0xffffffffu, a, k);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      out[o] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void scale_vec_kernel(double* v, int64_t n, double scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= scale;
+}
+__global__ void __launch_bounds__(1024)
+gemv_t_kernel(const double* __restrict__ X, int64_t rows, int cols, int64_t ld, const double* __restrict__ mu,
+              double* __restrict__ b) {
+  __shared__ double red[8][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  double a = 0.0;
+  if (tx < cols)
+    for (int64_t r = ty; r < rows; r += 8) a += X[r * ld + tx] * mu[r];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && tx < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][tx];
+    b[tx] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+rank1_sub_kernel(double* __restrict__ Z, int64_t rows, int cols, int64_t ld, const double* __restrict__ u,
+                 const double* __restrict__ v) {
+  const int64_t total = rows * cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t r = e / cols;
+    const int c = (int)(e - r * cols);
+    Z[r * ld + c] -= u[r] * v[c];
+  }
+}
+__global__ void __launch_bounds__(256)
+center_copy_kernel(const double* __restrict__ src, int64_t inner, int64_t outer, int64_t lds, double* __restrict__ dst,
+                   int64_t ldd, const double* __restrict__ mu, int by_inner) {
+  const int64_t total = inner * outer;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t o = e / inner, i = e - o * inner;
+    dst[o * ldd + i] = src[o * lds + i] - (by_inner ? mu[i] : mu[o]);
+  }
+}
+
 }  // namespace
+
+int sum_blocks(int64_t outer) { return (int)((outer + kSumRowsPerBlock - 1) / kSumRowsPerBlock); }
+
+cudaError_t sum_over_outer_launch(const double* p, int64_t inner, int64_t outer, int64_t ld, double* partials,
+                                  double* out, cudaStream_t s) {
+  if (inner <= 0 || outer <= 0) return cudaSuccess;
+  const int nb = sum_blocks(outer);
+  dim3 grid((unsigned)((inner + 127) / 128), (unsigned)nb);
+  sum_over_outer_kernel<<<grid, 1024, 0, s>>>(p, inner, outer, ld, partials);
+  sum_partials_kernel<<<(unsigned)((inner + 255) / 256), 256, 0, s>>>(partials, inner, nb, out);
+  return cudaGetLastError();
+}
+cudaError_t sum_over_inner_launch(const double* p, int64_t inner, int64_t outer, int64_t ld, double* out,
+                                  cudaStream_t s) {
+  if (inner <= 0 || outer <= 0) return cudaSuccess;
+  sum_over_inner_kernel<<<(unsigned)std::min<int64_t>(outer, 148 * 8), 256, 0, s>>>(p, inner, outer, ld, out);
+  return cudaGetLastError();
+}
+cudaError_t scale_vec_launch(double* v, int64_t n, double scale, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  scale_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, n, scale);
+  return cudaGetLastError();
+}
+cudaError_t gemv_t_launch(const double* X, int64_t rows, int cols, int64_t ld, const double* mu, double* b,
+                          cudaStream_t s) {
+  if (cols > 128) return cudaErrorInvalidValue;
+  gemv_t_kernel<<<1, 1024, 0, s>>>(X, rows, cols, ld, mu, b);
+  return cudaGetLastError();
+}
+cudaError_t rank1_sub_launch(double* Z, int64_t rows, int cols, int64_t ld, const double* u, const double* v,
+                             cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, 148 * 8);
+  rank1_sub_kernel<<<blocks, 256, 0, s>>>(Z, rows, cols, ld, u, v);
+  return cudaGetLastError();
+}
+cudaError_t center_copy_launch(const double* src, int64_t inner, int64_t outer, int64_t lds, double* dst, int64_t ldd,
+                               const double* mu, int mu_indexed_by_inner, cudaStream_t s) {
+  if (inner <= 0 || outer <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((inner * outer + 255) / 256, 148 * 16);
+  center_copy_kernel<<<blocks, 256, 0, s>>>(src, inner, outer, lds, dst, ldd, mu, mu_indexed_by_inner);
+  return cudaGetLastError();
+}
 
 cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld, uint64_t seed, cudaStream_t s) {
   const int64_t npairs = (rows * cols + 1) / 2;
@@ -410,7 +557,8 @@ cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrow
   const size_t smem = (size_t)l * (l + 1) * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // the kernel also has ~5 KB of static shared memory: leave room for it under the 227 KB limit
+    cudaError_t e = cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -431,7 +579,7 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose) {
   const int lp = l | 1;
   const size_t mat = (size_t)l * lp * 8;
-  const size_t small = (size_t)l * 8 + (size_t)(l + 2) * 4 + 16;
+  const size_t small = (size_t)l * 8 + (size_t)(l + 4) * 4 + 16;
   const size_t cap = 227 * 1024;
   int w_smem = 0, v_smem = 0;
   if (2 * mat + small <= cap) { w_smem = 1; v_smem = 1; }
@@ -439,11 +587,16 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
   const size_t smem = (w_smem + v_smem) * mat + small;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    cudaError_t e = cudaFuncSetAttribute(jacobi_svd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(jacobi_svd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  jacobi_svd_kernel<<<1, kJacobiThreads, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, transpose, info);
+  if (w_smem && v_smem)
+    jacobi_svd_kernel<true><<<1, kJacobiThreads, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, 1, 1, transpose, info);
+  else
+    jacobi_svd_kernel<false><<<1, kJacobiThreads, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, w_smem, v_smem, transpose, info);
   return cudaGetLastError();
 }
 

@@ -45,4 +45,25 @@ cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t
 cudaError_t scatter_launch(const double* src, int64_t rows, int64_t cols, int64_t ld, double* dst, int64_t drs,
                            int64_t dcs, cudaStream_t s);
 
+// ---- column statistics and rank-1 corrections for on-the-fly centring (PCA: pca_rsvd.rs:60-66) ----------------
+// out[i] = sum over o < outer of p[o*ld + i], i < inner  (column sums of a row-major matrix).  Deterministic:
+// per-block partial sums in `partials` (>= sum_blocks(outer) * inner doubles) are added in a fixed order.
+int sum_blocks(int64_t outer);
+cudaError_t sum_over_outer_launch(const double* p, int64_t inner, int64_t outer, int64_t ld, double* partials,
+                                  double* out, cudaStream_t s);
+// out[o] = sum over i < inner of p[o*ld + i], o < outer  (column sums of a column-major matrix).
+cudaError_t sum_over_inner_launch(const double* p, int64_t inner, int64_t outer, int64_t ld, double* out,
+                                  cudaStream_t s);
+// v[i] *= scale
+cudaError_t scale_vec_launch(double* v, int64_t n, double scale, cudaStream_t s);
+// b[c] = sum_r X[r*ld + c] * mu[r], c < cols (cols <= 128)
+cudaError_t gemv_t_launch(const double* X, int64_t rows, int cols, int64_t ld, const double* mu, double* b,
+                          cudaStream_t s);
+// Z[r*ld + c] -= u[r] * v[c]
+cudaError_t rank1_sub_launch(double* Z, int64_t rows, int cols, int64_t ld, const double* u, const double* v,
+                             cudaStream_t s);
+// dst[o*ldd + i] = src[o*lds + i] - (mean_along_inner ? mu[i] : mu[o])   (explicit centred copy, fallback path)
+cudaError_t center_copy_launch(const double* src, int64_t inner, int64_t outer, int64_t lds, double* dst, int64_t ldd,
+                               const double* mu, int mu_indexed_by_inner, cudaStream_t s);
+
 }  // namespace corrla

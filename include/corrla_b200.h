@@ -65,6 +65,9 @@ typedef struct corrla_rsvd_opts {
   corrla_ctx* ctx;         /* reuse buffers across calls; NULL => a temporary context per call */
   corrla_comm* comm;       /* NULL => single GPU.  Else `a` is this rank's block of rows of the thin matrix */
   int64_t global_rows;     /* with comm: total rows over all ranks (0 => computed with an all-reduce) */
+  int center;              /* 1 => decompose a - 1*mean_cols(a)^T (PCA centring, center_mat_col: mat_utils.rs:482-502)
+                              without forming the centred copy when the matrix is tall (rank-1 corrections inside the
+                              passes); fat inputs get an explicit centred copy */
 } corrla_rsvd_opts;
 
 typedef struct corrla_timings {
@@ -112,6 +115,13 @@ CORRLA_API int corrla_par_matmul_f64(double* res, int64_t res_rs, int64_t res_cs
  * Element (i, j) is draw number i*n_cols + j. */
 CORRLA_API int corrla_random_mat_normal_f64(uint64_t seed, int64_t n_rows, int64_t n_cols, double* out, int out_on_device,
                                  const corrla_rsvd_opts* opts);
+
+/* PCA by RSVD, PcaRsvd::new (src/lib_math_utils/pca_rsvd.rs:56-82) behind the pyo3 rpca (lib_math_utils_py.rs:38-55):
+ * column means, random_svd(centred a, n_rank, 20, min(ncols, 10)).  s: n_rank singular values; components: n_rank x ncols
+ * column-major (= Vt); means: ncols (optional, may be NULL).  U is never formed. */
+CORRLA_API int corrla_rpca_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                    size_t n_rank, const corrla_rsvd_opts* opts, double* s, double* components, double* means,
+                    corrla_timings* timings);
 
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
  * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 128.  rank_out (optional) = live columns. */

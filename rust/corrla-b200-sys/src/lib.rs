@@ -32,6 +32,7 @@ pub struct corrla_rsvd_opts {
     pub ctx: *mut corrla_ctx,
     pub comm: *mut corrla_comm,
     pub global_rows: i64,
+    pub center: c_int,
 }
 
 #[repr(C)]
@@ -60,6 +61,9 @@ extern "C" {
     pub fn corrla_power_iter_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                                  omega_rank: usize, n_iter: usize, opts: *const corrla_rsvd_opts, q: *mut f64,
                                  timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_rpca_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64, n_rank: usize,
+                           opts: *const corrla_rsvd_opts, s: *mut f64, components: *mut f64, means: *mut f64,
+                           timings: *mut corrla_timings) -> c_int;
     pub fn corrla_par_matmul_f64(res: *mut f64, res_rs: i64, res_cs: i64, lhs: *const f64, lhs_rows: i64,
                                  lhs_cols: i64, lhs_rs: i64, lhs_cs: i64, rhs: *const f64, rhs_cols: i64,
                                  rhs_rs: i64, rhs_cs: i64, beta: f64, on_device: c_int,

@@ -18,7 +18,7 @@ def declared_symbols():
 def test_header_symbols_all_exported(built_lib):
     from corrla_rs_b200 import _ffi
     names = declared_symbols()
-    assert len(names) >= 16
+    assert len(names) >= 17
     assert sorted(_ffi.SYMBOLS) == names            # the ctypes table binds the header 1:1
     for n in names:
         assert getattr(built_lib, n) is not None
@@ -40,7 +40,8 @@ def test_struct_layout_matches_header(built_lib):
     built_lib.corrla_rsvd_opts_default(C.byref(o))
     assert o.device == -1 and o.seed == 0 and o.omega is None and o.schedule == 0
     assert o.a_on_device == 0 and o.out_on_device == 0 and o.ctx is None and o.comm is None and o.global_rows == 0
-    assert C.sizeof(o) == 88
+    assert o.center == 0
+    assert C.sizeof(o) == 96
 
 
 def test_type_errors_like_pyo3(built_lib):
@@ -54,7 +55,7 @@ def test_type_errors_like_pyo3(built_lib):
     with pytest.raises(OverflowError):
         corrla_rs.rsvd(np.zeros((4, 4)), -1, 1, 1)                        # usize extraction
     with pytest.raises(NotImplementedError):
-        corrla_rs.rpca
+        corrla_rs.PyDMDc
 
 
 def test_no_cpu_fallback_without_gpu(built_lib):

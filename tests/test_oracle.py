@@ -136,3 +136,17 @@ def test_engine_model_jacobi_svd():
     assert np.max(np.abs(sig - s_ref)) < 1e-14 * s_ref[0]
     assert np.max(np.abs(sig - s_ref) / s_ref) < 1e-9          # high relative accuracy even at kappa = 1e10
     assert np.max(np.abs(ur @ np.diag(sig) @ vr.T - w)) < 1e-13
+
+
+def test_pca_oracle_matches_direct_svd():
+    """oracle/ref_pca.py (PcaRsvd::new restated) against a dense SVD of the centred data."""
+    from oracle import ref_pca
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((800, 12)) * np.arange(1, 13) + 7.0
+    p = ref_pca.pca_rsvd_new(x, 4, rng=rng)
+    s_ref = np.linalg.svd(x - x.mean(axis=0), compute_uv=False)[:4]
+    assert p["singular_values"].shape == (4, 1) and p["components"].shape == (4, 12) and p["means"].shape == (1, 12)
+    assert np.max(np.abs(p["singular_values"].ravel() - s_ref) / s_ref) < 1e-10
+    assert np.allclose(ref_pca.explained_var(p).ravel(), s_ref ** 2 / 799.0)
+    s, c = ref_pca.rpca(x, 4, 99, 99, omega=rng.standard_normal((12, 12)))          # extra args ignored (F7)
+    assert np.max(np.abs(s.ravel() - s_ref) / s_ref) < 1e-10
