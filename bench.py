@@ -72,6 +72,19 @@ def fp64_peak():
         return 37.0, "fallback: DMMA.8x8x4 issue-rate peak at 1965 MHz"
 
 
+def measured_traffic(rows_local, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from an `ncu --set full`
+    capture committed under profiles/ (bytes per row of A, scaled to this GPU's rows); None if no capture exists."""
+    f = ROOT / "profiles" / "traffic.json"
+    try:
+        d = json.loads(f.read_text())
+        if int(d["cols"]) != int(n):
+            return None
+        return float(d["dram_bytes_per_row"]) * rows_local
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of random_svd.rs on the host cores
 # --------------------------------------------------------------------------------------------------
@@ -300,7 +313,7 @@ def run_ours(args):
     avg_pass_ms = max_over_ranks(pass_ms / max(pass_launches, 1))
     achieved = pass_flops / (avg_pass_ms * 1e-3) * 1e-12 if pass_launches else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(m_local, n),
                 "kernel": "skinny_gemm_kernel (DMMA.8x8x4 + TMA), one launch = one pass over this GPU's rows of A",
                 "flops_per_launch": pass_flops, "avg_launch_ms": avg_pass_ms, "launches_timed": pass_launches,
                 "hbm_bytes_per_launch_algorithmic": m_local * n * 8.0,

@@ -202,7 +202,7 @@ struct Core {
       }
       Tzf = getz("Tzf", small_elems()); Wm = getz("Wm", small_elems()); Vr = getz("Vr", small_elems());
       Ur = getz("Ur", small_elems()); M1 = getz("M1", small_elems()); sig = getz("sig", (size_t)L16);
-      jscratch = getz("jscratch", 2 * (size_t)l * (l | 1) + 8);
+      jscratch = getz("jscratch", 2 * (size_t)l * (l + 2) + 8);
       ok = ok && Za && Zb && Qz && Tzf && Wm && Vr && Ur && M1 && sig && jscratch;
     }
     if (!ok) { set_last_error("device allocation failed (m=%lld n=%lld l=%d)", (long long)m, (long long)n, l); return CORRLA_ERR_ALLOC; }

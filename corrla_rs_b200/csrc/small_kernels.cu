@@ -231,28 +231,29 @@ refill_dead_kernel(double* __restrict__ X, int64_t rows, int l, int64_t ld, cons
 // Drmac & Veselic the rotations are applied to its transpose, which converges in fewer sweeps.
 // ------------------------------------------------------------------------------------------------
 constexpr int kJacobiMaxSweeps = 60;
-constexpr int kJacobiLanes = 8;          // lanes per column pair (a quarter warp)
+constexpr int kJacobiLanes = 8;          // lanes per column pair (a quarter warp); each lane moves 16-byte double2s,
+                                         // so one group's access is one full 128-byte shared-memory wavefront
 constexpr int kJacobiThreads = 512;      // 64 quarter warps >= 64 pairs (l <= 128); larger l loops
 
-// kAllSmem: both matrices live in shared memory (l <= 118) and every access compiles to LDS/STS; otherwise the
-// generic-pointer version runs with one or both matrices in global scratch.
+// kAllSmem: both matrices live in shared memory (l <= 118) and every access compiles to LDS.128/STS.128; otherwise
+// the generic-pointer version runs with one or both matrices in global scratch.
 template <bool kAllSmem>
 __global__ void __launch_bounds__(kJacobiThreads)
 jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                   double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, double* gscratch,
                   int w_smem, int v_smem, int transpose, int* info) {
-  extern __shared__ double sm[];
-  const int lp = l | 1;
+  extern __shared__ __align__(16) double smj[];
+  const int lp = (l + 1) & ~1;         // even pitch: columns are 16-byte aligned, row l (if any) is a zero pad
   const int h = (l + 1) >> 1;          // pairs per round; N = 2h players, player index >= l is a bye
   const int N1 = 2 * h - 1;
   double* Xc;                          // working columns (become U*Sigma)
   double* Vc;                          // accumulated rotations
   double* nrm;                         // squared column norms
-  if (kAllSmem) { Xc = sm; Vc = sm + l * lp; nrm = sm + 2 * l * lp; }
+  if (kAllSmem) { Xc = smj; Vc = smj + l * lp; nrm = smj + 2 * l * lp; }
   else {
-    Xc = w_smem ? sm : gscratch;
-    Vc = v_smem ? (sm + (w_smem ? l * lp : 0)) : (gscratch + l * lp);
-    nrm = sm + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);
+    Xc = w_smem ? smj : gscratch;
+    Vc = v_smem ? (smj + (w_smem ? l * lp : 0)) : (gscratch + l * lp);
+    nrm = smj + (w_smem ? l * lp : 0) + (v_smem ? l * lp : 0);
   }
   int* rnk = reinterpret_cast<int*>(nrm + l);
   int* anyflag = rnk + l;
@@ -283,27 +284,31 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
     rnk[j] = r;
   }
   __syncthreads();
-  for (int idx = tid; idx < l * l; idx += nt) {
-    const int j = idx / l, i = idx - j * l;                      // source column j, row i
+  for (int idx = tid; idx < l * lp; idx += nt) {
+    const int j = idx / lp, i = idx - j * lp;                     // source column j, row i (i == l: zero pad)
     const int c = rnk[j];
-    Xc[c * lp + i] = transpose ? Win[(int64_t)j * ldw + i] : Win[(int64_t)i * ldw + j];
-    Vc[c * lp + i] = (i == j) ? 1.0 : 0.0;                       // V starts as the permutation
+    double x = 0.0;
+    if (i < l) x = transpose ? Win[(int64_t)j * ldw + i] : Win[(int64_t)i * ldw + j];
+    Xc[c * lp + i] = x;
+    Vc[c * lp + i] = (i == j) ? 1.0 : 0.0;                        // V starts as the permutation
   }
   __syncthreads();
 
   const double tol = sqrt((double)l) * DBL_EPSILON;
   const double tol2 = tol * tol;
+  const int lp2 = lp >> 1;                                        // double2 elements per column
   int sweeps = 0, converged = 0;
   for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
     for (int j = grp; j < l; j += ngrp) {                         // exact norms once per sweep
+      const double2* xj = reinterpret_cast<const double2*>(Xc + j * lp);
       double a = 0.0;
-      for (int i = sub; i < l; i += LP) { const double x = Xc[j * lp + i]; a += x * x; }
+      for (int i = sub; i < lp2; i += LP) { const double2 x = xj[i]; a += x.x * x.x + x.y * x.y; }
 #pragma unroll
       for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
       if (sub == 0) nrm[j] = a;
     }
-    __syncthreads();
     if (tid == 0) *anyflag = 0;
+    __syncthreads();
     for (int r = 0; r < N1; ++r) {
       for (int pi = grp; pi < h; pi += ngrp) {
         int p, q;
@@ -311,10 +316,12 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
         else { p = r + pi; if (p >= N1) p -= N1; q = r - pi; if (q < 0) q += N1; }
         if (p > q) { const int tmp = p; p = q; q = tmp; }
         if (q >= l) continue;                                     // bye
-        double* xp = Xc + p * lp; double* xq = Xc + q * lp;
-        double c = 0.0;
+        double2* xp = reinterpret_cast<double2*>(Xc + p * lp);
+        double2* xq = reinterpret_cast<double2*>(Xc + q * lp);
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll 4
-        for (int i = sub; i < l; i += LP) c += xp[i] * xq[i];
+        for (int i = sub; i < lp2; i += LP) { const double2 x = xp[i], y = xq[i]; c0 += x.x * y.x; c1 += x.y * y.y; }
+        double c = c0 + c1;
 #pragma unroll
         for (int o = LP / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
         c = __shfl_sync(gmask, c, glead);                         // identical bits in all lanes of the group
@@ -324,13 +331,16 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
           const double d = b - a;
           const double t = copysign(2.0 * c, d * c) / (fabs(d) + sqrt(d * d + 4.0 * c * c));
           const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-          double* vp = Vc + p * lp; double* vq = Vc + q * lp;
+          double2* vp = reinterpret_cast<double2*>(Vc + p * lp);
+          double2* vq = reinterpret_cast<double2*>(Vc + q * lp);
 #pragma unroll 4
-          for (int i = sub; i < l; i += LP) {
-            const double x = xp[i], y = xq[i];
-            xp[i] = cs * x - sn * y; xq[i] = sn * x + cs * y;
-            const double vx = vp[i], vy = vq[i];
-            vp[i] = cs * vx - sn * vy; vq[i] = sn * vx + cs * vy;
+          for (int i = sub; i < lp2; i += LP) {
+            const double2 x = xp[i], y = xq[i];
+            xp[i] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+            xq[i] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+            const double2 vx = vp[i], vy = vq[i];
+            vp[i] = make_double2(cs * vx.x - sn * vy.x, cs * vx.y - sn * vy.y);
+            vq[i] = make_double2(sn * vx.x + cs * vy.x, sn * vx.y + cs * vy.y);
           }
           if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; *anyflag = 1; }
         }
@@ -577,7 +587,7 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose) {
-  const int lp = l | 1;
+  const int lp = (l + 1) & ~1;
   const size_t mat = (size_t)l * lp * 8;
   const size_t small = (size_t)l * 8 + (size_t)(l + 4) * 4 + 16;
   const size_t cap = 227 * 1024;
