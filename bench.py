@@ -368,6 +368,9 @@ def run_ours(args):
             "config": workload_config(args.workload, rows, n, k, q, p, world),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches, "sigma_head": s_dev,
+            "collectives": ("none (single GPU)" if world == 1 else
+                            (f"{tm['p2p_exchanges']} per call fused into the split-K reduction kernel over NVLink peer memory"
+                             if tm["p2p_exchanges"] else "NCCL all-reduce")),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

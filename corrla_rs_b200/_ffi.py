@@ -46,6 +46,7 @@ class Timings(C.Structure):
         ("pass_launches", C.c_int),
         ("pass_ms", C.c_double),
         ("pass_flops", C.c_double),
+        ("p2p_exchanges", C.c_int),
     ]
 
     def as_dict(self):

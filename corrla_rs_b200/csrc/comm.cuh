@@ -1,15 +1,48 @@
-// NCCL communicator for the row-sharded RSVD, bound at run time with dlopen so that libcorrla_b200.so
-// neither links libnccl nor fights with the copy PyTorch has already loaded into the process.
+// Communicator for the row-sharded RSVD (one process per GPU).
+//  * NCCL, bound at run time with dlopen so that libcorrla_b200.so neither links libnccl nor fights with the copy
+//    PyTorch has already loaded into the process: bootstrap, large or rare all-reduces.
+//  * Peer memory over NVLink/NVSwitch: every rank cudaMalloc's one "symmetric" region, exports it with CUDA IPC, and
+//    maps everybody else's.  The split-K reduction kernel of the GEMM then finishes the all-reduce itself
+//    (reduce_exchange_kernel in skinny_gemm.cu): local partial sums -> my region, one release flag per peer, acquire
+//    the peers' flags, sum the P regions in rank order straight out of peer memory.  No NCCL call on that path.
 #pragma once
 #include <cstddef>
+#include <cstdint>
 #include <cuda_runtime.h>
+
+namespace corrla {
+constexpr int kMaxPeers = 8;
+constexpr size_t kSymFlagBytes = 1024;                 // kMaxPeers epochs (one per source rank), padded
+constexpr size_t kSymHalfDoubles = (size_t)1 << 19;    // 4 MiB per half; two halves alternate by epoch parity
+
+// One exchange, by value into the kernel.
+struct PeerExchange {
+  double* mine;                                        // my half for this epoch
+  const double* peer[kMaxPeers];                       // every rank's half for this epoch (peer[rank] == mine)
+  unsigned long long* my_flags;                        // [src] = last epoch rank `src` has published, written by src
+  unsigned long long* peer_flags[kMaxPeers];           // the same array on every rank
+  unsigned int* block_counter;                         // local scratch, zero between launches
+  int* err;                                            // local: set to 1 if a peer never showed up (timeout)
+  int rank, nranks;
+  unsigned long long epoch;
+};
+}  // namespace corrla
 
 struct corrla_comm {
   void* lib = nullptr;
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1, device = 0;
-  // sum-all-reduce `count` doubles in place on `stream`; returns 0 or a negative corrla_status
+  // peer-memory path
+  bool p2p = false;
+  void* sym_local = nullptr;
+  void* sym_peer[corrla::kMaxPeers] = {};
+  unsigned int* block_counter = nullptr;
+  int* err_flag = nullptr;
+  unsigned long long epoch = 0;
+  // sum-all-reduce `count` doubles in place on `stream` with NCCL; returns 0 or a negative corrla_status
   int allreduce_f64(double* buf, size_t count, cudaStream_t stream);
+  // next exchange descriptor (advances the epoch); false if the peer path is off or `count` does not fit
+  bool next_exchange(size_t count, corrla::PeerExchange* px);
 };
 
 namespace corrla {

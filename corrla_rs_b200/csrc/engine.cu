@@ -194,7 +194,7 @@ struct Core {
     deadmask = reinterpret_cast<int*>(getz("deadmask", (size_t)L16));
     bool ok = Y && G && T1 && Tf && scal && flags && deadmask;
     if (need_z) {
-      Za = getz("Za", (size_t)n16 * ld + 128); Zb = getz("Zb", (size_t)n16 * ld + 128); Qz = getz("Qz", (size_t)n16 * ld);
+      Za = getz("Za", (size_t)n16 * ld + 256); Zb = getz("Zb", (size_t)n16 * ld + 256); Qz = getz("Qz", (size_t)n16 * ld);
       if (center) {
         mu = getz("mu", (size_t)n16 + 128); bvec = getz("bvec", 256);
         sum_partials = getz("sum_partials", (size_t)sum_blocks(m) * (size_t)std::max<int64_t>(n, Lc) + 128);
@@ -210,13 +210,21 @@ struct Core {
   }
 
   bool profile_passes = false;
+  int p2p_exchanges = 0;
   int n_pass_events = 0;    // pairs recorded so far: events 2i, 2i+1 (offset by 2 for the whole-call pair)
 
   int mm(const MatView& a, bool reduce_inner, const double* B, double* out, int64_t ors, int64_t ocs, int ncols_out,
          const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0,
-         bool is_pass = false, const double* col_bias = nullptr) {
+         bool is_pass = false, const double* col_bias = nullptr, size_t x_count = 0, size_t x_extra = 0) {
     GemmCall c{};
     c.col_bias = col_bias;
+    // cross-rank sum of the product: fused into the reduction kernel over peer memory when possible, else NCCL
+    PeerExchange px;
+    bool nccl_after = false;
+    if (x_count > 0 && comm != nullptr && comm->nranks > 1) {
+      if (comm->next_exchange(x_count, &px)) { c.px = &px; c.x_count = x_count; c.x_extra = x_extra; ++p2p_exchanges; }
+      else nccl_after = true;
+    }
     if (is_pass && profile_passes) {
       c.ev_begin = ctx->event(2 + 2 * (size_t)n_pass_events);
       c.ev_end = ctx->event(3 + 2 * (size_t)n_pass_events);
@@ -232,6 +240,7 @@ struct Core {
       cudaGetLastError();
       return CORRLA_ERR_CUDA;
     }
+    if (nccl_after) ST_TRY(allreduce(out, x_count));
     return CORRLA_OK;
   }
 
@@ -250,14 +259,15 @@ struct Core {
   }
   // Z[n x Lc] = C^T * Yin, summed over the ranks    (Yin: m16 x ld).  With centring: A^T Y - mu * (1^T Y).
   int mm_AtY(const double* Yin, double* Zout) {
-    ST_TRY(mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
-    double* colsum = Zout + (size_t)n16 * ld;            // contiguous with Z: one all-reduce for both
+    // tail of the Z buffer, summed over the ranks together with Z: [column sums of Y (Lc) | ||Y||_F^2 (1)]
+    double* colsum = Zout + (size_t)n16 * ld;
     if (center) {
       cudaError_t e = sum_over_outer_launch(Yin, Lc, m, ld, sum_partials, colsum, st);
       launches += 2;
       if (e != cudaSuccess) { set_last_error("column-sum launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
     }
-    ST_TRY(allreduce(Zout, (size_t)n16 * ld + (center ? (size_t)Lc : 0)));
+    ST_TRY(mm(av, !a_rowmajor, Yin, Zout, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true, nullptr,
+              (size_t)n16 * ld + (size_t)Lc + 1, (size_t)Lc + 1));
     if (center) {
       cudaError_t e = rank1_sub_launch(Zout, n, Lc, ld, mu, colsum, st);
       ++launches;
@@ -299,18 +309,16 @@ struct Core {
   int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold) {
     const MatView vx = view_rows(X, rows);
     const size_t gcount = (size_t)Lc * ld;
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc));
-    if (distributed) ST_TRY(allreduce(G, gcount));
+    const size_t gx = distributed ? gcount : 0;       // Gram matrices are summed over the ranks inside the reduction kernel
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
     ST_TRY(chol(kCholAuto, rows_for_shift, T1, nullptr));
     ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, nullptr, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc));
-    if (distributed) ST_TRY(allreduce(G, gcount));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
     ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, nullptr));
     // third pass, only when the first one had to be shifted (device-side flag, no host round trip)
     const int* f3 = flags + 0;
     ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, f3, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f3));
-    if (distributed) ST_TRY(allreduce(G, gcount));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f3, 0, false, nullptr, gx, 0));
     ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, f3));
     // Refill, only when columns were deflated as numerically dependent: form Q (zero columns where dead), overwrite
     // those columns with fresh Gaussian vectors and run CholeskyQR2 again -- the arbitrary completion a Householder
@@ -322,12 +330,10 @@ struct Core {
       ++launches;
       if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
     }
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd));
-    if (distributed) ST_TRY(allreduce(G, gcount));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, gx, 0));
     ST_TRY(chol(kCholPlain, rows_for_shift, T1, fd, true));
     ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, fd, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd));
-    if (distributed) ST_TRY(allreduce(G, gcount));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, gx, 0));
     ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, fd, true));
     count_third_pass();
     ++qr_calls;
@@ -343,9 +349,9 @@ struct Core {
       ++launches;
       if (e != cudaSuccess) { set_last_error("philox launch failed: %s", cudaGetErrorString(e)); return CORRLA_ERR_CUDA; }
     }
-    double* nu2 = scal + 0;
+    // ||Y||_F^2 lives in the tail of Zb: the next A^T*Y sums it over the ranks together with Z
+    double* nu2 = Zb + (size_t)n16 * ld + Lc;
     ST_TRY(mm_AX(Za, Y, nullptr, nu2));                       // random_svd.rs:31
-    ST_TRY(allreduce(nu2, 1));
     for (int i = 0; i < n_iter; ++i) {                        // :35
       const bool do_qr = (schedule == 1) || (i > 2);          // :37
       if (do_qr) {
@@ -357,7 +363,6 @@ struct Core {
         ST_TRY(mm_AtY(Y, Zb));
         ST_TRY(mm_AX(Zb, Y, nu2, nu2));                       // :47-51 with the deferred :53-55 scaling
       }
-      ST_TRY(allreduce(nu2, 1));
     }
     ST_TRY(qr_inplace(Y, m, true, grows, Tf));                // :57
     return CORRLA_OK;
@@ -648,6 +653,12 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       else cudaGetLastError();
     }
     tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l;
+    tm->p2p_exchanges = c.p2p_exchanges;
+    if (o.comm != nullptr && o.comm->p2p) {
+      int herr = 0;
+      CU_TRY(cudaMemcpy(&herr, o.comm->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+      if (herr != 0) { set_last_error("peer-memory exchange timed out: a rank never published its epoch"); return CORRLA_ERR_COMM; }
+    }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
     tm->qr_third_passes = hflags[8]; tm->qr_refills = hflags[9]; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1];

@@ -64,7 +64,7 @@ cudaError_t BounceBuffers::ensure(size_t want) {
   }
   bytes = want;
   const unsigned hc = std::thread::hardware_concurrency();
-  threads = (int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u));
+  threads = (int)std::max(1u, std::min(16u, hc ? hc : 4u));
   return cudaSuccess;
 }
 

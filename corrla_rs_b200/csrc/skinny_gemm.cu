@@ -303,6 +303,117 @@ splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split-K reduction fused with the cross-GPU all-reduce over NVLink peer memory (one process per GPU).
+//   phase 0  local:   mine[r*ld + c] = sum_s ws[s][...]          (ws == nullptr: the GEMM already wrote `mine`)
+//                     the x_extra caller values are copied from out's tail into mine's tail
+//   publish           last block to finish: st.release.sys of this epoch into every rank's flag array
+//   acquire           every block spins (bounded) until all ranks have published this epoch
+//   phase 1  global:  out[i] = sum over ranks, in rank order, of peer[rank][i]   (i < x_count) -- identical bits on
+//                     every rank, read straight out of the peers' HBM through NVLink (ld.relaxed.sys, not L1-cached)
+// The two halves of the symmetric region alternate by epoch parity, which makes a second barrier unnecessary: a rank
+// can only overwrite half h two epochs later, after it has seen every peer publish the epoch in between, i.e. after
+// every peer finished reading.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+reduce_exchange_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside, int64_t ld,
+                       double* __restrict__ out, size_t x_count, size_t x_extra, const PeerExchange px,
+                       const int* cond_flag) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  __shared__ int s_last;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  double* mine = px.mine;
+
+  // ---- phase 0: the whole ld-pitched block is (re)written, pads included, so nothing stale is ever summed
+  {
+    const int64_t ld2 = ld >> 1;
+    const int64_t body_pairs = (int64_t)((x_count - x_extra) >> 1);
+    const int64_t split_stride = (int64_t)tilesM * kTileM * Lc;
+    for (int64_t idx = tid; idx < body_pairs; idx += nthreads) {
+      const int64_t r = idx / ld2;
+      const int col = (int)(idx - r * ld2) * 2;
+      const bool valid = (r < Mside) && (col < Lc);
+      if (ws != nullptr) {
+        double s0 = 0.0, s1 = 0.0;
+        if (valid) {
+          const double* src = ws + r * Lc + col;              // (tile*128 + rt) * Lc == r * Lc
+          for (int s = 0; s < splits; ++s) {
+            const double2 v = *reinterpret_cast<const double2*>(src + s * split_stride);
+            s0 += v.x; s1 += v.y;
+          }
+        }
+        *reinterpret_cast<double2*>(mine + 2 * idx) = make_double2(s0, s1);
+      } else if (!valid) {
+        *reinterpret_cast<double2*>(mine + 2 * idx) = make_double2(0.0, 0.0);   // the GEMM wrote the valid part itself
+      }
+    }
+  }
+  for (size_t i = (size_t)tid; i < x_extra; i += (size_t)nthreads) mine[x_count - x_extra + i] = out[x_count - x_extra + i];
+
+  // ---- publish: every thread's stores are fenced system-wide, the last block raises the flags
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(px.block_counter, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < px.nranks) st_release_sys_u64(px.peer_flags[threadIdx.x] + px.rank, px.epoch);
+    if (threadIdx.x == 0) *px.block_counter = 0u;               // ready for the next launch (stream ordered)
+  }
+
+  // ---- acquire: wait (bounded) for every rank's flag
+  if (threadIdx.x < px.nranks) {
+    const unsigned long long* f = px.my_flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) < px.epoch) {
+      if (clock64() - t0 > 20000000000ll) { *px.err = 1; break; }   // ~10 s: a peer never arrived
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1
+  const size_t pairs = x_count >> 1;
+  for (size_t i = (size_t)tid; i < pairs; i += (size_t)nthreads) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < px.nranks) {
+        const double2 v = (r == px.rank) ? *reinterpret_cast<const double2*>(mine + 2 * i)
+                                         : ld_relaxed_sys_f64x2(px.peer[r] + 2 * i);
+        s0 += v.x; s1 += v.y;
+      }
+    *reinterpret_cast<double2*>(out + 2 * i) = make_double2(s0, s1);
+  }
+  if ((x_count & 1) && tid == 0) {
+    double s0 = 0.0;
+    for (int r = 0; r < px.nranks; ++r) {
+      const double* q = (r == px.rank) ? mine : px.peer[r];
+      double v;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(q + x_count - 1) : "memory");
+      s0 += v;
+    }
+    out[x_count - 1] = s0;
+  }
+}
+
 // *slot = sum(partials[0..n)) in a fixed order (bit-reproducible).
 __global__ void __launch_bounds__(1024)
 sumsq_finalize_kernel(const double* __restrict__ partials, int64_t n, double* slot, const int* cond_flag) {
@@ -441,6 +552,14 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   a.ws = w.ws;
   a.sumsq_partials = (c.sumsq_slot != nullptr && a.splits == 1) ? w.sumsq_partials : nullptr;
 
+  const bool fused_x = (c.px != nullptr);
+  if (fused_x) {
+    if (c.out_cs != 1 || c.alpha_sumsq != nullptr || c.col_bias != nullptr || c.sumsq_slot != nullptr ||
+        c.x_count < (size_t)(a.Mside * c.out_rs) + c.x_extra || ((c.x_count - c.x_extra) & 1) || (c.out_rs & 1) ||
+        c.ncols_out != c.nblk * 8)
+      return cudaErrorInvalidValue;
+    if (a.splits == 1) a.out = c.px->mine;        // the GEMM epilogue writes my half of the symmetric region directly
+  }
   a.b_stage_bytes = (uint32_t)(kChunkK * c.ldb * 8);
   const size_t per_stage = kAStageBytes + a.b_stage_bytes;
   const size_t fixed = 1024 + 16 * 8 + 16 * 8;  // alignment slack + barriers + reduction scratch
@@ -468,6 +587,15 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   if (e != cudaSuccess) return e;
 
   int64_t n_part_used = a.tilesM;
+  if (fused_x) {
+    const int Lc = a.nblk * 8;
+    const int64_t work = std::max<int64_t>(a.Mside * (Lc / 2), (int64_t)(c.x_count / 2));
+    const int blocks = (int)std::min<int64_t>((work + 255) / 256, w.num_sms);     // all co-resident: blocks spin
+    reduce_exchange_kernel<<<blocks, 256, 0, stream>>>(a.splits > 1 ? w.ws : nullptr, a.splits, a.tilesM, Lc, a.Mside,
+                                                       c.out_rs, c.out, c.x_count, c.x_extra, *c.px, a.cond_flag);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+  }
   if (a.splits > 1) {
     const int Lc = a.nblk * 8;
     const int64_t total = a.Mside * (Lc / 2);

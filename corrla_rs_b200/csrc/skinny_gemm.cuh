@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "comm.cuh"
+
 namespace corrla {
 
 constexpr int kTileM = 128;   // output rows per work item
@@ -57,6 +59,12 @@ struct GemmCall {
   const int* cond_flag = nullptr;
   int force_splits = 0;             // testing hook: 0 = choose
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;   // optional: recorded around the DMMA kernel only
+  // Fused all-reduce over peer memory (row-sharded runs): when px != nullptr the product is summed over the ranks
+  // by the reduction kernel itself.  `out` must then be a contiguous row-major block (out_cs == 1) of x_count
+  // doubles in total, of which the last x_extra are caller-provided local values already sitting at out + x_count -
+  // x_extra (e.g. a squared norm) that ride along with the matrix.
+  const PeerExchange* px = nullptr;
+  size_t x_count = 0, x_extra = 0;
 };
 
 struct GemmWorkspace {

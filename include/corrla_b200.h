@@ -84,6 +84,7 @@ typedef struct corrla_timings {
   int pass_launches;       /* launches of the DMMA GEMM kernel that stream A (== passes_over_a) */
   double pass_ms;          /* summed CUDA-event duration of those launches (the dominant kernel) */
   double pass_flops;       /* algorithmic flops of one such launch on this GPU: 2 * local_rows * ncols * l */
+  int p2p_exchanges;       /* cross-rank sums done inside the reduction kernel over NVLink peer memory (0 => NCCL only) */
 } corrla_timings;
 
 CORRLA_API void corrla_rsvd_opts_default(corrla_rsvd_opts* opts);

@@ -51,6 +51,7 @@ pub struct corrla_timings {
     pub pass_launches: c_int,
     pub pass_ms: f64,
     pub pass_flops: f64,
+    pub p2p_exchanges: c_int,
 }
 
 extern "C" {
