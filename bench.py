@@ -142,7 +142,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -372,14 +372,30 @@ def run_ours(args):
                             (f"{tm['p2p_exchanges']} per call fused into the split-K reduction kernel over NVLink peer memory"
                              if tm["p2p_exchanges"] else "NCCL all-reduce")),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         comm.close()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else (NCCL banners, library chatter) was
+    rerouted to stderr in main()."""
+    out = os.fdopen(os.dup(_REAL_STDOUT), "w") if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL prints "NCCL version ..." on stdout from C; keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
