@@ -135,6 +135,7 @@ struct Core {
   double grows = 0;         // global row count (for the CholeskyQR shift)
   int l = 0, nblk = 0, Lc = 0, ld = 0, L16 = 0;
   double *Y = nullptr, *Za = nullptr, *Zb = nullptr, *Qz = nullptr;
+  double *SK = nullptr;      // sketch of the matrix being orthonormalised: sketch_rows(Lc) x ld
   double *G = nullptr, *T1 = nullptr, *Tf = nullptr, *Tzf = nullptr, *Wm = nullptr, *Vr = nullptr, *Ur = nullptr,
          *M1 = nullptr, *sig = nullptr, *scal = nullptr, *jscratch = nullptr;
   // flags: [0] flag3 of the current QR, [1..2] chol info (live, shifted), [3] dead-column flag of the current QR,
@@ -171,6 +172,7 @@ struct Core {
       np = std::max(np, (size_t)t);
     };
     need(m, n); need(n, m); need(Lc, m); need(m, Lc);
+    ws = std::max(ws, sketch_ws_bytes(Lc, ctx->num_sms));
     if (need_z) { need(Lc, n); need(n, Lc); need(Lc, Lc); }
     gw.num_sms = ctx->num_sms;
     gw.ws_bytes = ws;
@@ -189,10 +191,11 @@ struct Core {
     };
     Y = getz("Y", (size_t)m16 * ld);
     G = getz("G", small_elems()); T1 = getz("T1", small_elems()); Tf = getz("Tf", small_elems());
+    SK = getz("SK", (size_t)256 * ld + 128);
     scal = getz("scal", 16);
     flags = reinterpret_cast<int*>(getz("flags", 16));
     deadmask = reinterpret_cast<int*>(getz("deadmask", (size_t)L16));
-    bool ok = Y && G && T1 && Tf && scal && flags && deadmask;
+    bool ok = Y && G && T1 && Tf && scal && flags && deadmask && SK;
     if (need_z) {
       Za = getz("Za", (size_t)n16 * ld + 256); Zb = getz("Zb", (size_t)n16 * ld + 256); Qz = getz("Qz", (size_t)n16 * ld);
       if (center) {
@@ -304,18 +307,41 @@ struct Core {
     return CORRLA_OK;
   }
 
-  // Adaptive CholeskyQR2/3 of X (rows x Lc, pitch ld), in place: on return X holds the next-to-last iterate
-  // and the orthonormal factor is X * Tfold (never formed here).  distributed: rows are sharded over comm.
+  // Sketch-preconditioned CholeskyQR of X (rows x Lc, pitch ld), in place (randomized Householder-Cholesky):
+  //   SK = S*X (sparse sign sketch, 2*Lc rows)  ->  Householder QR of SK in one CTA  ->  T1 = R^-1 (deflated)
+  //   X <- X*T1 has cond ~ 5 whatever cond(X) was (up to ~1e15), so ONE plain CholeskyQR pass (Gram -> Cholesky)
+  //   finishes: on return the orthonormal factor is X * Tfold (never formed here).
+  // A second CholeskyQR pass runs only if the pivot ratio says the embedding was unlucky (device flag, no host trip).
+  // distributed: rows are sharded over comm; the sketch and the Gram matrices are summed over the ranks.
   int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold) {
     const MatView vx = view_rows(X, rows);
     const size_t gcount = (size_t)Lc * ld;
     const size_t gx = distributed ? gcount : 0;       // Gram matrices are summed over the ranks inside the reduction kernel
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholAuto, rows_for_shift, T1, nullptr));
+    const int s_rows = sketch_rows(Lc);
+    const int s_pad = (s_rows + 127) / 128 * 128;
+    {
+      int grid = 0;
+      cudaError_t e = sketch_launch(X, rows, Lc, ld, refill_seed + 0x5ce7c4ull * (uint64_t)(qr_calls + 1), refill_stream,
+                                    gw.ws, gw.num_sms, &grid, nullptr, st);
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("sketch launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      const size_t xs = (size_t)s_rows * ld;
+      PeerExchange px;
+      const bool multi = distributed && comm != nullptr && comm->nranks > 1;
+      const bool fused = multi && comm->next_exchange(xs, &px);
+      if (fused) ++p2p_exchanges;
+      e = reduce_partials_launch(gw.ws, grid, s_pad, Lc, s_rows, SK, ld, fused ? &px : nullptr, xs, nullptr, gw.num_sms, st,
+                                 &launches);
+      if (e != cudaSuccess) { set_last_error("sketch reduction failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      if (multi && !fused) ST_TRY(allreduce(SK, xs));
+      e = hqr_inv_launch(SK, ld, s_rows, l, T1, L16, ld, flags + 1, deadmask, flags + 3, nullptr, st);
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("hqr_inv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    }
     ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, nullptr, 1));
     ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, nullptr));
-    // third pass, only when the first one had to be shifted (device-side flag, no host round trip)
+    ST_TRY(chol(kCholCheck, rows_for_shift, Tfold, nullptr));
+    // second pass, only when flagged
     const int* f3 = flags + 0;
     ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, f3, 1));
     ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f3, 0, false, nullptr, gx, 0));

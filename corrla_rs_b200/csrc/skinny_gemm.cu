@@ -530,6 +530,25 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
   *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM;
 }
 
+cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, int Lc, int64_t Mside, double* out,
+                                   int64_t ld, const PeerExchange* px, size_t x_count, const int* cond_flag,
+                                   int num_sms, cudaStream_t stream, int* launches) {
+  const int tilesM = rows_pad / kTileM;
+  if (px != nullptr) {
+    if ((ld & 1) || x_count < (size_t)(Mside * ld) || (x_count & 1)) return cudaErrorInvalidValue;
+    const int64_t work = std::max<int64_t>(Mside * (Lc / 2), (int64_t)(x_count / 2));
+    const int blocks = (int)std::min<int64_t>((work + 255) / 256, num_sms);
+    reduce_exchange_kernel<<<blocks, 256, 0, stream>>>(ws, splits, tilesM, Lc, Mside, ld, out, x_count, 0, *px, cond_flag);
+  } else {
+    const int64_t total = Mside * (Lc / 2);
+    const int blocks = (int)((total + 255) / 256);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, tilesM, Lc, Mside, out, ld, 1, Lc, nullptr, nullptr,
+                                                     nullptr, cond_flag);
+  }
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t stream, int* launches) {
   GemmArgs a{};
   const bool kc = c.reduce_inner;

@@ -82,4 +82,10 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
 
 bool tma_compatible(const MatView& v);
 
+// Sum `splits` partial blocks laid out like the split-K workspace ([split][rows_pad][Lc], rows_pad a multiple of 128)
+// into out (row-major, pitch ld, Mside valid rows); with px != nullptr the sum also runs over the ranks (x_count doubles).
+cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, int Lc, int64_t Mside, double* out,
+                                   int64_t ld, const PeerExchange* px, size_t x_count, const int* cond_flag,
+                                   int num_sms, cudaStream_t stream, int* launches = nullptr);
+
 }  // namespace corrla

@@ -175,6 +175,10 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
       shifted = 1;
     }
     if (tid == 0 && flag3 != nullptr) *flag3 = shifted;
+  } else if (mode == kCholCheck) {
+    // after the sketch preconditioner cond(Y) is O(1); a small pivot ratio means the embedding was unlucky (or columns
+    // were deflated): ask for one more CholeskyQR pass
+    if (tid == 0 && flag3 != nullptr) *flag3 = (st.minratio < 1e-3) ? 1 : 0;
   }
   __syncthreads();
 #pragma unroll
@@ -414,6 +418,185 @@ repack_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
+// sparse sign sketch
+// ------------------------------------------------------------------------------------------------
+constexpr int kSketchTile = 64;
+__constant__ int kSketchMul[kSketchZeta] = {1, 17, 19, 23, 29, 31, 37, 41};   // coprime with 16 * nblk, nblk <= 16
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// 1024 threads: column c = tid & 127 (idle if c >= Lc), row lane rj = tid >> 7 handles tile rows rj, rj + 8, ...
+__global__ void __launch_bounds__(1024, 1)
+sketch_kernel(const double* __restrict__ Y, int64_t rows, int Lc, int64_t ld, int s_rows, uint64_t seed,
+              uint64_t stream_id, double* __restrict__ partials, int rows_pad, const int* cond_flag) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  extern __shared__ double acc[];                      // s_rows x Lc
+  const int tid = threadIdx.x;
+  const int c = tid & 127, rj = tid >> 7;
+  for (int i = tid; i < s_rows * Lc; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const int64_t tiles = (rows + kSketchTile - 1) / kSketchTile;
+  const int64_t per = (tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = min(tiles, t_begin + per);
+  const bool active = c < Lc;
+  const float inv_s = 1.0f / (float)s_rows;
+  const uint64_t key = seed ^ (stream_id * 0xD1B54A32D192ED03ull) ^ ((uint64_t)blockIdx.x << 48);
+  double cur[8], nxt[8];
+  auto load_tile = [&](int64_t tile, double (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t r = tile * kSketchTile + rj + 8 * k;
+      v[k] = (active && r < rows) ? Y[r * ld + c] : 0.0;
+    }
+  };
+  if (t_begin < t_end) load_tile(t_begin, cur);
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    if (tile + 1 < t_end) load_tile(tile + 1, nxt);
+#pragma unroll 1
+    for (int t = 0; t < kSketchZeta; ++t) {
+      const uint64_t h = splitmix64(key + (uint64_t)(tile - t_begin) * kSketchZeta + t);
+      const uint64_t signs = splitmix64(h);
+      const int off = (int)(h % (uint64_t)s_rows);
+      const int mul = kSketchMul[t];
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = rj + 8 * k;
+          int x = mul * j + off;
+          x -= s_rows * (int)((float)x * inv_s);
+          if (x < 0) x += s_rows;
+          if (x >= s_rows) x -= s_rows;
+          const double v = ((signs >> j) & 1ull) ? cur[k] : -cur[k];
+          acc[x * Lc + c] += v;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+  }
+  double* dst = partials + (int64_t)blockIdx.x * rows_pad * Lc;
+  for (int i = tid; i < rows_pad * Lc; i += blockDim.x) dst[i] = (i < s_rows * Lc) ? acc[i] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder QR of the sketch + deflated triangular inverse, one CTA, sketch resident in shared memory
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+hqr_inv_kernel(const double* __restrict__ SK, int ldsk, int s_rows, int l, double* __restrict__ T, int Lrows, int ldt,
+               int* info, int* deadmask, int* flag_dead, const int* cond_flag) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  extern __shared__ double hsm[];
+  const int sp = s_rows | 1;                            // odd pitch: conflict-free both along rows and across columns
+  double* Ac = hsm;                                     // column-major: Ac[c*sp + r]
+  double* cn0 = Ac + (size_t)l * sp;                    // original column norms
+  double* vwork = cn0 + l;                              // l: column of R being inverted
+  double* bc = vwork + l;                               // [0] tau
+  int* rowof = reinterpret_cast<int*>(bc + 4);          // l: R row assigned to column j, or -1 (dead)
+  int* live = rowof + l;                                // compact list of live columns
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const double tol = 8.0 * l * DBL_EPSILON;
+
+  for (int idx = tid; idx < s_rows * l; idx += nt) {
+    const int r = idx / l, c = idx - r * l;
+    Ac[c * sp + r] = SK[(int64_t)r * ldsk + c];
+  }
+  __syncthreads();
+  for (int c = warp; c < l; c += nw) {
+    double a = 0.0;
+    for (int r = lane; r < s_rows; r += 32) { const double x = Ac[c * sp + r]; a += x * x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) cn0[c] = sqrt(a);
+  }
+  __syncthreads();
+
+  // ---- Householder sweeps; `rk` = next free row of R (does not advance on a dead column)
+  int rk = 0;
+  for (int j = 0; j < l; ++j) {
+    if (warp == 0) {
+      double* x = Ac + j * sp;
+      double sig = 0.0;
+      for (int r = rk + 1 + lane; r < s_rows; r += 32) sig += x[r] * x[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(0xffffffffu, sig, o);
+      const double alpha = (rk < s_rows) ? x[rk] : 0.0;
+      const double nrm = sqrt(alpha * alpha + sig);
+      const bool dead = (rk >= s_rows) || !(nrm > tol * cn0[j]) || !(cn0[j] > 0.0);
+      double tau = 0.0;
+      if (!dead) {
+        const double beta = (alpha >= 0.0) ? -nrm : nrm;
+        tau = (beta - alpha) / beta;
+        const double scal = 1.0 / (alpha - beta);
+        for (int r = rk + 1 + lane; r < s_rows; r += 32) x[r] *= scal;     // v (v[rk] = 1 implied)
+        if (lane == 0) x[rk] = beta;                                       // R[rk][j]
+      }
+      if (lane == 0) { bc[0] = tau; rowof[j] = dead ? -1 : rk; }
+    }
+    __syncthreads();
+    const double tau = bc[0];
+    const bool dead = rowof[j] < 0;
+    if (!dead) {
+      const double* v = Ac + j * sp;
+      for (int k = j + 1 + warp; k < l; k += nw) {
+        double* y = Ac + k * sp;
+        double w = 0.0;
+        for (int r = rk + 1 + lane; r < s_rows; r += 32) w += v[r] * y[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        w = (w + y[rk]) * tau;
+        for (int r = rk + 1 + lane; r < s_rows; r += 32) y[r] -= w * v[r];
+        __syncwarp();
+        if (lane == 0) y[rk] -= w;
+      }
+      ++rk;
+    }
+    __syncthreads();
+  }
+  const int rank = rk;
+  if (tid == 0) {
+    int n = 0;
+    for (int j = 0; j < l; ++j) if (rowof[j] >= 0) live[n++] = j;
+  }
+  __syncthreads();
+
+  // ---- invert the rank x rank upper-triangular R_c[a][b] = Ac[live[b]*sp + a] in place, column by column
+  for (int b = 0; b < rank; ++b) {
+    double* colb = Ac + live[b] * sp;
+    const double tbb = 1.0 / colb[b];
+    for (int a = tid; a < b; a += nt) vwork[a] = colb[a];
+    __syncthreads();
+    for (int a = warp; a < b; a += nw) {
+      double dot = 0.0;
+      for (int k = a + lane; k < b; k += 32) dot += Ac[live[k] * sp + a] * vwork[k];   // T_c[a][k], already inverted
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane == 0) colb[a] = -dot * tbb;
+    }
+    if (tid == 0) colb[b] = tbb;
+    __syncthreads();
+  }
+  // T[live[a]][live[b]] = T_c[a][b], a <= b; zero elsewhere
+  for (int idx = tid; idx < Lrows * ldt; idx += nt) T[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < rank * rank; idx += nt) {
+    const int a = idx / rank, b = idx - a * rank;
+    if (a <= b) T[(int64_t)live[a] * ldt + live[b]] = Ac[live[b] * sp + a];
+  }
+  if (tid == 0) {
+    if (info != nullptr) { info[0] = rank; info[1] = 0; }
+    if (flag_dead != nullptr) *flag_dead = (rank < l) ? 1 : 0;
+  }
+  if (deadmask != nullptr)
+    for (int j = tid; j < l; j += nt) deadmask[j] = rowof[j] < 0 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // column statistics / rank-1 corrections
 // ------------------------------------------------------------------------------------------------
 constexpr int kSumRowsPerBlock = 4096;
@@ -508,6 +691,51 @@ center_copy_kernel(const double* __restrict__ src, int64_t inner, int64_t outer,
 }
 
 }  // namespace
+
+int sketch_rows(int Lc) {
+  // s = 2*Lc buckets, capped so that both the s x Lc accumulator of the sketch kernel and the l x s panel of the
+  // Householder kernel fit in shared memory; always a multiple of 16 with prime factors <= 13 (coprime with kSketchMul)
+  int s = std::max(2 * Lc, 64);
+  const int cap = (int)((size_t)220 * 1024 / ((size_t)Lc * 8));
+  if (s > cap) s = cap / 16 * 16;
+  return s;
+}
+size_t sketch_ws_bytes(int Lc, int num_sms) {
+  const int rows_pad = (sketch_rows(Lc) + 127) / 128 * 128;
+  return (size_t)num_sms * rows_pad * Lc * 8;
+}
+cudaError_t sketch_launch(const double* Y, int64_t rows, int Lc, int64_t ld, uint64_t seed, uint64_t stream_id,
+                          double* partials, int num_sms, int* grid_out, const int* cond_flag, cudaStream_t s) {
+  const int s_rows = sketch_rows(Lc);
+  const int rows_pad = (s_rows + 127) / 128 * 128;
+  const size_t smem = (size_t)s_rows * Lc * 8;
+  if (Lc > 128 || smem > 227 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int64_t tiles = (rows + kSketchTile - 1) / kSketchTile;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, num_sms));
+  sketch_kernel<<<grid, 1024, smem, s>>>(Y, rows, Lc, ld, s_rows, seed, stream_id, partials, rows_pad, cond_flag);
+  if (grid_out) *grid_out = grid;
+  return cudaGetLastError();
+}
+cudaError_t hqr_inv_launch(const double* SK, int ldsk, int s_rows, int l, double* T, int Lrows, int ldt, int* info,
+                           int* deadmask, int* flag_dead, const int* cond_flag, cudaStream_t s) {
+  const int sp = s_rows | 1;
+  const size_t smem = ((size_t)l * sp + 2 * (size_t)l + 4) * 8 + 2 * (size_t)l * 4 + 16;
+  if (smem > 226 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(hqr_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  hqr_inv_kernel<<<1, 1024, smem, s>>>(SK, ldsk, s_rows, l, T, Lrows, ldt, info, deadmask, flag_dead, cond_flag);
+  return cudaGetLastError();
+}
 
 int sum_blocks(int64_t outer) { return (int)((outer + kSumRowsPerBlock - 1) / kSumRowsPerBlock); }
 

@@ -11,7 +11,7 @@ namespace corrla {
 // regenerates the same matrix without a broadcast.  oracle/ref_rsvd.py:philox_normal restates it.
 cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld, uint64_t seed, cudaStream_t s);
 
-enum CholMode { kCholAuto = 0, kCholPlain = 1 };
+enum CholMode { kCholAuto = 0, kCholPlain = 1, kCholCheck = 2 };   // kCholCheck: plain, and *flag3 = (min pivot ratio < 1e-3)
 
 // Upper Cholesky G = R^T R of the l x l Gram matrix (row-major, pitch ldg) in shared memory, then the
 // "deflated" inverse T = R^-1 (columns whose pivot vanished are zero, so Q = Y*T has exact zero columns there).
@@ -44,6 +44,26 @@ cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t
 // dst[i*drs + j*dcs] = src[i*ld + j]  (scatter a padded row-major matrix to arbitrary output strides)
 cudaError_t scatter_launch(const double* src, int64_t rows, int64_t cols, int64_t ld, double* dst, int64_t drs,
                            int64_t dcs, cudaStream_t s);
+
+// ---- sketch-preconditioned CholeskyQR (randomized Householder-Cholesky, Higgins et al. 2023) ------------------------
+// Sparse sign embedding of the tall matrix Y (rows x Lc, pitch ld): each row is added, with a random sign, to
+// kSketchZeta of the s buckets.  Rows are taken in tiles of 64; inside a tile hash t sends row j to bucket
+// (a_t * j + offset(tile, t)) mod s with a_t coprime to s, an injection, so one (tile, t) step updates 64 distinct
+// bucket rows and needs neither atomics nor a fixed summation tree: the result is bit-reproducible.
+// Every CTA writes its partial sketch into `partials` in the split-K workspace layout [cta][sketch_tiles*128][Lc], so the
+// ordinary split-K reduction (and its fused cross-GPU variant) finishes the job.  Returns the grid size used.
+constexpr int kSketchZeta = 8;
+int sketch_rows(int Lc);                     // s = 2 * Lc
+size_t sketch_ws_bytes(int Lc, int num_sms);
+cudaError_t sketch_launch(const double* Y, int64_t rows, int Lc, int64_t ld, uint64_t seed, uint64_t stream_id,
+                          double* partials, int num_sms, int* grid_out, const int* cond_flag, cudaStream_t s);
+
+// Householder QR of the s x l sketch SK (row-major, pitch ldsk) in shared memory, column-relative rank test, then the
+// deflated inverse T = R^-1 (l x l upper triangular on the live columns, zero columns where dead), written as
+// Lrows x ldt like chol_inv.  Y * T is then well conditioned (cond ~ 5) whatever cond(Y) was, and one plain
+// CholeskyQR pass finishes the orthonormalisation.  deadmask / flag_dead / info as in chol_inv_launch.
+cudaError_t hqr_inv_launch(const double* SK, int ldsk, int s_rows, int l, double* T, int Lrows, int ldt, int* info,
+                           int* deadmask, int* flag_dead, const int* cond_flag, cudaStream_t s);
 
 // ---- column statistics and rank-1 corrections for on-the-fly centring (PCA: pca_rsvd.rs:60-66) ----------------
 // out[i] = sum over o < outer of p[o*ld + i], i < inner  (column sums of a row-major matrix).  Deterministic:

@@ -1,7 +1,8 @@
 """CPU model of the B200 engine's *algorithm* (not of the reference) -- TEST INFRASTRUCTURE ONLY.
 
 corrla_rs_b200/csrc/engine.cu reorganises random_svd.rs:15-110 so that it maps onto skinny GEMMs and
-small replicated factors: CholeskyQR2/3 with a deflated triangular inverse instead of Householder QR,
+small replicated factors: sketch-preconditioned CholeskyQR (sparse sign sketch -> Householder QR of the small sketch ->
+one CholeskyQR pass) with a deflated triangular inverse instead of Householder QR of the tall matrix,
 R^-1 folded into the small side, the Frobenius scaling deferred into the next product, QR-preconditioned
 one-sided Jacobi for the SVD of B, and row sharding with all-reduces of Z = A^T Y and of the Gram matrices.
 This file restates that reorganisation in numpy so that
@@ -75,19 +76,67 @@ def chol_inv(g: np.ndarray, mode_auto: bool, global_rows: float):
     return t, shifted, dead
 
 
-def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None):
-    """Adaptive CholeskyQR2/3 with refill of numerically dependent columns (they are replaced by fresh
-    Gaussian vectors and re-orthonormalised, which is what a Householder QR's arbitrary completion amounts to).
-    Returns (x_last, t_fold, shifted, live): the orthonormal factor is x_last @ t_fold."""
-    g = distributed_allreduce(x.T @ x)
-    t1, shifted, _ = chol_inv(g, True, global_rows)
+SKETCH_ZETA = 8
+SKETCH_TILE = 64
+SKETCH_MUL = (1, 17, 19, 23, 29, 31, 37, 41)
+
+
+def sketch_rows(lc: int) -> int:
+    s = max(2 * lc, 64)
+    cap = (220 * 1024) // (lc * 8)
+    if s > cap:
+        s = cap // 16 * 16
+    return s
+
+
+def sparse_sign_sketch(x: np.ndarray, s: int, rng: np.random.Generator) -> np.ndarray:
+    """Structured sparse sign embedding of sketch_kernel (small_kernels.cu): rows in tiles of 64; in a tile, hash t sends
+    row j to bucket (a_t * j + offset) mod s (an injection) with a random sign.  The hash bits differ from the CUDA
+    kernel's (splitmix64 there), the structure and the statistics are the same."""
+    m, l = x.shape
+    out = np.zeros((s, l))
+    for b in range((m + SKETCH_TILE - 1) // SKETCH_TILE):
+        rows = np.arange(b * SKETCH_TILE, min(m, (b + 1) * SKETCH_TILE))
+        j = rows - b * SKETCH_TILE
+        for t in range(SKETCH_ZETA):
+            bucket = (SKETCH_MUL[t] * j + int(rng.integers(0, s))) % s
+            sign = rng.integers(0, 2, size=len(rows)) * 2.0 - 1.0
+            out[bucket] += sign[:, None] * x[rows]          # buckets are distinct within one (tile, t) step
+    return out
+
+
+def hqr_inv(sk: np.ndarray):
+    """Householder R of the sketch with a column-relative rank test, then the deflated inverse (hqr_inv_kernel)."""
+    l = sk.shape[1]
+    r0 = np.linalg.qr(sk, mode="r") if sk.shape[0] >= l else np.linalg.qr(np.vstack([sk, np.zeros((l - sk.shape[0], l))]), mode="r")
+    cn = np.linalg.norm(sk, axis=0)
+    dead = ~(np.abs(np.diag(r0)) > TOL_DEAD_PER_COL * l * cn) | ~(cn > 0.0)
+    live = np.flatnonzero(~dead)
+    t = np.zeros((l, l))
+    if live.size:
+        # staircase: the live columns restricted to their own rows form an upper-triangular block
+        rl = np.linalg.qr(sk[:, live], mode="r")
+        t[np.ix_(live, live)] = np.triu(np.linalg.solve(rl, np.eye(live.size)))
+    return t, dead
+
+
+def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None):
+    """Sketch-preconditioned CholeskyQR with refill of numerically dependent columns (Core::qr_inplace in engine.cu).
+    Returns (x_last, t_fold, second_pass, live): the orthonormal factor is x_last @ t_fold."""
+    lc = (x.shape[1] + 7) // 8 * 8
+    sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), sketch_rng or np.random.default_rng(777)))
+    t1, dead = hqr_inv(sk)
     x = x @ t1
     g = distributed_allreduce(x.T @ x)
-    tf, _, dead = chol_inv(g, False, global_rows)
-    if shifted:
+    d0 = np.diag(g).copy()
+    _, dead_c, minratio = chol_factor(g, d0, False, TOL_DEAD_PER_COL * x.shape[1])
+    tf, _, dead2 = chol_inv(g, False, global_rows)
+    second = minratio < 1e-3
+    if second:
         x = x @ tf
         g = distributed_allreduce(x.T @ x)
-        tf, _, dead = chol_inv(g, False, global_rows)
+        tf, _, dead2 = chol_inv(g, False, global_rows)
+    dead = dead | dead2
     if dead.any():
         rng = refill_rng or np.random.default_rng(12345)
         x = x @ tf
@@ -97,7 +146,7 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
         x = x @ t1
         g = distributed_allreduce(x.T @ x)
         tf, _, dead = chol_inv(g, False, global_rows)
-    return x, tf, shifted, int(np.sum(~dead))
+    return x, tf, second, int(np.sum(~dead))
 
 
 def jacobi_svd(w: np.ndarray, max_sweeps: int = 60):
