@@ -218,9 +218,11 @@ struct Core {
 
   int mm(const MatView& a, bool reduce_inner, const double* B, double* out, int64_t ors, int64_t ocs, int ncols_out,
          const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0,
-         bool is_pass = false, const double* col_bias = nullptr, size_t x_count = 0, size_t x_extra = 0) {
+         bool is_pass = false, const double* col_bias = nullptr, size_t x_count = 0, size_t x_extra = 0,
+         bool accumulate = false) {
     GemmCall c{};
     c.col_bias = col_bias;
+    c.accumulate = accumulate;
     // cross-rank sum of the product: fused into the reduction kernel over peer memory when possible, else NCCL
     PeerExchange px;
     bool nccl_after = false;
@@ -297,70 +299,83 @@ struct Core {
     return comm->allreduce_f64(buf, count, st);
   }
 
-  // main-phase factorisations publish liveness (flags[1..3], deadmask); refill-phase ones must not clobber them
-  int chol(int mode, double rows_for_shift, double* T, const int* cond, bool refill_phase = false) {
-    cudaError_t e = refill_phase
-        ? chol_inv_launch(G, ld, l, T, L16, ld, mode, rows_for_shift, nullptr, flags + 12, scal + 9, nullptr, flags + 14, cond, st)
-        : chol_inv_launch(G, ld, l, T, L16, ld, mode, rows_for_shift, flags + 0, flags + 1, scal + 8, deadmask, flags + 3, cond, st);
+  // Cholesky + inverse of G -> T.  quiet: do not publish liveness (deadmask / flags[1..3]); f2: where kCholCheck
+  // writes its "one more pass" flag.
+  int chol(int mode, double rows_for_shift, double* T, const int* cond, bool quiet = false, int* f2 = nullptr) {
+    cudaError_t e = quiet
+        ? chol_inv_launch(G, ld, l, T, L16, ld, mode, rows_for_shift, f2, flags + 12, scal + 9, nullptr, flags + 14, cond, st)
+        : chol_inv_launch(G, ld, l, T, L16, ld, mode, rows_for_shift, f2 ? f2 : flags + 0, flags + 1, scal + 8, deadmask, flags + 3, cond, st);
     ++launches;
     if (e != cudaSuccess) { set_last_error("chol_inv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
     return CORRLA_OK;
   }
 
-  // Sketch-preconditioned CholeskyQR of X (rows x Lc, pitch ld), in place (randomized Householder-Cholesky):
-  //   SK = S*X (sparse sign sketch, 2*Lc rows)  ->  Householder QR of SK in one CTA  ->  T1 = R^-1 (deflated)
-  //   X <- X*T1 has cond ~ 5 whatever cond(X) was (up to ~1e15), so ONE plain CholeskyQR pass (Gram -> Cholesky)
-  //   finishes: on return the orthonormal factor is X * Tfold (never formed here).
-  // A second CholeskyQR pass runs only if the pivot ratio says the embedding was unlucky (device flag, no host trip).
-  // distributed: rows are sharded over comm; the sketch and the Gram matrices are summed over the ranks.
-  int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold) {
+  // One sketch-preconditioned CholeskyQR stage on X (rows x Lc, pitch ld), in place; every kernel of the stage is
+  // skipped on the device when cond != nullptr and *cond == 0.
+  //   SK = S*X (sparse sign sketch)  ->  Householder QR of SK in one CTA  ->  T1 = R^-1 (deflated)  ->  X <- X*T1
+  //   (cond ~ 5 whatever cond(X) was, up to ~1e15)  ->  Gram  ->  Cholesky  ->  Tfold;  Q = X*Tfold is never formed.
+  // A second CholeskyQR pass runs only if the pivot ratio says the embedding was unlucky (device flag f2).
+  int qr_stage(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold, const int* cond,
+               int* f2, bool refill_phase) {
     const MatView vx = view_rows(X, rows);
-    const size_t gcount = (size_t)Lc * ld;
-    const size_t gx = distributed ? gcount : 0;       // Gram matrices are summed over the ranks inside the reduction kernel
+    const size_t gx = distributed ? (size_t)Lc * ld : 0;   // Gram matrices are summed over the ranks in the reduction kernel
     const int s_rows = sketch_rows(Lc);
     const int s_pad = (s_rows + 127) / 128 * 128;
-    {
-      int grid = 0;
-      cudaError_t e = sketch_launch(X, rows, Lc, ld, refill_seed + 0x5ce7c4ull * (uint64_t)(qr_calls + 1), refill_stream,
-                                    gw.ws, gw.num_sms, &grid, nullptr, st);
-      ++launches;
-      if (e != cudaSuccess) { set_last_error("sketch launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-      const size_t xs = (size_t)s_rows * ld;
-      PeerExchange px;
-      const bool multi = distributed && comm != nullptr && comm->nranks > 1;
-      const bool fused = multi && comm->next_exchange(xs, &px);
-      if (fused) ++p2p_exchanges;
-      e = reduce_partials_launch(gw.ws, grid, s_pad, Lc, s_rows, SK, ld, fused ? &px : nullptr, xs, nullptr, gw.num_sms, st,
-                                 &launches);
-      if (e != cudaSuccess) { set_last_error("sketch reduction failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-      if (multi && !fused) ST_TRY(allreduce(SK, xs));
-      e = hqr_inv_launch(SK, ld, s_rows, l, T1, L16, ld, flags + 1, deadmask, flags + 3, nullptr, st);
-      ++launches;
-      if (e != cudaSuccess) { set_last_error("hqr_inv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-    }
-    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, nullptr, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholCheck, rows_for_shift, Tfold, nullptr));
-    // second pass, only when flagged
-    const int* f3 = flags + 0;
-    ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, f3, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f3, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, f3));
-    // Refill, only when columns were deflated as numerically dependent: form Q (zero columns where dead), overwrite
-    // those columns with fresh Gaussian vectors and run CholeskyQR2 again -- the arbitrary completion a Householder
-    // QR would return (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
+    int grid = 0;
+    cudaError_t e = sketch_launch(X, rows, Lc, ld, refill_seed + 0x5ce7c4ull * (uint64_t)(2 * qr_calls + (refill_phase ? 2 : 1)),
+                                  refill_stream, gw.ws, gw.num_sms, &grid, cond, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("sketch launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    const size_t xs = (size_t)s_rows * ld;
+    PeerExchange px;
+    const bool multi = distributed && comm != nullptr && comm->nranks > 1;
+    const bool fused = multi && comm->next_exchange(xs, &px);
+    if (fused) ++p2p_exchanges;
+    e = reduce_partials_launch(gw.ws, grid, s_pad, Lc, s_rows, SK, ld, fused ? &px : nullptr, xs, cond, gw.num_sms, st, &launches);
+    if (e != cudaSuccess) { set_last_error("sketch reduction failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    if (multi && !fused) ST_TRY(allreduce(SK, xs));
+    // main phase publishes liveness (flags[1..3], deadmask); the refill phase must not clobber it
+    e = refill_phase ? hqr_inv_launch(SK, ld, s_rows, l, T1, L16, ld, flags + 12, nullptr, flags + 14, cond, st)
+                     : hqr_inv_launch(SK, ld, s_rows, l, T1, L16, ld, flags + 1, deadmask, flags + 3, cond, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("hqr_inv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, cond, 1));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, cond, 0, false, nullptr, gx, 0));
+    ST_TRY(chol(kCholCheck, rows_for_shift, Tfold, cond, true, f2));
+    ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, f2, 1));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f2, 0, false, nullptr, gx, 0));
+    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, f2, true, nullptr));
+    return CORRLA_OK;
+  }
+
+  // Thin-Q factor of X in place: on return the orthonormal factor is X * Tfold (never formed here).
+  // distributed: rows are sharded over comm.  refill_from_a: X is A times something, so directions lost to numerical
+  // rank deficiency are replaced by fresh vectors from range(A) instead of arbitrary ones.
+  int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold,
+                 bool refill_from_a = false) {
+    const MatView vx = view_rows(X, rows);
+    CU_TRY(cudaMemsetAsync(flags + 6, 0, sizeof(int), st));      // the refill stage's "one more pass" flag starts clear
+    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, nullptr, flags + 0, false));
+    // Refill, only when columns were deflated as numerically dependent (device flag): form Q (zero columns where dead),
+    // put fresh vectors into those columns and orthonormalise again -- the completion a Householder QR would return
+    // (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
     const int* fd = flags + 3;
     ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, fd, 1));
-    {
+    if (refill_from_a && Za != nullptr) {
+      // X[:, dead] += A * Omega', Omega' Gaussian in the dead columns and zero elsewhere (Za is free while Y is being
+      // orthonormalised).  Householder's completion of a numerically rank-deficient Y is rounding noise of A*(...),
+      // which lies in range(A) too; vectors from outside it would waste the slots.
+      CU_TRY(cudaMemsetAsync(Za, 0, (size_t)n16 * ld * 8, st));
+      cudaError_t e = refill_dead_launch(Za, n, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, 0, fd, st);
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      ST_TRY(mm(av, a_rowmajor, Za, X, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, 0, 0, true));
+    } else {
       cudaError_t e = refill_dead_launch(X, rows, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, refill_stream, fd, st);
       ++launches;
       if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
     }
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholPlain, rows_for_shift, T1, fd, true));
-    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, fd, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, gx, 0));
-    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, fd, true));
+    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, fd, flags + 6, true));
     count_third_pass();
     ++qr_calls;
     return CORRLA_OK;
@@ -381,7 +396,7 @@ struct Core {
     for (int i = 0; i < n_iter; ++i) {                        // :35
       const bool do_qr = (schedule == 1) || (i > 2);          // :37
       if (do_qr) {
-        ST_TRY(qr_inplace(Y, m, true, grows, Tf));            // :38
+        ST_TRY(qr_inplace(Y, m, true, grows, Tf, true));      // :38
         ST_TRY(mm_AtY(Y, Zb));                                // :42-46 (on the pre-fold iterate), all-reduced
         ST_TRY(mm(view_rows(Zb, n), true, Tf, Za, ld, 1, Lc)); // fold R^-1 into the small side
         ST_TRY(mm_AX(Za, Y, nullptr, nu2));                   // :47-51
@@ -390,13 +405,13 @@ struct Core {
         ST_TRY(mm_AX(Zb, Y, nu2, nu2));                       // :47-51 with the deferred :53-55 scaling
       }
     }
-    ST_TRY(qr_inplace(Y, m, true, grows, Tf));                // :57
+    ST_TRY(qr_inplace(Y, m, true, grows, Tf, true));          // :57
     return CORRLA_OK;
   }
 };
 
 __global__ void add_flag_kernel(const int* flags, int* counters) {
-  if (flags[0]) ++counters[0];
+  if (flags[0] || flags[6]) ++counters[0];
   if (flags[3]) ++counters[1];
 }
 void Core::count_third_pass() { add_flag_kernel<<<1, 1, 0, st>>>(flags, flags + 8); ++launches; }

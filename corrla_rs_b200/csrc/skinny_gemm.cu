@@ -162,8 +162,12 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
               double v0 = acc[i][j][0], v1 = acc[i][j][1];
               if (p.col_bias != nullptr) { v0 -= p.col_bias[col]; v1 -= p.col_bias[col + 1]; }
               v0 *= alpha; v1 *= alpha;
-              ss += v0 * v0 + v1 * v1;
               double* o = p.out + row * p.out_rs + (int64_t)col * p.out_cs;
+              if (p.accumulate) {
+                if (col < p.ncols_out) v0 += o[0];
+                if (col + 1 < p.ncols_out) v1 += o[p.out_cs];
+              }
+              ss += v0 * v0 + v1 * v1;
               if (p.out_cs == 1 && (p.out_rs & 1) == 0 && col + 1 < p.ncols_out) {
                 *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
               } else {
@@ -263,7 +267,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside,
                      double* __restrict__ out, int64_t out_rs, int64_t out_cs, int ncols_out,
-                     const double* alpha_sumsq, const double* col_bias, double* sumsq_partials, const int* cond_flag) {
+                     const double* alpha_sumsq, const double* col_bias, double* sumsq_partials, const int* cond_flag,
+                     int accumulate) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
   __shared__ double red[8];
   const int half = Lc >> 1;
@@ -285,8 +290,12 @@ splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int 
     }
     if (col_bias != nullptr) { s0 -= col_bias[col]; s1 -= col_bias[col + 1]; }
     s0 *= alpha; s1 *= alpha;
-    ss = s0 * s0 + s1 * s1;
     double* o = out + r * out_rs + (int64_t)col * out_cs;
+    if (accumulate) {
+      if (col < ncols_out) s0 += o[0];
+      if (col + 1 < ncols_out) s1 += o[out_cs];
+    }
+    ss = s0 * s0 + s1 * s1;
     if (col < ncols_out) o[0] = s0;
     if (col + 1 < ncols_out) o[out_cs] = s1;
   }
@@ -543,7 +552,7 @@ cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, i
     const int64_t total = Mside * (Lc / 2);
     const int blocks = (int)((total + 255) / 256);
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, tilesM, Lc, Mside, out, ld, 1, Lc, nullptr, nullptr,
-                                                     nullptr, cond_flag);
+                                                     nullptr, cond_flag, 0);
   }
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -558,6 +567,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   a.out = c.out; a.out_rs = c.out_rs; a.out_cs = c.out_cs; a.ncols_out = c.ncols_out;
   a.alpha_sumsq = c.alpha_sumsq;
   a.col_bias = c.col_bias;
+  a.accumulate = c.accumulate ? 1 : 0;
   a.cond_flag = c.cond_flag;
   if (c.nblk < 1 || c.nblk > kMaxNblk || (c.ldb % 8) != 4 || c.ldb < c.nblk * 8) return cudaErrorInvalidValue;
   if (!tma_compatible(c.a)) return cudaErrorInvalidValue;
@@ -573,7 +583,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
 
   const bool fused_x = (c.px != nullptr);
   if (fused_x) {
-    if (c.out_cs != 1 || c.alpha_sumsq != nullptr || c.col_bias != nullptr || c.sumsq_slot != nullptr ||
+    if (c.out_cs != 1 || c.alpha_sumsq != nullptr || c.col_bias != nullptr || c.sumsq_slot != nullptr || c.accumulate ||
         c.x_count < (size_t)(a.Mside * c.out_rs) + c.x_extra || ((c.x_count - c.x_extra) & 1) || (c.out_rs & 1) ||
         c.ncols_out != c.nblk * 8)
       return cudaErrorInvalidValue;
@@ -621,7 +631,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
     const int blocks = (int)((total + 255) / 256);
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(w.ws, a.splits, a.tilesM, Lc, a.Mside, a.out, a.out_rs, a.out_cs,
                                                      a.ncols_out, a.alpha_sumsq, a.col_bias,
-                                                     c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag);
+                                                     c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag, a.accumulate);
     if (launches) ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

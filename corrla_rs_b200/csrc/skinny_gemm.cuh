@@ -41,6 +41,7 @@ struct GemmArgs {
   const double* alpha_sumsq;
   // out = alpha * (acc - col_bias[col]) when non-null (rank-1 centring correction: 1 * (mu^T X))
   const double* col_bias;
+  int accumulate;          // out += alpha * (acc - bias) instead of out = ...
   // per-work-item (splits==1) sum of squares of the scaled output, or null
   double* sumsq_partials;
   // when non-null and *cond_flag == 0 the kernel does nothing
@@ -55,6 +56,7 @@ struct GemmCall {
   double* out; int64_t out_rs, out_cs; int ncols_out;
   const double* alpha_sumsq = nullptr;
   const double* col_bias = nullptr;
+  bool accumulate = false;          // out += product (used to refill deflated columns with fresh A*omega vectors)
   double* sumsq_slot = nullptr;     // if set: *sumsq_slot = sum of squares of the (scaled) output
   const int* cond_flag = nullptr;
   int force_splits = 0;             // testing hook: 0 = choose
