@@ -430,55 +430,78 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-// 1024 threads: column c = tid & 127 (idle if c >= Lc), row lane rj = tid >> 7 handles tile rows rj, rj + 8, ...
+// 1024 threads: column pair cp = tid & 63 (columns 2cp, 2cp+1; idle if 2cp >= Lc), row lane rj = tid >> 6 handles the
+// tile rows rj, rj + 16, rj + 32, rj + 48.  The per-(tile, hash) bucket offset and sign word are drawn by 8 threads
+// one tile ahead and shared through a small table; bucket indices advance incrementally (no division in the loop).
 __global__ void __launch_bounds__(1024, 1)
 sketch_kernel(const double* __restrict__ Y, int64_t rows, int Lc, int64_t ld, int s_rows, uint64_t seed,
               uint64_t stream_id, double* __restrict__ partials, int rows_pad, const int* cond_flag) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
-  extern __shared__ double acc[];                      // s_rows x Lc
+  extern __shared__ __align__(16) double acc[];        // s_rows x Lc
+  __shared__ int tab_off[2][kSketchZeta];
+  __shared__ unsigned long long tab_sign[2][kSketchZeta];
+  __shared__ int tab_step[kSketchZeta];
   const int tid = threadIdx.x;
-  const int c = tid & 127, rj = tid >> 7;
+  const int cp = tid & 63, rj = tid >> 6;
   for (int i = tid; i < s_rows * Lc; i += blockDim.x) acc[i] = 0.0;
-  __syncthreads();
   const int64_t tiles = (rows + kSketchTile - 1) / kSketchTile;
   const int64_t per = (tiles + gridDim.x - 1) / gridDim.x;
   const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = min(tiles, t_begin + per);
-  const bool active = c < Lc;
-  const float inv_s = 1.0f / (float)s_rows;
+  const bool active = 2 * cp < Lc;
   const uint64_t key = seed ^ (stream_id * 0xD1B54A32D192ED03ull) ^ ((uint64_t)blockIdx.x << 48);
-  double cur[8], nxt[8];
-  auto load_tile = [&](int64_t tile, double (&v)[8]) {
+  auto draw = [&](int64_t tile, int buf) {              // threads 0..7: hash t = tid
+    const uint64_t h = splitmix64(key + (uint64_t)(tile - t_begin) * kSketchZeta + tid);
+    tab_off[buf][tid] = (int)(((h >> 32) * (uint64_t)s_rows) >> 32);
+    tab_sign[buf][tid] = splitmix64(h);
+  };
+  // per-thread constants: first bucket of my rows and the bucket stride between them, for every hash
+  int base[kSketchZeta];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int64_t r = tile * kSketchTile + rj + 8 * k;
-      v[k] = (active && r < rows) ? Y[r * ld + c] : 0.0;
+  for (int t = 0; t < kSketchZeta; ++t) base[t] = (kSketchMul[t] * rj) % s_rows;
+  if (tid < kSketchZeta) tab_step[tid] = (kSketchMul[tid] * 16) % s_rows;
+  if (tid < kSketchZeta && t_begin < t_end) draw(t_begin, 0);
+  double2 cur[4], nxt[4];
+  auto load_tile = [&](int64_t tile, double2 (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t r = tile * kSketchTile + rj + 16 * k;
+      v[k] = (active && r < rows) ? *reinterpret_cast<const double2*>(Y + r * ld + 2 * cp) : make_double2(0.0, 0.0);
     }
   };
   if (t_begin < t_end) load_tile(t_begin, cur);
+  __syncthreads();
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    if (tile + 1 < t_end) load_tile(tile + 1, nxt);
-#pragma unroll 1
-    for (int t = 0; t < kSketchZeta; ++t) {
-      const uint64_t h = splitmix64(key + (uint64_t)(tile - t_begin) * kSketchZeta + t);
-      const uint64_t signs = splitmix64(h);
-      const int off = (int)(h % (uint64_t)s_rows);
-      const int mul = kSketchMul[t];
-      if (active) {
+    const int buf = (int)((tile - t_begin) & 1);
+    if (tile + 1 < t_end) {
+      load_tile(tile + 1, nxt);
+      if (tid < kSketchZeta) draw(tile + 1, buf ^ 1);
+    }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int j = rj + 8 * k;
-          int x = mul * j + off;
-          x -= s_rows * (int)((float)x * inv_s);
-          if (x < 0) x += s_rows;
-          if (x >= s_rows) x -= s_rows;
-          const double v = ((signs >> j) & 1ull) ? cur[k] : -cur[k];
-          acc[x * Lc + c] += v;
+    for (int t = 0; t < kSketchZeta; ++t) {
+      const int off = tab_off[buf][t];
+      const unsigned long long sg = tab_sign[buf][t];
+      const int stp = tab_step[t];
+      if (active) {
+        int x[4];
+        x[0] = base[t] + off; if (x[0] >= s_rows) x[0] -= s_rows;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) { x[k] = x[k - 1] + stp; if (x[k] >= s_rows) x[k] -= s_rows; }
+        double2 old[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) old[k] = *reinterpret_cast<const double2*>(acc + x[k] * Lc + 2 * cp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool neg = ((sg >> (rj + 16 * k)) & 1ull) == 0ull;
+          old[k].x += neg ? -cur[k].x : cur[k].x;
+          old[k].y += neg ? -cur[k].y : cur[k].y;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<double2*>(acc + x[k] * Lc + 2 * cp) = old[k];
       }
       __syncthreads();
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
   }
   double* dst = partials + (int64_t)blockIdx.x * rows_pad * Lc;
   for (int i = tid; i < rows_pad * Lc; i += blockDim.x) dst[i] = (i < s_rows * Lc) ? acc[i] : 0.0;
@@ -487,7 +510,33 @@ sketch_kernel(const double* __restrict__ Y, int64_t rows, int Lc, int64_t ld, in
 // ------------------------------------------------------------------------------------------------
 // Householder QR of the sketch + deflated triangular inverse, one CTA, sketch resident in shared memory
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
+constexpr int kHqrThreads = 512;   // 16 warps: column k belongs to warp k & 15 (slot k >> 4, at most 8 slots: l <= 128)
+constexpr int kHqrRI = 8;          // row slots per lane: rows lane + 32*i, s_rows <= 256
+
+// Householder reflector of column j acting on rows >= rk, by ONE warp (LAPACK dlarfg).  Leaves v (v[rk] = 1 implied)
+// below row rk, beta = R[rk][j] at row rk, tau in tauv[j]; rowof[j] = rk, or -1 if the column is numerically dependent.
+__device__ __forceinline__ void hqr_make_reflector(double* x, int rk, int s_rows, double cn0j, double tol, int lane,
+                                                   double* tau_out, int* rowof_out) {
+  double sig = 0.0;
+  for (int r = rk + 1 + lane; r < s_rows; r += 32) sig += x[r] * x[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(0xffffffffu, sig, o);
+  const double alpha = (rk < s_rows) ? x[rk] : 0.0;
+  const double nrm = sqrt(alpha * alpha + sig);
+  const bool dead = (rk >= s_rows) || !(nrm > tol * cn0j) || !(cn0j > 0.0);
+  double tau = 0.0;
+  __syncwarp();
+  if (!dead) {
+    const double beta = (alpha >= 0.0) ? -nrm : nrm;
+    tau = (beta - alpha) / beta;
+    const double scal = 1.0 / (alpha - beta);
+    for (int r = rk + 1 + lane; r < s_rows; r += 32) x[r] *= scal;
+    if (lane == 0) x[rk] = beta;
+  }
+  if (lane == 0) { *tau_out = tau; *rowof_out = dead ? -1 : rk; }
+}
+
+__global__ void __launch_bounds__(kHqrThreads, 1)
 hqr_inv_kernel(const double* __restrict__ SK, int ldsk, int s_rows, int l, double* __restrict__ T, int Lrows, int ldt,
                int* info, int* deadmask, int* flag_dead, const int* cond_flag) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
@@ -496,8 +545,8 @@ hqr_inv_kernel(const double* __restrict__ SK, int ldsk, int s_rows, int l, doubl
   double* Ac = hsm;                                     // column-major: Ac[c*sp + r]
   double* cn0 = Ac + (size_t)l * sp;                    // original column norms
   double* vwork = cn0 + l;                              // l: column of R being inverted
-  double* bc = vwork + l;                               // [0] tau
-  int* rowof = reinterpret_cast<int*>(bc + 4);          // l: R row assigned to column j, or -1 (dead)
+  double* tauv = vwork + l;                             // l: tau of every reflector
+  int* rowof = reinterpret_cast<int*>(tauv + l);        // l: R row assigned to column j, or -1 (dead)
   int* live = rowof + l;                                // compact list of live columns
   const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const double tol = 8.0 * l * DBL_EPSILON;
@@ -515,48 +564,72 @@ hqr_inv_kernel(const double* __restrict__ SK, int ldsk, int s_rows, int l, doubl
     if (lane == 0) cn0[c] = sqrt(a);
   }
   __syncthreads();
+  if (warp == 0) hqr_make_reflector(Ac, 0, s_rows, cn0[0], tol, lane, &tauv[0], &rowof[0]);
+  __syncthreads();
 
-  // ---- Householder sweeps; `rk` = next free row of R (does not advance on a dead column)
+  // ---- Householder sweeps with one barrier per column: every warp applies reflector j to the columns it owns, and the
+  // owner of column j+1 builds the next reflector right after updating it.  `rk` = next free row of R (does not advance
+  // on a dead column).
   int rk = 0;
   for (int j = 0; j < l; ++j) {
-    if (warp == 0) {
-      double* x = Ac + j * sp;
-      double sig = 0.0;
-      for (int r = rk + 1 + lane; r < s_rows; r += 32) sig += x[r] * x[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(0xffffffffu, sig, o);
-      const double alpha = (rk < s_rows) ? x[rk] : 0.0;
-      const double nrm = sqrt(alpha * alpha + sig);
-      const bool dead = (rk >= s_rows) || !(nrm > tol * cn0[j]) || !(cn0[j] > 0.0);
-      double tau = 0.0;
-      if (!dead) {
-        const double beta = (alpha >= 0.0) ? -nrm : nrm;
-        tau = (beta - alpha) / beta;
-        const double scal = 1.0 / (alpha - beta);
-        for (int r = rk + 1 + lane; r < s_rows; r += 32) x[r] *= scal;     // v (v[rk] = 1 implied)
-        if (lane == 0) x[rk] = beta;                                       // R[rk][j]
-      }
-      if (lane == 0) { bc[0] = tau; rowof[j] = dead ? -1 : rk; }
-    }
-    __syncthreads();
-    const double tau = bc[0];
-    const bool dead = rowof[j] < 0;
-    if (!dead) {
+    const bool dead_j = rowof[j] < 0;
+    const double tau = tauv[j];
+    const int rk_next = dead_j ? rk : rk + 1;
+    if (!dead_j) {
+      double vr[kHqrRI];
       const double* v = Ac + j * sp;
-      for (int k = j + 1 + warp; k < l; k += nw) {
-        double* y = Ac + k * sp;
-        double w = 0.0;
-        for (int r = rk + 1 + lane; r < s_rows; r += 32) w += v[r] * y[r];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-        w = (w + y[rk]) * tau;
-        for (int r = rk + 1 + lane; r < s_rows; r += 32) y[r] -= w * v[r];
-        __syncwarp();
-        if (lane == 0) y[rk] -= w;
+      for (int i = 0; i < kHqrRI; ++i) {
+        const int r = lane + 32 * i;
+        vr[i] = (r < s_rows && r > rk) ? v[r] : ((r == rk) ? 1.0 : 0.0);
       }
-      ++rk;
+      const int i_lo = rk >> 5;                          // row slots below this one are finished rows of R
+#pragma unroll 1
+      for (int g4 = 0; g4 < 2; ++g4) {                   // my columns, four at a time (independent dot products)
+        double vals[4][kHqrRI];
+        double dot[4];
+        bool on[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = warp + 16 * (4 * g4 + q);
+          on[q] = (k > j) && (k < l);
+          dot[q] = 0.0;
+          if (on[q]) {
+            const double* y = Ac + k * sp;
+#pragma unroll
+            for (int i = 0; i < kHqrRI; ++i) {
+              const int r = lane + 32 * i;
+              vals[q][i] = (i >= i_lo && r < s_rows) ? y[r] : 0.0;
+              dot[q] += vr[i] * vals[q][i];
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (on[q]) {
+            const int k = warp + 16 * (4 * g4 + q);
+            double* y = Ac + k * sp;
+            const double w = tau * dot[q];
+#pragma unroll
+            for (int i = 0; i < kHqrRI; ++i) {
+              const int r = lane + 32 * i;
+              if (i >= i_lo && r < s_rows && r >= rk) y[r] = vals[q][i] - w * vr[i];
+            }
+          }
+        }
+      }
+    }
+    if (j + 1 < l && ((j + 1) & 15) == warp) {
+      __syncwarp();
+      hqr_make_reflector(Ac + (j + 1) * sp, rk_next, s_rows, cn0[j + 1], tol, lane, &tauv[j + 1], &rowof[j + 1]);
     }
     __syncthreads();
+    rk = rk_next;
   }
   const int rank = rk;
   if (tid == 0) {
@@ -709,10 +782,10 @@ cudaError_t sketch_launch(const double* Y, int64_t rows, int Lc, int64_t ld, uin
   const int s_rows = sketch_rows(Lc);
   const int rows_pad = (s_rows + 127) / 128 * 128;
   const size_t smem = (size_t)s_rows * Lc * 8;
-  if (Lc > 128 || smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (Lc > 128 || smem > 224 * 1024) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -725,7 +798,7 @@ cudaError_t sketch_launch(const double* Y, int64_t rows, int Lc, int64_t ld, uin
 cudaError_t hqr_inv_launch(const double* SK, int ldsk, int s_rows, int l, double* T, int Lrows, int ldt, int* info,
                            int* deadmask, int* flag_dead, const int* cond_flag, cudaStream_t s) {
   const int sp = s_rows | 1;
-  const size_t smem = ((size_t)l * sp + 2 * (size_t)l + 4) * 8 + 2 * (size_t)l * 4 + 16;
+  const size_t smem = ((size_t)l * sp + 3 * (size_t)l + 4) * 8 + 2 * (size_t)l * 4 + 16;
   if (smem > 226 * 1024) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
@@ -733,7 +806,7 @@ cudaError_t hqr_inv_launch(const double* SK, int ldsk, int s_rows, int l, double
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  hqr_inv_kernel<<<1, 1024, smem, s>>>(SK, ldsk, s_rows, l, T, Lrows, ldt, info, deadmask, flag_dead, cond_flag);
+  hqr_inv_kernel<<<1, kHqrThreads, smem, s>>>(SK, ldsk, s_rows, l, T, Lrows, ldt, info, deadmask, flag_dead, cond_flag);
   return cudaGetLastError();
 }
 
