@@ -349,13 +349,27 @@ struct Core {
   }
 
   // Thin-Q factor of X in place: on return the orthonormal factor is X * Tfold (never formed here).
+  //   1. Gram + Cholesky probe.  If every pivot ratio is >= 1e-8 (cond(X) below ~1e4) plain CholeskyQR2 finishes:
+  //      apply, Gram, Cholesky -- the cheapest path, taken by the benchmark matrices.
+  //   2. Otherwise (device flag, no host round trip) the sketch-preconditioned stage runs instead: Householder-grade
+  //      stability up to cond ~ 1e15, rank decisions made column-relative on the sketch.
+  //   3. Columns found numerically dependent are refilled with fresh vectors and orthonormalised again.
   // distributed: rows are sharded over comm.  refill_from_a: X is A times something, so directions lost to numerical
   // rank deficiency are replaced by fresh vectors from range(A) instead of arbitrary ones.
   int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold,
                  bool refill_from_a = false) {
     const MatView vx = view_rows(X, rows);
-    CU_TRY(cudaMemsetAsync(flags + 6, 0, sizeof(int), st));      // the refill stage's "one more pass" flag starts clear
-    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, nullptr, flags + 0, false));
+    const size_t gx = distributed ? (size_t)Lc * ld : 0;
+    CU_TRY(cudaMemsetAsync(flags, 0, 8 * sizeof(int), st));      // f2 (0), liveness (1..3), refill-stage f2 (6) start clear
+    int* fs = flags + 16;                                        // [0] robust stage needed, [1] fast path ok
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
+    ST_TRY(chol(kCholProbe, rows_for_shift, T1, nullptr, true, fs));
+    // fast path: CholeskyQR2
+    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, fs + 1, 1));
+    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fs + 1, 0, false, nullptr, gx, 0));
+    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, fs + 1, true, nullptr));
+    // robust path
+    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, fs, flags + 0, false));
     // Refill, only when columns were deflated as numerically dependent (device flag): form Q (zero columns where dead),
     // put fresh vectors into those columns and orthonormalise again -- the completion a Householder QR would return
     // (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
@@ -702,7 +716,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
-    tm->qr_third_passes = hflags[8]; tm->qr_refills = hflags[9]; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1];
+    tm->qr_third_passes = hflags[8]; tm->qr_refills = hflags[9]; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1] ? hflags[1] : l;
     tm->total_ms = total.ms();
   } else if (out_dev) {
     // nothing to wait for: results are ordered on the caller's stream
@@ -826,7 +840,7 @@ int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row
     CU_TRY(cudaMemcpyAsync(hinfo, c.flags + 1, 8, cudaMemcpyDeviceToHost, sc.st));
     if (!on_device) CU_TRY(cudaMemcpyAsync(q, qd, (size_t)nrows * ncols * 8, cudaMemcpyDeviceToHost, sc.st));
     CU_TRY(cudaStreamSynchronize(sc.st));
-    if (rank_out) *rank_out = hinfo[0];
+    if (rank_out) *rank_out = hinfo[0] ? hinfo[0] : (int)ncols;   // 0: the probe passed, plain CholeskyQR2, full rank
     return CORRLA_OK;
   } catch (...) { set_last_error("exception"); return CORRLA_ERR_ALLOC; }
 }

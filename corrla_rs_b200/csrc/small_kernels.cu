@@ -179,6 +179,11 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
     // after the sketch preconditioner cond(Y) is O(1); a small pivot ratio means the embedding was unlucky (or columns
     // were deflated): ask for one more CholeskyQR pass
     if (tid == 0 && flag3 != nullptr) *flag3 = (st.minratio < 1e-3) ? 1 : 0;
+  } else if (mode == kCholProbe) {
+    if (tid == 0 && flag3 != nullptr) {
+      const int robust = (st.minratio < 1e-8) ? 1 : 0;      // dead columns have ratio 0
+      flag3[0] = robust; flag3[1] = 1 - robust;
+    }
   }
   __syncthreads();
 #pragma unroll

@@ -11,7 +11,10 @@ namespace corrla {
 // regenerates the same matrix without a broadcast.  oracle/ref_rsvd.py:philox_normal restates it.
 cudaError_t philox_normal_launch(double* out, int64_t rows, int cols, int64_t ld, uint64_t seed, cudaStream_t s);
 
-enum CholMode { kCholAuto = 0, kCholPlain = 1, kCholCheck = 2 };   // kCholCheck: plain, and *flag3 = (min pivot ratio < 1e-3)
+// kCholCheck: plain, and *flag3 = (min pivot ratio < 1e-3).
+// kCholProbe: plain, and flag3[0] = (min pivot ratio < 1e-8, i.e. cond(Y) beyond ~1e4, or a deflated column): the
+//             robust sketch-preconditioned stage is needed; flag3[1] = !flag3[0]: plain CholeskyQR2 may proceed.
+enum CholMode { kCholAuto = 0, kCholPlain = 1, kCholCheck = 2, kCholProbe = 3 };
 
 // Upper Cholesky G = R^T R of the l x l Gram matrix (row-major, pitch ldg) in shared memory, then the
 // "deflated" inverse T = R^-1 (columns whose pivot vanished are zero, so Q = Y*T has exact zero columns there).

@@ -120,9 +120,20 @@ def hqr_inv(sk: np.ndarray):
     return t, dead
 
 
-def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None):
-    """Sketch-preconditioned CholeskyQR with refill of numerically dependent columns (Core::qr_inplace in engine.cu).
+def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None,
+            refill_a: np.ndarray | None = None):
+    """CholeskyQR2 when a Cholesky probe says cond(x) is below ~1e4, else sketch-preconditioned CholeskyQR with refill
+    of numerically dependent columns (Core::qr_inplace in engine.cu).
     Returns (x_last, t_fold, second_pass, live): the orthonormal factor is x_last @ t_fold."""
+    # probe: Gram + Cholesky pivots; well-conditioned matrices take plain CholeskyQR2
+    g = distributed_allreduce(x.T @ x)
+    _, _, probe = chol_factor(g, np.diag(g).copy(), False, TOL_DEAD_PER_COL * x.shape[1])
+    if probe >= 1e-8:
+        t1, _, _ = chol_inv(g, False, global_rows)
+        x = x @ t1
+        g = distributed_allreduce(x.T @ x)
+        tf, _, _ = chol_inv(g, False, global_rows)
+        return x, tf, False, x.shape[1]
     lc = (x.shape[1] + 7) // 8 * 8
     sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), sketch_rng or np.random.default_rng(777)))
     t1, dead = hqr_inv(sk)
@@ -140,9 +151,16 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
     if dead.any():
         rng = refill_rng or np.random.default_rng(12345)
         x = x @ tf
-        x[:, dead] = rng.standard_normal((x.shape[0], int(dead.sum())))
-        g = distributed_allreduce(x.T @ x)
-        t1, _, _ = chol_inv(g, False, global_rows)
+        nd = int(dead.sum())
+        if refill_a is not None:
+            # fresh directions from range(A): the same Omega' on every rank (engine: Philox stream 0)
+            x[:, dead] = refill_a @ rng.standard_normal((refill_a.shape[1], nd))
+        else:
+            x[:, dead] = rng.standard_normal((x.shape[0], nd))
+        # the refill stage is the robust (sketch) stage again
+        lc = (x.shape[1] + 7) // 8 * 8
+        sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), np.random.default_rng(778)))
+        t1, _ = hqr_inv(sk)
         x = x @ t1
         g = distributed_allreduce(x.T @ x)
         tf, _, dead = chol_inv(g, False, global_rows)
@@ -207,14 +225,14 @@ def engine_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: in
     nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
     for i in range(n_iter):
         if schedule == 1 or i > 2:
-            y, tf, _, _ = qr_fold(y, allreduce, grows)
+            y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a)
             z = allreduce(a.T @ y) @ tf
             y = a @ z
         else:
             z = allreduce(a.T @ y)
             y = (a @ z) * (1.0 / np.sqrt(nu2))
         nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
-    y, tf, _, _ = qr_fold(y, allreduce, grows)
+    y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a)
     zb = allreduce(a.T @ y) @ tf                      # B^T, replicated
     qz, tzf, _, _ = qr_fold(zb.copy(), _identity_allreduce, float(n))
     qz = qz @ tzf
