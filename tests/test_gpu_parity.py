@@ -329,3 +329,36 @@ def test_large_device_properties(cb):
     assert float(resid.abs().max()) < 1e-9 * float(sig[0])
     pu = u0[:, :k] - u @ (u.T @ u0[:, :k])
     assert float(torch.linalg.matrix_norm(pu, 2)) < 1e-8
+
+
+# ------------------------------------------------------------------ beyond the parity class: robustness
+def test_thin_q_cond_1e14_sketch_preconditioned(cb):
+    """cond 1e14: the Cholesky probe must hand over to the sketch-preconditioned stage (Householder QR of a sparse sign
+    sketch), which keeps orthonormality at machine precision where CholeskyQR2 cannot."""
+    rng = np.random.default_rng(115)
+    m, l = 20000, 60
+    u, _ = np.linalg.qr(rng.standard_normal((m, l)))
+    v, _ = np.linalg.qr(rng.standard_normal((l, l)))
+    a = (u * np.logspace(0, -14, l)) @ v.T
+    q, rank = cb.thin_q(a, return_rank=True)
+    assert rank == l
+    assert np.max(np.abs(q.T @ q - np.eye(l))) < 1e-12
+    assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-12 * np.linalg.norm(a)
+
+
+@pytest.mark.parametrize("decay", [1.2, 2.0])
+def test_fast_decay_reference_schedule_stays_accurate(cb, decay):
+    """sigma_j = decay^-j: after the reference's three raw power iterations cond(Y) is 1e16 and beyond.  The reference
+    (Householder) still returns the leading singular values to ~1e-13; the engine must not fall apart either."""
+    rng = np.random.default_rng(116)
+    m, n, k, q, p = 4000, 300, 20, 4, 10
+    uu, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    vv, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sig = decay ** -np.arange(n, dtype=np.float64)
+    a = (uu * sig) @ vv.T
+    omega = rng.standard_normal((n, k + p))
+    u, s, vt = cb.rsvd(a, k, q, p, omega=omega, seed=4)
+    assert np.max(np.abs(s.ravel() - sig[:k]) / sig[:k]) < 1e-9
+    assert np.max(np.abs(np.asarray(u).T @ np.asarray(u) - np.eye(k))) < 1e-12
+    t = cb.last_timings()
+    assert t["live_columns"] <= k + p
