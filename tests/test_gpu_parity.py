@@ -362,3 +362,19 @@ def test_fast_decay_reference_schedule_stays_accurate(cb, decay):
     assert np.max(np.abs(np.asarray(u).T @ np.asarray(u) - np.eye(k))) < 1e-12
     t = cb.last_timings()
     assert t["live_columns"] <= k + p
+
+
+def test_plain_c_caller_of_the_abi(tmp_path):
+    """The C ABI without Python in the way: tools/c_abi_example.c compiled with gcc against include/corrla_b200.h."""
+    import shutil
+    import subprocess
+    root = Path(__file__).resolve().parents[1]
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    exe = tmp_path / "c_abi_example"
+    libdir = root / "corrla_rs_b200" / "lib"
+    subprocess.run(["gcc", "-O2", f"-I{root / 'include'}", "-o", str(exe), str(root / "tools" / "c_abi_example.c"),
+                    f"-L{libdir}", "-lcorrla_b200", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "C ABI example OK" in r.stdout
