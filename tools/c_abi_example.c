@@ -1,7 +1,8 @@
 /* Plain-C caller of libcorrla_b200.so: what a non-Python, non-Rust host (or the Rust -sys crate) does.
  * Build:  gcc -O2 -Iinclude -o tools/c_abi_example tools/c_abi_example.c -Lcorrla_rs_b200/lib -lcorrla_b200 \
  *             -Wl,-rpath,'$ORIGIN/../corrla_rs_b200/lib' -lm
- * Runs random_svd on a 2000 x 64 matrix with planted singular values 64, 63, ..., and on the reference's
+ * Runs random_svd on a 2000 x 64 matrix of exact rank 12 with planted singular values 64, 63, ..., 53 (rank <= l = 18,
+ * so the range finder captures it exactly), and on the reference's
  * known-answer 5 x 5 matrix (random_svd.rs:155-161), checks the results and prints the timings struct. */
 #include <math.h>
 #include <stdio.h>
@@ -33,10 +34,10 @@ int main(void) {
   for (int i = 0; i < m * n; ++i) u0[i] = urand(&seed);
   for (int i = 0; i < n * n; ++i) v0[i] = urand(&seed);
   orthonormalise(u0, m, n); orthonormalise(v0, n, n);
-  /* A = U0 diag(64 - j) V0^T, stored ROW-major (row_stride = n, col_stride = 1), like a numpy array */
+  /* A = U0[:, :12] diag(64 - j) V0[:, :12]^T, stored ROW-major (row_stride = n, col_stride = 1), like a numpy array */
   double* a = calloc((size_t)m * n, sizeof(double));
   for (int r = 0; r < m; ++r) for (int c = 0; c < n; ++c) {
-    double s = 0; for (int j = 0; j < n; ++j) s += u0[j * m + r] * (double)(64 - j) * v0[j * n + c];
+    double s = 0; for (int j = 0; j < 12; ++j) s += u0[j * m + r] * (double)(64 - j) * v0[j * n + c];
     a[(size_t)r * n + c] = s;
   }
   corrla_rsvd_opts opts; corrla_rsvd_opts_default(&opts); opts.seed = 7;
