@@ -23,7 +23,9 @@ def main():
     comm = cb.ShardComm(device=local)
     results = {}
     cases = {"gauss_rowmajor": (20011, 512, 30, 5, 10, "C"), "lowrank_colmajor": (16384, 300, 20, 4, 10, "F"),
-             "tiny_rank_deficient": (64, 16, 8, 12, 8, "C")}
+             "tiny_rank_deficient": (64, 16, 8, 12, 8, "C"),
+             # Z = n16 x ld = 16000 x 36 doubles exceeds the 4 MiB peer-memory half: this case takes the NCCL fallback
+             "wide_nccl_fallback": (18000, 16000, 20, 2, 8, "C")}
     for name, (m, n, k, q, p, order) in cases.items():
         rng = np.random.default_rng(77)
         if name.startswith("lowrank"):
@@ -41,6 +43,7 @@ def main():
         shard = np.asfortranarray(a[r0:r1]) if order == "F" else np.ascontiguousarray(a[r0:r1])
         # host path and device path
         u_loc, s, vt = cb.rsvd(shard, k, q, p, omega=omega, comm=comm, global_rows=m, seed=9)
+        p2p_used = cb.last_timings()["p2p_exchanges"]
         ud, sd, vd = cb.rsvd(torch.from_numpy(shard).cuda(), k, q, p, omega=torch.from_numpy(omega).cuda(), comm=comm, seed=9)
         torch.cuda.synchronize()
         gathered = [None] * world
@@ -58,7 +61,7 @@ def main():
                 "sin_u": ref_rsvd.subspace_sine(uo[:, :kk], u[:, :kk]), "sin_v": ref_rsvd.subspace_sine(vo[:kk].T, vt[:kk].T),
                 "orth_u": float(np.max(np.abs(u.T @ u - np.eye(k)))),
                 "device_vs_host_sigma": float(np.max(np.abs(sd.cpu().numpy() - s))),
-                "device_vs_host_u": float(np.max(np.abs(u2 - u))), "k_checked": kk}
+                "device_vs_host_u": float(np.max(np.abs(u2 - u))), "k_checked": kk, "p2p_exchanges": p2p_used}
     # thin_q sharded
     rng = np.random.default_rng(5)
     a = rng.standard_normal((9000, 48))

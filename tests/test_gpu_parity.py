@@ -434,3 +434,52 @@ def test_bench_line_contract_small(tmp_path):
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 1024 * 8 and d["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_full_size_c3_properties(cb):
+    """BASELINE config C3 at full size (4 194 304 x 1024, k 100, q 4, p 10) on the device, through size-independent
+    properties: planted spectrum recovered, U and V orthonormal, A^T U = V S.  Needs ~45 GB of HBM."""
+    import torch
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("not enough free device memory for the full-size case")
+    torch.manual_seed(1)
+    m, n, r, k, q, p = 4_194_304, 1024, 104, 100, 4, 10          # rank 104 <= l = 110: exact recovery
+    u0, _ = torch.linalg.qr(torch.randn(m, r, dtype=torch.float64, device="cuda"))
+    v0, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device="cuda"))
+    sig = 50.0 * 0.985 ** torch.arange(r, dtype=torch.float64, device="cuda")
+    a = torch.empty((m, n), dtype=torch.float64, device="cuda")
+    step = 1 << 19
+    for r0 in range(0, m, step):                                  # build A in row blocks to bound temporaries
+        a[r0:r0 + step] = (u0[r0:r0 + step] * sig) @ v0.T
+    u, s, vt = cb.rsvd(a, k, q, p, seed=11)
+    torch.cuda.synchronize()
+    t = cb.last_timings()
+    assert t["passes_over_a"] == 10 and t["pass_launches"] == 10
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float((u.T @ u - eye).abs().max()) < 1e-12
+    assert float((vt @ vt.T - eye).abs().max()) < 1e-12
+    assert float(((s.ravel() - sig[:k]).abs() / sig[:k]).max()) < 1e-10
+    resid = a.T @ u - vt.T * s.ravel()
+    assert float(resid.abs().max()) < 1e-9 * float(sig[0])
+    del a, u0, resid
+    torch.cuda.empty_cache()
+
+
+def test_full_size_c2_properties(cb):
+    """BASELINE config C2 (20 000 x 20 000, k 100, q 4, p 10): split-K on both products, Z of 18 MB."""
+    import torch
+    torch.manual_seed(2)
+    m = n = 20000
+    r, k, q, p = 104, 100, 4, 10
+    u0, _ = torch.linalg.qr(torch.randn(m, r, dtype=torch.float64, device="cuda"))
+    v0, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device="cuda"))
+    sig = 50.0 * 0.985 ** torch.arange(r, dtype=torch.float64, device="cuda")
+    a = (u0 * sig) @ v0.T
+    u, s, vt = cb.rsvd(a, k, q, p, seed=12)
+    torch.cuda.synchronize()
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float((u.T @ u - eye).abs().max()) < 1e-12
+    assert float((vt @ vt.T - eye).abs().max()) < 1e-12
+    assert float(((s.ravel() - sig[:k]).abs() / sig[:k]).max()) < 1e-10
+    assert float(torch.linalg.matrix_norm(v0[:, :k] - vt.T @ (vt @ v0[:, :k]), 2)) < 1e-8
