@@ -197,7 +197,29 @@ def _colmajor_empty_like(a: _Mat, rows: int, cols: int):
     if a.on_device:
         import torch
         return torch.empty((cols, rows), dtype=torch.float64, device=a.keep.device).t()
+    n = rows * cols
+    if n * 8 >= _HUGE_OUTPUT_BYTES:
+        big = _huge_empty(n)
+        if big is not None:
+            return big.reshape((rows, cols), order="F")
     return np.empty((rows, cols), dtype=np.float64, order="F")
+
+
+_HUGE_OUTPUT_BYTES = 64 << 20
+
+
+def _huge_empty(n: int):
+    """n float64 in a buffer from corrla_host_alloc (2 MiB pages when the kernel allows): large outputs such as U are
+    filled by a threaded device->host copy whose speed is otherwise set by 4 KiB first-touch page faults."""
+    import weakref
+    lib = _ffi.load()
+    nbytes = n * 8
+    p = lib.corrla_host_alloc(nbytes)
+    if not p:
+        return None
+    buf = (C.c_double * n).from_address(p)
+    weakref.finalize(buf, lib.corrla_host_free, p, nbytes)
+    return np.frombuffer(buf, dtype=np.float64)
 
 
 def _ptr(x):

@@ -70,6 +70,8 @@ SYMBOLS = {
                                                C.POINTER(RsvdOpts)]),
     "corrla_thin_q_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                     C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(C.c_int)]),
+    "corrla_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "corrla_host_free": (None, [C.c_void_p, C.c_size_t]),
     "corrla_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "corrla_ctx_destroy": (None, [C.c_void_p]),
     "corrla_comm_unique_id": (C.c_int, [C.c_char_p]),

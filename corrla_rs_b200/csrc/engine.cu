@@ -1,6 +1,8 @@
 // Host-side engine and C ABI of libcorrla_b200.so: orchestrates the RSVD of the reference
 // (random_svd.rs:15-110) as a sequence of skinny DMMA GEMMs, CholeskyQR and a Jacobi SVD, all on one
 // CUDA stream, with NCCL all-reduces of the small replicated factors when the rows are sharded.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -219,10 +221,11 @@ struct Core {
   int mm(const MatView& a, bool reduce_inner, const double* B, double* out, int64_t ors, int64_t ocs, int ncols_out,
          const double* alpha = nullptr, double* sumsq = nullptr, const int* cond = nullptr, int force_splits = 0,
          bool is_pass = false, const double* col_bias = nullptr, size_t x_count = 0, size_t x_extra = 0,
-         bool accumulate = false) {
+         bool accumulate = false, int mode = 0) {
     GemmCall c{};
     c.col_bias = col_bias;
     c.accumulate = accumulate;
+    c.mode = mode;
     // cross-rank sum of the product: fused into the reduction kernel over peer memory when possible, else NCCL
     PeerExchange px;
     bool nccl_after = false;
@@ -250,6 +253,15 @@ struct Core {
   }
 
   MatView view_rows(const double* p, int64_t rows) const { return MatView{p, (int64_t)Lc, rows, (int64_t)ld}; }
+
+  // G = X^T X (upper triangle only: mode 1), summed over the ranks when gx > 0
+  int gram(const MatView& vx, const double* X, const int* cond, size_t gx) {
+    return mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, cond, 0, false, nullptr, gx, 0, false, 1);
+  }
+  // X <- X * T in place, T upper triangular (mode 2)
+  int apply_tri(const MatView& vx, const double* T, double* X, const int* cond) {
+    return mm(vx, true, T, X, ld, 1, Lc, nullptr, nullptr, cond, 1, false, nullptr, 0, 0, false, 2);
+  }
 
   // Y[m x Lc] = alpha * C * X, C = A or A - 1*mu^T        (X: n16 x ld)
   int mm_AX(const double* X, double* Yout, const double* alpha, double* sumsq) {
@@ -339,11 +351,11 @@ struct Core {
                      : hqr_inv_launch(SK, ld, s_rows, l, T1, L16, ld, flags + 1, deadmask, flags + 3, cond, st);
     ++launches;
     if (e != cudaSuccess) { set_last_error("hqr_inv launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, cond, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, cond, 0, false, nullptr, gx, 0));
+    ST_TRY(apply_tri(vx, T1, X, cond));
+    ST_TRY(gram(vx, X, cond, gx));
     ST_TRY(chol(kCholCheck, rows_for_shift, Tfold, cond, true, f2));
-    ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, f2, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, f2, 0, false, nullptr, gx, 0));
+    ST_TRY(apply_tri(vx, Tfold, X, f2));
+    ST_TRY(gram(vx, X, f2, gx));
     ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, f2, true, nullptr));
     return CORRLA_OK;
   }
@@ -362,11 +374,11 @@ struct Core {
     const size_t gx = distributed ? (size_t)Lc * ld : 0;
     CU_TRY(cudaMemsetAsync(flags, 0, 8 * sizeof(int), st));      // f2 (0), liveness (1..3), refill-stage f2 (6) start clear
     int* fs = flags + 16;                                        // [0] robust stage needed, [1] fast path ok
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx, 0));
+    ST_TRY(gram(vx, X, nullptr, gx));
     ST_TRY(chol(kCholProbe, rows_for_shift, T1, nullptr, true, fs));
     // fast path: CholeskyQR2
-    ST_TRY(mm(vx, true, T1, X, ld, 1, Lc, nullptr, nullptr, fs + 1, 1));
-    ST_TRY(mm(vx, false, X, G, ld, 1, Lc, nullptr, nullptr, fs + 1, 0, false, nullptr, gx, 0));
+    ST_TRY(apply_tri(vx, T1, X, fs + 1));
+    ST_TRY(gram(vx, X, fs + 1, gx));
     ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, fs + 1, true, nullptr));
     // robust path
     ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, fs, flags + 0, false));
@@ -374,7 +386,7 @@ struct Core {
     // put fresh vectors into those columns and orthonormalise again -- the completion a Householder QR would return
     // (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
     const int* fd = flags + 3;
-    ST_TRY(mm(vx, true, Tfold, X, ld, 1, Lc, nullptr, nullptr, fd, 1));
+    ST_TRY(apply_tri(vx, Tfold, X, fd));
     if (refill_from_a && Za != nullptr) {
       // X[:, dead] += A * Omega', Omega' Gaussian in the dead columns and zero elsewhere (Za is free while Y is being
       // orthonormalised).  Householder's completion of a numerically rank-deficient Y is rounding noise of A*(...),
@@ -843,6 +855,23 @@ int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row
     if (rank_out) *rank_out = hinfo[0] ? hinfo[0] : (int)ncols;   // 0: the probe passed, plain CholeskyQR2, full rank
     return CORRLA_OK;
   } catch (...) { set_last_error("exception"); return CORRLA_ERR_ALLOC; }
+}
+
+void* corrla_host_alloc(size_t bytes) {
+  if (bytes == 0) return nullptr;
+  const size_t two_mb = (size_t)2 << 20;
+  const size_t len = (bytes + two_mb - 1) / two_mb * two_mb;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+  madvise(p, len, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+void corrla_host_free(void* p, size_t bytes) {
+  if (p == nullptr) return;
+  const size_t two_mb = (size_t)2 << 20;
+  munmap(p, (bytes + two_mb - 1) / two_mb * two_mb);
 }
 
 int corrla_ctx_create(int device, corrla_ctx** out) {

@@ -44,7 +44,12 @@ constexpr int kProducerRegs = 40;
 constexpr int kThreads = 12 * 32;
 
 // One consumer warp, all work items of this CTA.  FULL: every n-block of the warp is valid (no predicates on the DMMAs).
-template <bool KC, int WM, int WN, int MI, int JW, bool FULL>
+// MODE 0: dense.  MODE 1 (MC only): the output is symmetric (Gram matrix) and only its upper triangle is consumed, so
+// 8x8 blocks entirely below the diagonal are skipped and m-blocks are dealt round-robin to the warps to balance what
+// is left.  MODE 2 (KC only): B is upper triangular (a Cholesky/Householder inverse), so k4-steps whose rows of B are
+// zero for a given n-block are skipped.  n-blocks are always interleaved between the WN warps (nb = wn + WN*j), which
+// balances both triangular cases.
+template <bool KC, int WM, int WN, int MI, int JW, bool FULL, int MODE>
 __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* smem, unsigned char* smemB, uint32_t sBar,
                                               double* red, int warp, int lane, int jn) {
   constexpr int NCW = WM * WN;
@@ -63,7 +68,7 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
       a_xo[1][s] = a_xo[0][s];
     }
   } else {
-    a_base = ((wm * MI) >> 1) * 2048;
+    a_base = (MODE == 1) ? (wm >> 1) * 2048 : ((wm * MI) >> 1) * 2048;
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
       const int mc = colperm(g, par);
@@ -74,7 +79,7 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
       }
     }
   }
-  const int b_off = t * p.ldb * 8 + (8 * wn * JW + g) * 8;
+  const int b_off = t * p.ldb * 8 + (8 * wn + g) * 8;      // n-block of slot j: nb = wn + WN*j
   const int b_step = 4 * p.ldb * 8;
 
   double alpha = 1.0;
@@ -83,12 +88,25 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
   auto load_frags = [&](double (&af)[MI], double (&bf)[JW], const unsigned char* a, const unsigned char* b, int s) {
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-      const int off = KC ? (i * 1024 + a_xo[0][s]) : ((i >> 1) * 2048 + a_xo[i & 1][s]);
+      const int off = KC ? (i * 1024 + a_xo[0][s])
+                         : (MODE == 1 ? (2 * i * 2048 + a_xo[wm & 1][s]) : ((i >> 1) * 2048 + a_xo[i & 1][s]));
       af[i] = *reinterpret_cast<const double*>(a + off);
     }
 #pragma unroll
     for (int j = 0; j < JW; ++j)
-      if (FULL || j < jn) bf[j] = *reinterpret_cast<const double*>(b + s * b_step + j * 64);
+      if (FULL || j < jn) bf[j] = *reinterpret_cast<const double*>(b + s * b_step + j * (WN * 64));
+  };
+  // does DMMA (i, j) of k4-step s in chunk c contribute?  (warp-uniform)
+  auto keep = [&](int i, int j, int s, int64_t c) -> bool {
+    if (MODE == 1) return (wn + WN * j) >= 2 * ((wm >> 1) + 2 * i);          // n-block reaches the diagonal of box(i)
+    if (MODE == 2) return (int64_t)(wn + WN * j) >= 2 * c + (s >= 2 ? 1 : 0); // rows of B in this step are not all zero
+    return true;
+  };
+  // tile row of accumulator slot i for lane group g
+  auto tile_row = [&](int i) -> int {
+    if (KC) return (wm * MI + i) * 8 + rowperm(g);
+    if (MODE == 1) return 16 * ((wm >> 1) + 2 * i) + colperm(g, wm & 1);
+    return 16 * ((wm * MI + i) >> 1) + colperm(g, i & 1);
   };
 
   const int W = p.tilesM * p.splits;
@@ -127,7 +145,8 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
         for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < JW; ++j)
-            if (FULL || j < jn) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[s & 1][i], bf[s & 1][j]);
+            if ((FULL || j < jn) && (MODE == 0 || keep(i, j, s, c)))
+              dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[s & 1][i], bf[s & 1][j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sBar + 8 * (8 + stage));
@@ -141,24 +160,24 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
       double* wsp = p.ws + (int64_t)w * kTileM * Lc;
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
-        const int tr = KC ? ((wm * MI + i) * 8 + rowperm(g)) : (16 * ((wm * MI + i) >> 1) + colperm(g, i & 1));
+        const int tr = tile_row(i);
 #pragma unroll
         for (int j = 0; j < JW; ++j)
           if (FULL || j < jn) {
-            const int col = 8 * (wn * JW + j) + 2 * t;
+            const int col = 8 * (wn + WN * j) + 2 * t;
             *reinterpret_cast<double2*>(wsp + (int64_t)tr * Lc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
           }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
-        const int tr = KC ? ((wm * MI + i) * 8 + rowperm(g)) : (16 * ((wm * MI + i) >> 1) + colperm(g, i & 1));
+        const int tr = tile_row(i);
         const int64_t row = (int64_t)tile * kTileM + tr;
         if (row < p.Mside) {
 #pragma unroll
           for (int j = 0; j < JW; ++j)
             if (FULL || j < jn) {
-              const int col = 8 * (wn * JW + j) + 2 * t;
+              const int col = 8 * (wn + WN * j) + 2 * t;
               double v0 = acc[i][j][0], v1 = acc[i][j][1];
               if (p.col_bias != nullptr) { v0 -= p.col_bias[col]; v1 -= p.col_bias[col + 1]; }
               v0 *= alpha; v1 *= alpha;
@@ -193,7 +212,7 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
   }
 }
 
-template <bool KC, int WM, int WN, int MI, int JW>
+template <bool KC, int WM, int WN, int MI, int JW, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
   static_assert(WM * MI * 8 == kTileM, "tile rows");
@@ -258,9 +277,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
 
   // ------------------------------ DMMA consumer warpgroups ------------------------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
-  const int jn = min(JW, p.nblk - (warp / WM) * JW);   // valid n-blocks of this warp (may be <= 0)
-  if (jn == JW) consumer_loop<KC, WM, WN, MI, JW, true>(p, smem, smemB, sBar, red, warp, lane, jn);
-  else consumer_loop<KC, WM, WN, MI, JW, false>(p, smem, smemB, sBar, red, warp, lane, jn);
+  const int jn = min(JW, (p.nblk - (warp / WM) + WN - 1) / WN);   // valid n-block slots of this warp (nb = wn + WN*j)
+  if (jn == JW) consumer_loop<KC, WM, WN, MI, JW, true, MODE>(p, smem, smemB, sBar, red, warp, lane, jn);
+  else consumer_loop<KC, WM, WN, MI, JW, false, MODE>(p, smem, smemB, sBar, red, warp, lane, jn);
 }
 
 // out(r, c) = alpha * sum_s ws[s][tile(r)][r % 128][c]; one thread per column pair.
@@ -479,22 +498,26 @@ bool encode_map(CUtensorMap* tm, const MatView& v, bool kc) {
 
 typedef void (*KernelFn)(const CUtensorMap, const GemmArgs);
 
-template <bool KC>
+template <bool KC, int MODE>
 KernelFn pick_kernel(int nblk, int* threads) {
   *threads = kThreads;
   switch (nblk) {
-    case 1: return skinny_gemm_kernel<KC, 8, 1, 2, 1>;
-    case 2: return skinny_gemm_kernel<KC, 8, 1, 2, 2>;
-    case 3: return skinny_gemm_kernel<KC, 8, 1, 2, 3>;
-    case 4: return skinny_gemm_kernel<KC, 8, 1, 2, 4>;
-    case 5: return skinny_gemm_kernel<KC, 8, 1, 2, 5>;
-    case 6: return skinny_gemm_kernel<KC, 8, 1, 2, 6>;
-    case 7: return skinny_gemm_kernel<KC, 8, 1, 2, 7>;
-    case 8: return skinny_gemm_kernel<KC, 4, 2, 4, 4>;
-    case 9: case 10: return skinny_gemm_kernel<KC, 4, 2, 4, 5>;
-    case 11: case 12: return skinny_gemm_kernel<KC, 4, 2, 4, 6>;
-    case 13: case 14: return skinny_gemm_kernel<KC, 4, 2, 4, 7>;
-    case 15: case 16: return skinny_gemm_kernel<KC, 4, 2, 4, 8>;
+    case 8: return skinny_gemm_kernel<KC, 4, 2, 4, 4, MODE>;
+    case 9: case 10: return skinny_gemm_kernel<KC, 4, 2, 4, 5, MODE>;
+    case 11: case 12: return skinny_gemm_kernel<KC, 4, 2, 4, 6, MODE>;
+    case 13: case 14: return skinny_gemm_kernel<KC, 4, 2, 4, 7, MODE>;
+    case 15: case 16: return skinny_gemm_kernel<KC, 4, 2, 4, 8, MODE>;
+    default: break;
+  }
+  if (MODE != 0) return nullptr;      // narrow outputs (8x1 warp layout): dense only
+  switch (nblk) {
+    case 1: return skinny_gemm_kernel<KC, 8, 1, 2, 1, 0>;
+    case 2: return skinny_gemm_kernel<KC, 8, 1, 2, 2, 0>;
+    case 3: return skinny_gemm_kernel<KC, 8, 1, 2, 3, 0>;
+    case 4: return skinny_gemm_kernel<KC, 8, 1, 2, 4, 0>;
+    case 5: return skinny_gemm_kernel<KC, 8, 1, 2, 5, 0>;
+    case 6: return skinny_gemm_kernel<KC, 8, 1, 2, 6, 0>;
+    case 7: return skinny_gemm_kernel<KC, 8, 1, 2, 7, 0>;
     default: return nullptr;
   }
 }
@@ -600,7 +623,10 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   if (!encode_map(&tm, c.a, kc)) return cudaErrorInvalidValue;
 
   int threads = 0;
-  KernelFn fn = kc ? pick_kernel<true>(a.nblk, &threads) : pick_kernel<false>(a.nblk, &threads);
+  KernelFn fn = nullptr;
+  if (c.mode == 1 && !kc) fn = pick_kernel<false, 1>(a.nblk, &threads);
+  else if (c.mode == 2 && kc) fn = pick_kernel<true, 2>(a.nblk, &threads);
+  if (fn == nullptr) fn = kc ? pick_kernel<true, 0>(a.nblk, &threads) : pick_kernel<false, 0>(a.nblk, &threads);
   if (fn == nullptr) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMaxDynSmem);

@@ -56,6 +56,8 @@ struct GemmCall {
   double* out; int64_t out_rs, out_cs; int ncols_out;
   const double* alpha_sumsq = nullptr;
   const double* col_bias = nullptr;
+  int mode = 0;                     // 1: symmetric output, only the upper triangle is needed (Gram; reduce_outer);
+                                    // 2: B is upper triangular (reduce_inner).  Work below the diagonal is skipped.
   bool accumulate = false;          // out += product (used to refill deflated columns with fresh A*omega vectors)
   double* sumsq_slot = nullptr;     // if set: *sumsq_slot = sum of squares of the (scaled) output
   const int* cond_flag = nullptr;

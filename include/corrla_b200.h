@@ -129,6 +129,12 @@ CORRLA_API int corrla_rpca_f64(const double* a, int64_t nrows, int64_t ncols, in
 CORRLA_API int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
                       int on_device, const corrla_rsvd_opts* opts, double* q, int* rank_out);
 
+/* Host buffers for large outputs: page-aligned, advised to use transparent huge pages (2 MiB), so that the threaded
+ * device->host copy is not dominated by 4 KiB first-touch page faults.  Any host memory works as an output; this is
+ * only faster.  Free with corrla_host_free. */
+CORRLA_API void* corrla_host_alloc(size_t bytes);
+CORRLA_API void corrla_host_free(void* p, size_t bytes);
+
 /* contexts */
 CORRLA_API int corrla_ctx_create(int device, corrla_ctx** out);
 CORRLA_API void corrla_ctx_destroy(corrla_ctx* ctx);

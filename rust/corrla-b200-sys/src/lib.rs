@@ -73,6 +73,8 @@ extern "C" {
                                         opts: *const corrla_rsvd_opts) -> c_int;
     pub fn corrla_thin_q_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                              on_device: c_int, opts: *const corrla_rsvd_opts, q: *mut f64, rank_out: *mut c_int) -> c_int;
+    pub fn corrla_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn corrla_host_free(p: *mut c_void, bytes: usize);
     pub fn corrla_ctx_create(device: c_int, out: *mut *mut corrla_ctx) -> c_int;
     pub fn corrla_ctx_destroy(ctx: *mut corrla_ctx);
     pub fn corrla_comm_unique_id(id: *mut u8) -> c_int;

@@ -18,7 +18,7 @@ def declared_symbols():
 def test_header_symbols_all_exported(built_lib):
     from corrla_rs_b200 import _ffi
     names = declared_symbols()
-    assert len(names) >= 17
+    assert len(names) >= 19
     assert sorted(_ffi.SYMBOLS) == names            # the ctypes table binds the header 1:1
     for n in names:
         assert getattr(built_lib, n) is not None
@@ -83,3 +83,17 @@ def test_product_never_imports_oracle():
         for f in (ROOT / pkg).rglob("*"):
             if f.suffix in (".py", ".cu", ".cuh", ".cpp", ".h"):
                 assert pat.search(f.read_text()) is None, f
+
+
+def test_host_alloc_roundtrip(built_lib):
+    """corrla_host_alloc / corrla_host_free and the numpy wrapper used for large outputs."""
+    import gc
+    import numpy as np
+    import corrla_rs_b200 as cb
+    arr = cb._huge_empty(3 * (1 << 20))
+    assert arr is not None and arr.shape == (3 * (1 << 20),) and arr.dtype == np.float64
+    arr[:] = 1.5
+    view = arr.reshape((3, 1 << 20), order="F")
+    assert float(view.sum()) == 1.5 * 3 * (1 << 20)
+    del arr, view
+    gc.collect()
