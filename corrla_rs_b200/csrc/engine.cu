@@ -171,7 +171,7 @@ struct Core {
       int t, s; int64_t cps; size_t w, p;
       gemm_plan(Mside, K, nblk, ctx->num_sms, 0, &t, &s, &cps, &w, &p);
       ws = std::max(ws, w); np = std::max(np, p);
-      np = std::max(np, (size_t)t);
+      np = std::max(np, (size_t)t * 8);
     };
     need(m, n); need(n, m); need(Lc, m); need(m, Lc);
     ws = std::max(ws, sketch_ws_bytes(Lc, ctx->num_sms));

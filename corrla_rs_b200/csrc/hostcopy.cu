@@ -8,7 +8,7 @@
 namespace corrla {
 
 namespace {
-constexpr size_t kChunkBytes = (size_t)64 << 20;
+constexpr size_t kChunkBytes = (size_t)256 << 20;
 
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;

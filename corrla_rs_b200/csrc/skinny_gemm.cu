@@ -32,9 +32,6 @@ __device__ __forceinline__ int colperm(int g, int mbl) {
   return (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2) + 4 * mbl;
 }
 
-__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
 
 // Register budget: 12 warps are launched (two consumer warpgroups + one producer warpgroup); the producer group gives
 // its registers back (setmaxnreg.dec) and the consumers grow to 232, which holds 112 accumulator registers plus two
@@ -197,16 +194,10 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
         }
       }
       if (p.sumsq_partials != nullptr) {
+        // one partial per (work item, warp): no CTA-wide barrier in the epilogue; sumsq_finalize adds them in order
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) red[warp] = ss;
-        consumer_bar_sync(NCW * 32);
-        if (warp == 0 && lane == 0) {
-          double tot = 0.0;
-          for (int i = 0; i < NCW; ++i) tot += red[i];
-          p.sumsq_partials[w] = tot;
-        }
-        consumer_bar_sync(NCW * 32);
+        if (lane == 0) p.sumsq_partials[(int64_t)w * NCW + warp] = ss;
       }
     }
   }
@@ -559,7 +550,7 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
   *cps_out = cps;
   *ws_bytes = best_s > 1 ? (size_t)tilesM * best_s * tile_bytes : 0;
   const int64_t reduce_blocks = (Mside * (Lc / 2) + 255) / 256;
-  *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM;
+  *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM * 8;   // 8 consumer warps per work item
 }
 
 cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, int Lc, int64_t Mside, double* out,
@@ -641,7 +632,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 
-  int64_t n_part_used = a.tilesM;
+  int64_t n_part_used = (int64_t)a.tilesM * 8;
   if (fused_x) {
     const int Lc = a.nblk * 8;
     const int64_t work = std::max<int64_t>(a.Mside * (Lc / 2), (int64_t)(c.x_count / 2));
