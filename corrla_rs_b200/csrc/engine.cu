@@ -32,6 +32,7 @@ struct corrla_ctx {
   std::map<std::string, Buf> pool;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   BounceBuffers bounce;
+  int* hflag = nullptr;              // pinned: device-side decisions read back by the host (two ints)
   std::vector<cudaEvent_t> events;   // reusable timing events
   cudaEvent_t event(size_t i) {
     while (events.size() <= i) {
@@ -66,6 +67,7 @@ struct corrla_ctx {
     for (auto e : events) cudaEventDestroy(e);
     if (pinned) cudaFreeHost(pinned);
     bounce.release();
+    if (hflag) cudaFreeHost(hflag);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 };
@@ -113,8 +115,9 @@ int ctx_create(int device, corrla_ctx** out) {
   c->device = device;
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) == cudaSuccess) c->num_sms = p.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    set_last_error("cudaStreamCreate failed");
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&c->hflag), 64) != cudaSuccess) {
+    set_last_error("cudaStreamCreate / cudaMallocHost failed");
     delete c;
     return CORRLA_ERR_CUDA;
   }
@@ -368,6 +371,16 @@ struct Core {
   //   3. Columns found numerically dependent are refilled with fresh vectors and orthonormalised again.
   // distributed: rows are sharded over comm.  refill_from_a: X is A times something, so directions lost to numerical
   // rank deficiency are replaced by fresh vectors from range(A) instead of arbitrary ones.
+  // Read two device ints back (pinned buffer + stream sync).  The three decisions per QR that the host takes this way
+  // cost ~10 us each; enqueueing every alternative behind device-side flags cost more in empty launches.
+  int read_flags(const int* dev, int* out0, int* out1) {
+    CU_TRY(cudaMemcpyAsync(ctx->hflag, dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *out0 = ctx->hflag[0];
+    if (out1) *out1 = ctx->hflag[1];
+    return CORRLA_OK;
+  }
+
   int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold,
                  bool refill_from_a = false) {
     const MatView vx = view_rows(X, rows);
@@ -376,38 +389,48 @@ struct Core {
     int* fs = flags + 16;                                        // [0] robust stage needed, [1] fast path ok
     ST_TRY(gram(vx, X, nullptr, gx));
     ST_TRY(chol(kCholProbe, rows_for_shift, T1, nullptr, true, fs));
-    // fast path: CholeskyQR2
-    ST_TRY(apply_tri(vx, T1, X, fs + 1));
-    ST_TRY(gram(vx, X, fs + 1, gx));
-    ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, fs + 1, true, nullptr));
-    // robust path
-    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, fs, flags + 0, false));
-    // Refill, only when columns were deflated as numerically dependent (device flag): form Q (zero columns where dead),
-    // put fresh vectors into those columns and orthonormalise again -- the completion a Householder QR would return
-    // (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
-    const int* fd = flags + 3;
-    ST_TRY(apply_tri(vx, Tfold, X, fd));
-    if (refill_from_a && Za != nullptr) {
-      // X[:, dead] += A * Omega', Omega' Gaussian in the dead columns and zero elsewhere (Za is free while Y is being
-      // orthonormalised).  Householder's completion of a numerically rank-deficient Y is rounding noise of A*(...),
-      // which lies in range(A) too; vectors from outside it would waste the slots.
-      CU_TRY(cudaMemsetAsync(Za, 0, (size_t)n16 * ld * 8, st));
-      cudaError_t e = refill_dead_launch(Za, n, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, 0, fd, st);
-      ++launches;
-      if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-      ST_TRY(mm(av, a_rowmajor, Za, X, ld, 1, Lc, nullptr, nullptr, fd, 0, false, nullptr, 0, 0, true));
-    } else {
-      cudaError_t e = refill_dead_launch(X, rows, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, refill_stream, fd, st);
-      ++launches;
-      if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    int robust = 0;
+    ST_TRY(read_flags(fs, &robust, nullptr));                    // identical on every rank: G is the all-reduced Gram
+    if (!robust) {
+      // fast path: CholeskyQR2
+      ST_TRY(apply_tri(vx, T1, X, nullptr));
+      ST_TRY(gram(vx, X, nullptr, gx));
+      ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, nullptr, true, nullptr));
+      ++qr_calls;
+      return CORRLA_OK;
     }
-    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, fd, flags + 6, true));
-    count_third_pass();
+    ++n_robust;
+    ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, nullptr, flags + 0, false));
+    // Refill, only when columns were deflated as numerically dependent: form Q (zero columns where dead), put fresh
+    // vectors into those columns and orthonormalise again -- the completion a Householder QR would return
+    // (random_svd.rs:38 keeps l orthonormal columns even for rank-deficient Y).
+    int any_dead = 0;
+    ST_TRY(read_flags(flags + 3, &any_dead, nullptr));
+    if (any_dead) {
+      ++n_refill;
+      ST_TRY(apply_tri(vx, Tfold, X, nullptr));
+      if (refill_from_a && Za != nullptr) {
+        // X[:, dead] += A * Omega', Omega' Gaussian in the dead columns and zero elsewhere (Za is free while Y is being
+        // orthonormalised).  Householder's completion of a numerically rank-deficient Y is rounding noise of A*(...),
+        // which lies in range(A) too; vectors from outside it would waste the slots.
+        CU_TRY(cudaMemsetAsync(Za, 0, (size_t)n16 * ld * 8, st));
+        cudaError_t e = refill_dead_launch(Za, n, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, 0, nullptr, st);
+        ++launches;
+        if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+        ST_TRY(mm(av, a_rowmajor, Za, X, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, true));
+      } else {
+        cudaError_t e = refill_dead_launch(X, rows, l, ld, deadmask, refill_seed + (uint64_t)qr_calls, refill_stream, nullptr, st);
+        ++launches;
+        if (e != cudaSuccess) { set_last_error("refill launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      }
+      ST_TRY(qr_stage(X, rows, distributed, rows_for_shift, Tfold, nullptr, flags + 6, true));
+    }
     ++qr_calls;
     return CORRLA_OK;
   }
 
-  void count_third_pass();
+  int n_robust = 0, n_refill = 0;
+
 
   // power iteration with the reference schedule; leaves Y and Tf such that Q = Y * Tf
   int power_iter(const double* omega_dev_packed, uint64_t seed, int n_iter, int schedule) {
@@ -436,11 +459,6 @@ struct Core {
   }
 };
 
-__global__ void add_flag_kernel(const int* flags, int* counters) {
-  if (flags[0] || flags[6]) ++counters[0];
-  if (flags[3]) ++counters[1];
-}
-void Core::count_third_pass() { add_flag_kernel<<<1, 1, 0, st>>>(flags, flags + 8); ++launches; }
 
 struct Timer {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -728,7 +746,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
-    tm->qr_third_passes = hflags[8]; tm->qr_refills = hflags[9]; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1] ? hflags[1] : l;
+    tm->qr_third_passes = c.n_robust; tm->qr_refills = c.n_refill; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1] ? hflags[1] : l;
     tm->total_ms = total.ms();
   } else if (out_dev) {
     // nothing to wait for: results are ordered on the caller's stream

@@ -77,7 +77,7 @@ typedef struct corrla_timings {
   double d2h_ms;           /* device->host copy of the results */
   int gpu_launches;        /* kernels of this library launched by the call */
   int passes_over_a;       /* 2 + 2*n_iter */
-  int qr_third_passes;     /* how many CholeskyQR calls needed the shifted third pass */
+  int qr_third_passes;     /* how many QR calls left plain CholeskyQR2 for the sketch-preconditioned (robust) stage */
   int qr_refills;          /* how many CholeskyQR calls replaced numerically dependent columns by random vectors */
   int jacobi_sweeps;
   int live_columns;        /* numerical rank kept by the last CholeskyQR (<= l) */
