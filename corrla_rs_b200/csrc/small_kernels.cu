@@ -788,11 +788,9 @@ cudaError_t sketch_launch(const double* Y, int64_t rows, int Lc, int64_t ld, uin
   const int rows_pad = (s_rows + 127) / 128 * 128;
   const size_t smem = (size_t)s_rows * Lc * 8;
   if (Lc > 128 || smem > 224 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // function attributes are per device: set on every launch (about a microsecond)
     cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int64_t tiles = (rows + kSketchTile - 1) / kSketchTile;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, num_sms));
@@ -805,11 +803,9 @@ cudaError_t hqr_inv_launch(const double* SK, int ldsk, int s_rows, int l, double
   const int sp = s_rows | 1;
   const size_t smem = ((size_t)l * sp + 3 * (size_t)l + 4) * 8 + 2 * (size_t)l * 4 + 16;
   if (smem > 226 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // function attributes are per device: set on every launch (about a microsecond)
     cudaError_t e = cudaFuncSetAttribute(hqr_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   hqr_inv_kernel<<<1, kHqrThreads, smem, s>>>(SK, ldsk, s_rows, l, T, Lrows, ldt, info, deadmask, flag_dead, cond_flag);
   return cudaGetLastError();
@@ -871,12 +867,10 @@ cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrow
                             const int* cond_flag, cudaStream_t s) {
   if (l > 128) return cudaErrorInvalidValue;
   const size_t smem = (size_t)l * (l + 1) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // function attributes are per device: set on every launch (about a microsecond)
     // the kernel also has ~5 KB of static shared memory: leave room for it under the 227 KB limit
     cudaError_t e = cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   chol_inv_kernel<<<1, 512, smem, s>>>(G, ldg, l, T, Lrows, ldt, mode, global_rows, flag3, info, dinfo, deadmask,
                                        flag_dead, cond_flag);
@@ -901,13 +895,11 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
   if (2 * mat + small <= cap) { w_smem = 1; v_smem = 1; }
   else if (mat + small <= cap) { w_smem = 1; }
   const size_t smem = (w_smem + v_smem) * mat + small;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // function attributes are per device: set on every launch (about a microsecond)
     cudaError_t e = cudaFuncSetAttribute(jacobi_svd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(jacobi_svd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (w_smem && v_smem)
     jacobi_svd_kernel<true><<<1, kJacobiThreads, smem, s>>>(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, scratch, 1, 1, transpose, info);
