@@ -483,3 +483,61 @@ def test_full_size_c2_properties(cb):
     assert float((vt @ vt.T - eye).abs().max()) < 1e-12
     assert float(((s.ravel() - sig[:k]).abs() / sig[:k]).max()) < 1e-10
     assert float(torch.linalg.matrix_norm(v0[:, :k] - vt.T @ (vt @ v0[:, :k]), 2)) < 1e-8
+
+
+def test_fuzz_random_shapes_layouts_parameters(cb):
+    """40 seeded random problems: shapes from 1 to a few thousand, every layout, random (k, q, p); singular values and the
+    rank-k reconstruction against the oracle (vectors can differ by sign / rotation inside clusters)."""
+    rng = np.random.default_rng(2026)
+    for case in range(40):
+        m = int(rng.integers(1, 2500))
+        n = int(rng.integers(1, 260))
+        if rng.random() < 0.3:
+            m, n = n, m                                        # fat
+        thin_cols = min(m, n)
+        k = int(rng.integers(1, min(thin_cols, 100) + 1))
+        p = int(rng.integers(0, 20))
+        if k + p > 128:
+            p = 128 - k
+        q = int(rng.integers(0, 7))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            a = rng.standard_normal((m, n))
+        elif kind == 1:                                        # low rank + noise
+            r = int(rng.integers(1, thin_cols + 1))
+            a = rng.standard_normal((m, r)) @ rng.standard_normal((r, n)) + 1e-3 * rng.standard_normal((m, n))
+        else:                                                  # exactly rank deficient
+            r = max(1, thin_cols // 3)
+            a = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+        layout = rng.integers(0, 4)
+        if layout == 1:
+            a_in = np.asfortranarray(a)
+        elif layout == 2:                                      # strided view (every other column of a wider buffer)
+            wide = np.zeros((m, 2 * n)); wide[:, ::2] = a; a_in = wide[:, ::2]
+        elif layout == 3:                                      # offset sub-view with odd pitch
+            wide = np.zeros((m + 1, n + 3)); wide[1:, 1:n + 1] = a; a_in = wide[1:, 1:n + 1]
+        else:
+            a_in = a
+        l = min(k + p, thin_cols)
+        omega = rng.standard_normal((thin_cols, l))
+        ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+        u, s, vt = (np.asarray(x) for x in cb.rsvd(a_in, k, q, p, omega=omega, seed=case))
+        tag = f"case {case}: {m}x{n} k={k} q={q} p={p} kind={kind} layout={layout}"
+        assert u.shape == (m, k) and s.shape == (k, 1) and vt.shape == (k, n), tag
+        s0 = ref[1].ravel()
+        scale = max(float(s0[0]), 1e-300)
+        # parity class (SURVEY F9): direction j survives the reference's raw power iterations with relative weight
+        # (sigma_j / sigma_1)^(2 min(q, 3) + 1) in Y; below ~1e-6 the reference itself is not reproducible, so only the
+        # components above that are compared tightly (the rest must merely be finite and no larger than the reference's)
+        expo = 2 * min(q, 3) + 1
+        elig = (s0 / scale) ** expo > 1e-6
+        ne = int(np.sum(elig))
+        assert ne >= 1, tag
+        assert np.max(np.abs(s.ravel()[:ne] - s0[:ne])) < 1e-9 * scale, tag
+        rec = u[:, :ne] @ np.diag(s.ravel()[:ne]) @ vt[:ne]
+        rec0 = ref[0][:, :ne] @ np.diag(s0[:ne]) @ ref[2][:ne]
+        gap_ok = ne == k or (s0[ne - 1] - s0[ne]) > 1e-3 * scale      # a cluster cut in two is not comparable
+        if gap_ok:
+            assert np.max(np.abs(rec - rec0)) < 1e-6 * scale, tag
+        assert np.all(np.isfinite(u)) and np.all(np.isfinite(vt)) and np.all(np.isfinite(s)), tag
+        assert np.all(s.ravel() <= 1.001 * scale + 1e-300), tag
