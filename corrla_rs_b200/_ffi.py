@@ -47,6 +47,7 @@ class Timings(C.Structure):
         ("pass_ms", C.c_double),
         ("pass_flops", C.c_double),
         ("p2p_exchanges", C.c_int),
+        ("streamed_chunks", C.c_int),
     ]
 
     def as_dict(self):

@@ -27,6 +27,7 @@ struct corrla_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host->device chunks of A while the main stream computes on earlier chunks
   std::mutex mu;
   struct Buf { void* p = nullptr; size_t bytes = 0; };
   std::map<std::string, Buf> pool;
@@ -69,6 +70,7 @@ struct corrla_ctx {
     bounce.release();
     if (hflag) cudaFreeHost(hflag);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 
@@ -116,6 +118,7 @@ int ctx_create(int device, corrla_ctx** out) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) == cudaSuccess) c->num_sms = p.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&c->hflag), 64) != cudaSuccess) {
     set_last_error("cudaStreamCreate / cudaMallocHost failed");
     delete c;
@@ -153,6 +156,7 @@ struct Core {
   double *mu = nullptr, *bvec = nullptr, *sum_partials = nullptr;
   uint64_t refill_seed = 0x5eedu; uint64_t refill_stream = 0; int qr_calls = 0;
   int launches = 0;
+  int64_t chunk_rows = 0;   // > 0: the first two passes run per row chunk while A is still arriving from the host
 
   size_t small_elems() const { return (size_t)L16 * ld; }
 
@@ -177,6 +181,7 @@ struct Core {
       np = std::max(np, (size_t)t * 8);
     };
     need(m, n); need(n, m); need(Lc, m); need(m, Lc);
+    if (chunk_rows > 0) { need(chunk_rows, n); need(n, chunk_rows); need(m % chunk_rows ? m % chunk_rows : chunk_rows, n); need(n, m % chunk_rows ? m % chunk_rows : chunk_rows); }
     ws = std::max(ws, sketch_ws_bytes(Lc, ctx->num_sms));
     if (need_z) { need(Lc, n); need(n, Lc); need(Lc, Lc); }
     gw.num_sms = ctx->num_sms;
@@ -432,16 +437,75 @@ struct Core {
   int n_robust = 0, n_refill = 0;
 
 
-  // power iteration with the reference schedule; leaves Y and Tf such that Q = Y * Tf
-  int power_iter(const double* omega_dev_packed, uint64_t seed, int n_iter, int schedule) {
-    if (omega_dev_packed == nullptr) {
-      cudaError_t e = philox_normal_launch(Za, n, l, ld, seed, st);
-      ++launches;
-      if (e != cudaSuccess) { set_last_error("philox launch failed: %s", cudaGetErrorString(e)); return CORRLA_ERR_CUDA; }
+  // Omega (n x l, standard normal, Philox counter = element index) into Za     random_svd.rs:27
+  int draw_omega(uint64_t seed) {
+    cudaError_t e = philox_normal_launch(Za, n, l, ld, seed, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("philox launch failed: %s", cudaGetErrorString(e)); return CORRLA_ERR_CUDA; }
+    return CORRLA_OK;
+  }
+
+  // Host-resident A: copy it in row chunks on the copy stream and run the first product Y = A*Omega -- and, when
+  // `with_second` is set, the first Z = A^T*Y as a running sum -- chunk by chunk behind the copies, so that the two
+  // passes cost no time on top of the transfer.  Leaves `av` describing the full resident matrix.
+  // `a` is the thin matrix on the host with strides (rs, cs); rowmajor_like says which stride is 1.
+  int stream_in(const double* a, int64_t rs, int64_t cs, bool rowmajor_like, bool with_second, int* n_chunks) {
+    const int64_t inner = rowmajor_like ? n : m, outer = rowmajor_like ? m : n;
+    const int64_t src_ld = rowmajor_like ? rs : cs;
+    const int64_t ldd = round_up(inner, 2);
+    double* buf = static_cast<double*>(ctx->get("A", (size_t)outer * ldd * 8));
+    if (!buf) { set_last_error("device allocation for A failed (%lld x %lld)", (long long)m, (long long)n); return CORRLA_ERR_ALLOC; }
+    av = MatView{buf, inner, outer, ldd};
+    a_rowmajor = rowmajor_like;
+    const int nch = (int)((m + chunk_rows - 1) / chunk_rows);
+    double* slots = static_cast<double*>(ctx->get("chunk_nu2", (size_t)nch * 8));
+    cudaEvent_t ev = ctx->event(0);           // re-recorded per chunk: a stream wait binds to the record before it
+    if (!slots || !ev) { set_last_error("allocation failed (streamed input)"); return CORRLA_ERR_ALLOC; }
+    cudaStream_t cst = ctx->copy_stream;
+    // earlier work on the compute stream may still read the A buffer (context reuse without a sync in between)
+    CU_TRY(cudaEventRecord(ev, st));
+    CU_TRY(cudaStreamWaitEvent(cst, ev, 0));
+    double* nu2 = Zb + (size_t)n16 * ld + Lc;
+    int status = CORRLA_OK;
+    for (int ci = 0; ci < nch && status == CORRLA_OK; ++ci) {
+      const int64_t r0 = (int64_t)ci * chunk_rows, rc = std::min<int64_t>(chunk_rows, m - r0);
+      cudaError_t e;
+      MatView cv;
+      if (rowmajor_like) {
+        e = copy_h2d_2d(ctx->bounce, cst, buf + r0 * ldd, ldd * 8, a + r0 * src_ld, src_ld * 8, n * 8, rc, false);
+        cv = MatView{buf + r0 * ldd, n, rc, ldd};
+      } else {
+        e = copy_h2d_2d(ctx->bounce, cst, buf + r0, ldd * 8, a + r0, src_ld * 8, rc * 8, n, false);
+        cv = MatView{buf + r0, rc, n, ldd};
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(ev, cst);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+      if (e != cudaSuccess) { set_last_error("host->device copy of A failed: %s", cudaGetErrorString(e)); cudaGetLastError(); status = CORRLA_ERR_CUDA; break; }
+      double* Yc = Y + (size_t)r0 * ld;
+      status = mm(cv, a_rowmajor, Za, Yc, ld, 1, Lc, nullptr, slots + ci);
+      if (status == CORRLA_OK && with_second)
+        status = mm(cv, !a_rowmajor, Yc, Zb, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, ci > 0);
     }
+    // the caller may free or overwrite its matrix once we return: wait for the last DMA (the products stay queued)
+    cudaError_t e = cudaStreamSynchronize(cst);
+    ctx->bounce.in_flight[0] = ctx->bounce.in_flight[1] = false;
+    if (status != CORRLA_OK) return status;
+    if (e != cudaSuccess) { set_last_error("host->device copy of A failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    e = sum_array_launch(slots, nch, nu2, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("norm reduction launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    *n_chunks = nch;
+    return CORRLA_OK;
+  }
+
+  // power iteration with the reference schedule; leaves Y and Tf such that Q = Y * Tf
+  // resume: 0 = from scratch; 1 = Omega, Y = A*Omega and its norm are already there (streamed host path);
+  //         2 = additionally Zb = A^T*Y of the first iteration is there, summed over the ranks
+  int power_iter(const double* omega_dev_packed, uint64_t seed, int n_iter, int schedule, int resume = 0) {
+    if (omega_dev_packed == nullptr && resume == 0) ST_TRY(draw_omega(seed));
     // ||Y||_F^2 lives in the tail of Zb: the next A^T*Y sums it over the ranks together with Z
     double* nu2 = Zb + (size_t)n16 * ld + Lc;
-    ST_TRY(mm_AX(Za, Y, nullptr, nu2));                       // random_svd.rs:31
+    if (resume == 0) ST_TRY(mm_AX(Za, Y, nullptr, nu2));      // random_svd.rs:31
     for (int i = 0; i < n_iter; ++i) {                        // :35
       const bool do_qr = (schedule == 1) || (i > 2);          // :37
       if (do_qr) {
@@ -450,7 +514,7 @@ struct Core {
         ST_TRY(mm(view_rows(Zb, n), true, Tf, Za, ld, 1, Lc)); // fold R^-1 into the small side
         ST_TRY(mm_AX(Za, Y, nullptr, nu2));                   // :47-51
       } else {
-        ST_TRY(mm_AtY(Y, Zb));
+        if (!(i == 0 && resume == 2)) ST_TRY(mm_AtY(Y, Zb));
         ST_TRY(mm_AX(Zb, Y, nu2, nu2));                       // :47-51 with the deferred :53-55 scaling
       }
     }
@@ -609,13 +673,24 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   c.refill_stream = o.comm ? (uint64_t)o.comm->rank : 0;
   ST_TRY(c.setup_dims(m, n, l));
 
-  double h2d_ms = 0.0;
-  ST_TRY(stage_matrix(sc.ctx, sc.st, "A", a, m, n, trs, tcs, o.a_on_device != 0, &c.av, &c.a_rowmajor, &h2d_ms, &c.launches));
-  if (tm) tm->h2d_ms = h2d_ms;
-
   const bool want_center = (o.center != 0) && !power_only;
   if (want_center && fat && o.comm != nullptr) { set_last_error("centring of a fat matrix is not supported with a communicator"); return CORRLA_ERR_UNSUPPORTED; }
   c.center = (want_center && !fat) ? 1 : 0;       // tall: rank-1 corrections inside the passes
+
+  // Large host-resident inputs are streamed: the first product (and the first transposed product when the schedule
+  // starts without a QR and no other rank is involved) runs chunk by chunk behind the host->device copies.
+  const bool host_rowmajor = (tcs == 1 && trs >= n), host_colmajor = !host_rowmajor && (trs == 1 && tcs >= m);
+  int64_t stream_rows = 0;
+  if (!o.a_on_device && !want_center && (host_rowmajor || host_colmajor)) {
+    int64_t rows = ((int64_t)512 << 20) / (n * 8) / 128 * 128;
+    if (const char* env = getenv("CORRLA_B200_STREAM_ROWS")) rows = atoll(env) / 128 * 128;   // 0 disables
+    if (rows >= 128 && m > rows) stream_rows = rows;
+  }
+  c.chunk_rows = stream_rows;
+
+  double h2d_ms = 0.0;
+  if (stream_rows == 0)
+    ST_TRY(stage_matrix(sc.ctx, sc.st, "A", a, m, n, trs, tcs, o.a_on_device != 0, &c.av, &c.a_rowmajor, &h2d_ms, &c.launches));
   ST_TRY(c.alloc_workspace(true));
   ST_TRY(c.alloc_buffers(true));
 
@@ -656,6 +731,23 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     CU_TRY(cudaMemcpyAsync(means_out, c.mu, (size_t)cnt * 8, o.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sc.st));
   }
 
+  const double* omega_packed = nullptr;
+  if (o.omega != nullptr) {
+    ST_TRY(pack_small(sc.ctx, sc.st, o.omega, n, l, o.omega_rs, o.omega_cs, o.omega_on_device != 0, c.Za, c.ld, 1.0, &c.launches));
+    omega_packed = c.Za;
+  }
+  int resume = 0, n_chunks = 0;
+  if (stream_rows > 0) {
+    Timer t;
+    if (omega_packed == nullptr) ST_TRY(c.draw_omega(o.seed));
+    const bool single = (o.comm == nullptr || o.comm->nranks <= 1);
+    const bool with_second = single && n_iter >= 1 && o.schedule == 0;     // ranks could disagree on streaming: keep collectives out of it
+    ST_TRY(c.stream_in(a, trs, tcs, host_rowmajor, with_second, &n_chunks));
+    resume = with_second ? 2 : 1;
+    h2d_ms = t.ms();
+  }
+  if (tm) tm->h2d_ms = h2d_ms;
+
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (tm) {
     ev0 = sc.ctx->event(0); ev1 = sc.ctx->event(1);
@@ -663,13 +755,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     c.profile_passes = true;
     CU_TRY(cudaEventRecord(ev0, sc.st));
   }
-
-  const double* omega_packed = nullptr;
-  if (o.omega != nullptr) {
-    ST_TRY(pack_small(sc.ctx, sc.st, o.omega, n, l, o.omega_rs, o.omega_cs, o.omega_on_device != 0, c.Za, c.ld, 1.0, &c.launches));
-    omega_packed = c.Za;
-  }
-  ST_TRY(c.power_iter(omega_packed, o.seed, (int)n_iter, o.schedule));
+  ST_TRY(c.power_iter(omega_packed, o.seed, (int)n_iter, o.schedule, resume));
 
   const bool out_dev = o.out_on_device != 0;
   double d2h_ms = 0.0;
@@ -739,6 +825,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     }
     tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l;
     tm->p2p_exchanges = c.p2p_exchanges;
+    tm->streamed_chunks = n_chunks;
     if (o.comm != nullptr && o.comm->p2p) {
       int herr = 0;
       CU_TRY(cudaMemcpy(&herr, o.comm->err_flag, sizeof(int), cudaMemcpyDeviceToHost));

@@ -63,6 +63,7 @@ cudaError_t BounceBuffers::ensure(size_t want) {
     if (e != cudaSuccess) { release(); return e; }
   }
   bytes = want;
+  in_flight[0] = in_flight[1] = false;
   const unsigned hc = std::thread::hardware_concurrency();
   threads = (int)std::max(1u, std::min(16u, hc ? hc : 4u));
   return cudaSuccess;
@@ -70,6 +71,8 @@ cudaError_t BounceBuffers::ensure(size_t want) {
 
 void BounceBuffers::release() {
   for (int i = 0; i < 2; ++i) {
+    if (in_flight[i] && done[i]) cudaEventSynchronize(done[i]);
+    in_flight[i] = false;
     if (buf[i]) cudaFreeHost(buf[i]);
     if (done[i]) cudaEventDestroy(done[i]);
     buf[i] = nullptr; done[i] = nullptr;
@@ -78,31 +81,35 @@ void BounceBuffers::release() {
 }
 
 cudaError_t copy_h2d_2d(BounceBuffers& bb, cudaStream_t st, void* dst_dev, size_t dst_pitch, const void* src_host,
-                        size_t src_pitch, size_t row_bytes, size_t rows) {
+                        size_t src_pitch, size_t row_bytes, size_t rows, bool sync_at_end) {
   if (rows == 0 || row_bytes == 0) return cudaSuccess;
   cudaError_t e;
   if (is_pinned(src_host)) {
     e = cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(st);
+    return sync_at_end ? cudaStreamSynchronize(st) : cudaSuccess;
   }
   const size_t total = row_bytes * rows;
   const size_t chunk = std::min(kChunkBytes, std::max<size_t>(total, 4096));
   if ((e = bb.ensure(std::max(chunk, row_bytes))) != cudaSuccess) return e;
   const size_t rows_per = std::max<size_t>(1, bb.bytes / row_bytes);
-  bool used[2] = {false, false};
   int slot = 0;
   for (size_t r = 0; r < rows; r += rows_per, slot ^= 1) {
     const size_t nr = std::min(rows_per, rows - r);
-    if (used[slot] && (e = cudaEventSynchronize(bb.done[slot])) != cudaSuccess) return e;
+    if (bb.in_flight[slot]) {
+      if ((e = cudaEventSynchronize(bb.done[slot])) != cudaSuccess) return e;
+      bb.in_flight[slot] = false;
+    }
     par_copy_2d(static_cast<char*>(bb.buf[slot]), row_bytes, static_cast<const char*>(src_host) + r * src_pitch,
                 src_pitch, row_bytes, nr, bb.threads);
     e = cudaMemcpy2DAsync(static_cast<char*>(dst_dev) + r * dst_pitch, dst_pitch, bb.buf[slot], row_bytes, row_bytes, nr,
                           cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(bb.done[slot], st)) != cudaSuccess) return e;
-    used[slot] = true;
+    bb.in_flight[slot] = true;
   }
+  if (!sync_at_end) return cudaSuccess;
+  bb.in_flight[0] = bb.in_flight[1] = false;
   return cudaStreamSynchronize(st);
 }
 
@@ -131,6 +138,8 @@ cudaError_t copy_d2h_2d(BounceBuffers& bb, cudaStream_t st, void* dst_host, size
   const size_t total = row_bytes * rows;
   const size_t chunk = std::min(kChunkBytes, std::max<size_t>(total, 4096));
   if ((e = bb.ensure(std::max(chunk, row_bytes))) != cudaSuccess) return e;
+  for (int i = 0; i < 2; ++i)
+    if (bb.in_flight[i]) { if ((e = cudaEventSynchronize(bb.done[i])) != cudaSuccess) return e; bb.in_flight[i] = false; }
   const size_t rows_per = std::max<size_t>(1, bb.bytes / row_bytes);
   const size_t nchunks = (rows + rows_per - 1) / rows_per;
   auto issue = [&](size_t ci) -> cudaError_t {

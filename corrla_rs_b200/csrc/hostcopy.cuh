@@ -10,15 +10,17 @@ namespace corrla {
 struct BounceBuffers {
   void* buf[2] = {nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
+  bool in_flight[2] = {false, false};   // a DMA out of this slot may still be running (cleared by waiting on done[])
   size_t bytes = 0;
   int threads = 4;
   cudaError_t ensure(size_t want);
   void release();
 };
 
-// rows x row_bytes block, pitches in bytes.  Synchronous with respect to the host on return.
+// rows x row_bytes block, pitches in bytes.  With sync_at_end the call returns when the data is on the device; without
+// it the last DMA may still be in flight on `st` (the source must stay valid; bounce slots are tracked across calls).
 cudaError_t copy_h2d_2d(BounceBuffers& bb, cudaStream_t st, void* dst_dev, size_t dst_pitch, const void* src_host,
-                        size_t src_pitch, size_t row_bytes, size_t rows);
+                        size_t src_pitch, size_t row_bytes, size_t rows, bool sync_at_end = true);
 cudaError_t copy_d2h_2d(BounceBuffers& bb, cudaStream_t st, void* dst_host, size_t dst_pitch, const void* src_dev,
                         size_t src_pitch, size_t row_bytes, size_t rows);
 

@@ -553,6 +553,11 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
   *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM * 8;   // 8 consumer warps per work item
 }
 
+cudaError_t sum_array_launch(const double* partials, int64_t n, double* slot, cudaStream_t stream) {
+  sumsq_finalize_kernel<<<1, 1024, 0, stream>>>(partials, n, slot, nullptr);
+  return cudaGetLastError();
+}
+
 cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, int Lc, int64_t Mside, double* out,
                                    int64_t ld, const PeerExchange* px, size_t x_count, const int* cond_flag,
                                    int num_sms, cudaStream_t stream, int* launches) {

@@ -86,6 +86,9 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
 
 bool tma_compatible(const MatView& v);
 
+// *slot = partials[0] + ... + partials[n-1] in index order (one CTA).
+cudaError_t sum_array_launch(const double* partials, int64_t n, double* slot, cudaStream_t stream);
+
 // Sum `splits` partial blocks laid out like the split-K workspace ([split][rows_pad][Lc], rows_pad a multiple of 128)
 // into out (row-major, pitch ld, Mside valid rows); with px != nullptr the sum also runs over the ranks (x_count doubles).
 cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, int Lc, int64_t Mside, double* out,

@@ -85,6 +85,7 @@ typedef struct corrla_timings {
   double pass_ms;          /* summed CUDA-event duration of those launches (the dominant kernel) */
   double pass_flops;       /* algorithmic flops of one such launch on this GPU: 2 * local_rows * ncols * l */
   int p2p_exchanges;       /* cross-rank sums done inside the reduction kernel over NVLink peer memory (0 => NCCL only) */
+  int streamed_chunks;     /* host input: row chunks whose first product(s) ran behind the host->device copy (0 = copied first) */
 } corrla_timings;
 
 CORRLA_API void corrla_rsvd_opts_default(corrla_rsvd_opts* opts);

@@ -52,6 +52,7 @@ pub struct corrla_timings {
     pub pass_ms: f64,
     pub pass_flops: f64,
     pub p2p_exchanges: c_int,
+    pub streamed_chunks: c_int,
 }
 
 extern "C" {

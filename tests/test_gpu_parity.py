@@ -541,3 +541,56 @@ def test_fuzz_random_shapes_layouts_parameters(cb):
             assert np.max(np.abs(rec - rec0)) < 1e-6 * scale, tag
         assert np.all(np.isfinite(u)) and np.all(np.isfinite(vt)) and np.all(np.isfinite(s)), tag
         assert np.all(s.ravel() <= 1.001 * scale + 1e-300), tag
+
+
+# ------------------------------------------------------------------ streamed host input
+@pytest.mark.parametrize("layout", ["row", "col"])
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("q,schedule", [(4, "reference"), (0, "reference"), (5, "reference"), (2, "stabilised")])
+def test_streamed_host_input_matches_resident(cb, monkeypatch, layout, pinned, q, schedule):
+    """Host matrices above the streaming threshold are copied in row chunks with the first product(s) running behind
+    the copies (engine.cu stream_in).  Forced here with a 256-row chunk on a small matrix (ragged last chunk): same
+    factors as the copy-then-compute path up to summation order, and the same parity with the oracle."""
+    import torch
+    rng = np.random.default_rng(77)
+    m, n, k, p = 2000 + 72, 96, 12, 6
+    a = lowrank_noise(rng, m, n, 20, 1e-3)
+    omega = rng.standard_normal((n, k + p))
+    if layout == "col":
+        a = np.asfortranarray(a)
+    if pinned:
+        t = torch.from_numpy(a.T if layout == "col" else a).contiguous().pin_memory()
+        host = t.numpy().T if layout == "col" else t.numpy()
+        assert np.array_equal(host, a)
+    else:
+        host = a
+    monkeypatch.setenv("CORRLA_B200_STREAM_ROWS", "0")
+    base = cb.rsvd(host, k, q, p, omega=omega, schedule=schedule)
+    assert cb.last_timings()["streamed_chunks"] == 0
+    monkeypatch.setenv("CORRLA_B200_STREAM_ROWS", "256")
+    out = cb.rsvd(host, k, q, p, omega=omega, schedule=schedule)
+    t = cb.last_timings()
+    assert t["streamed_chunks"] == 9
+    assert t["pass_launches"] == 2 + 2 * q - (2 if (q >= 1 and schedule == "reference") else 1)
+    assert_parity(out, base, k, tol_sigma=1e-12, tol_angle=1e-10)
+    if schedule == "reference":
+        assert_parity(out, ref_rsvd.random_svd(a, k, q, p, omega=omega), k)
+
+
+def test_streamed_host_input_drawn_omega_and_power_iter(cb, monkeypatch):
+    """Streaming with the engine's own Philox Omega (same seed => same Omega as the resident path) and through
+    corrla_power_iter_f64."""
+    rng = np.random.default_rng(78)
+    m, n, k, p, q = 3000, 64, 10, 6, 3
+    a = lowrank_noise(rng, m, n, 16, 1e-4)
+    monkeypatch.setenv("CORRLA_B200_STREAM_ROWS", "0")
+    base = cb.rsvd(a, k, q, p, seed=5)
+    qb = cb.power_iter(a, 16, q, seed=5)
+    monkeypatch.setenv("CORRLA_B200_STREAM_ROWS", "512")
+    out = cb.rsvd(a, k, q, p, seed=5)
+    assert cb.last_timings()["streamed_chunks"] == 6
+    assert_parity(out, base, k, tol_sigma=1e-12, tol_angle=1e-10)
+    qs = cb.power_iter(a, 16, q, seed=5)
+    assert cb.last_timings()["streamed_chunks"] == 6
+    assert ref_rsvd.subspace_sine(qb, qs) < 1e-10
+    assert np.max(np.abs(qs.T @ qs - np.eye(16))) < 1e-12
