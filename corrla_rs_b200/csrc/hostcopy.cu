@@ -80,6 +80,23 @@ void BounceBuffers::release() {
   bytes = 0;
 }
 
+void PreTouch::add(void* p, size_t bytes) {
+  if (p == nullptr || bytes < ((size_t)64 << 20) || is_pinned(p)) return;
+  const int nt = 4;
+  const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  for (int t = 0; t < nt; ++t) {
+    const size_t b0 = std::min(bytes, (size_t)t * per), b1 = std::min(bytes, b0 + per);
+    if (b1 <= b0) continue;
+    volatile char* base = static_cast<volatile char*>(p);
+    th.emplace_back([base, b0, b1] { for (size_t off = b0; off < b1; off += 4096) base[off] = 0; });
+  }
+}
+
+void PreTouch::join() {
+  for (auto& t : th) if (t.joinable()) t.join();
+  th.clear();
+}
+
 cudaError_t copy_h2d_2d(BounceBuffers& bb, cudaStream_t st, void* dst_dev, size_t dst_pitch, const void* src_host,
                         size_t src_pitch, size_t row_bytes, size_t rows, bool sync_at_end) {
   if (rows == 0 || row_bytes == 0) return cudaSuccess;

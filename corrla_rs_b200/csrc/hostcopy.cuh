@@ -5,6 +5,9 @@
 #include <cstddef>
 #include <cuda_runtime.h>
 
+#include <thread>
+#include <vector>
+
 namespace corrla {
 
 struct BounceBuffers {
@@ -23,5 +26,15 @@ cudaError_t copy_h2d_2d(BounceBuffers& bb, cudaStream_t st, void* dst_dev, size_
                         size_t src_pitch, size_t row_bytes, size_t rows, bool sync_at_end = true);
 cudaError_t copy_d2h_2d(BounceBuffers& bb, cudaStream_t st, void* dst_host, size_t dst_pitch, const void* src_dev,
                         size_t src_pitch, size_t row_bytes, size_t rows);
+
+// Fault in the pages of a pageable host OUTPUT buffer on helper threads while the GPU is still computing, so that the
+// device->host copy at the end of the call runs at DMA speed instead of page-fault speed (a fresh 3 GB numpy array
+// costs ~60 ms of first-touch faults).  Writes zeros: the buffer is about to be overwritten with the results.
+struct PreTouch {
+  std::vector<std::thread> th;
+  void add(void* p, size_t bytes);     // no-op for small, null or pinned buffers
+  void join();
+  ~PreTouch() { join(); }
+};
 
 }  // namespace corrla
