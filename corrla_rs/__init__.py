@@ -1,18 +1,23 @@
 """Drop-in module name of the reference's pyo3 extension (`import corrla_rs`, Cargo.toml:7,
-src/lib_math_utils_py.rs:17-18).  The RSVD hot path is provided: `corrla_rs.rsvd(a_mat, n_rank,
-n_iters, n_oversamples)` with the reference's positional signature (src/lib_math_utils_py.rs:21-23,
-examples/benchmark_rsvd.py:101), executed by the B200 engine, and its first consumer `corrla_rs.rpca` (:38-55, PCA with the centring fused into
-the passes).  The other functions of the reference
-module (active_ss, cs_*, PyRbfInterp, PyPodI, PyDMDc) are out of scope and raise on access."""
-from corrla_rs_b200 import rpca, rsvd  # noqa: F401
+src/lib_math_utils_py.rs:17-18), executed by the B200 engine:
 
-_OUT_OF_SCOPE = ("active_ss", "cs_dirichlet_sample", "cs_mcmc_dirichlet_sample", "PyRbfInterp", "PyPodI",
-                 "PyDMDc")
+  * `corrla_rs.rsvd(a_mat, n_rank, n_iters, n_oversamples)`  -- the hot path (lib_math_utils_py.rs:21-36,
+    examples/benchmark_rsvd.py:101);
+  * `corrla_rs.rpca(a_mat, n_rank, n_iters, n_oversamples)`  -- PCA with the centring fused into the passes (:38-55);
+  * `corrla_rs.PyDMDc(x, u, n_modes, n_iters).predict(x0, u)` -- DMD with control (:255-283);
+  * `corrla_rs.PyPodI(x, t, n_modes).predict(t)` and `corrla_rs.PyRbfInterp` -- POD with interpolated weights (:172-250).
+
+The remaining functions of the reference module (active_ss, cs_dirichlet_sample, cs_mcmc_dirichlet_sample) do not sit on
+the RSVD hot path, are out of scope and raise on access."""
+from corrla_rs_b200 import rpca, rsvd  # noqa: F401
+from corrla_rs_b200.rom import PyDMDc, PyPodI, PyRbfInterp  # noqa: F401
+
+_OUT_OF_SCOPE = ("active_ss", "cs_dirichlet_sample", "cs_mcmc_dirichlet_sample")
 
 
 def __getattr__(name):
     if name in _OUT_OF_SCOPE:
         raise NotImplementedError(
-            f"corrla_rs.{name} is outside the scope of the B200 engine (only the RSVD hot path is replaced); "
-            "use the reference crate for it")
+            f"corrla_rs.{name} is outside the scope of the B200 engine (only the RSVD hot path and the reduced-order "
+            "models built directly on it are replaced); use the reference crate for it")
     raise AttributeError(name)

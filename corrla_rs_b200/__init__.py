@@ -22,7 +22,8 @@ from . import _ffi
 from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 
 __all__ = ["rsvd", "random_svd", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
-           "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings"]
+           "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings",
+           "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights"]
 
 _SCHEDULES = {"reference": 0, "stabilised": 1, "stabilized": 1, 0: 0, 1: 1}
 _tls = threading.local()
@@ -383,3 +384,6 @@ def thin_q(a_mat, *, ctx: Context | None = None, comm: ShardComm | None = None, 
                                C.byref(o), _ptr(q), C.byref(rank))
     _ffi.check(st)
     return (q, rank.value) if return_rank else q
+
+
+from .rom import DMDc, PodI, RbfInterp, dmdc_operators, pod_modes_weights  # noqa: E402,F401

@@ -69,6 +69,11 @@ SYMBOLS = {
                                         C.c_double, C.c_int, C.POINTER(RsvdOpts)]),
     "corrla_random_mat_normal_f64": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                                C.POINTER(RsvdOpts)]),
+    "corrla_dmdc_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int64, C.c_int64, C.c_size_t, C.c_size_t, C.POINTER(RsvdOpts), C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
+    "corrla_pod_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
+                                 C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
     "corrla_thin_q_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                     C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(C.c_int)]),
     "corrla_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -1,0 +1,314 @@
+// Reduced-order models that sit directly on the RSVD: DMD with control
+// (dmd_rom.rs:46-146) and POD modes/weights (pod_rom.rs:53-75).  Everything that touches the tall snapshot matrix
+// runs through the same skinny DMMA GEMM as the RSVD passes; the r x r eigendecomposition (DMDc) and the
+// n_snap x n_snap RBF interpolation (POD) stay with the caller, as they are negligible and not data-parallel.
+#include "engine_core.cuh"
+
+using namespace corrla_eng;
+
+namespace {
+
+// X[i][j] *= pinv_diag(s)[j] for j < r  (mat_pinv_diag, mat_utils.rs:386-402: 0 if |s| < 1e-20 else 1/(s + 1e-20))
+__global__ void __launch_bounds__(256)
+scale_cols_pinv_kernel(double* __restrict__ X, int64_t rows, int r, int64_t ld, const double* __restrict__ s) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * r) return;
+  const int64_t i = idx / r;
+  const int j = (int)(idx - i * r);
+  const double sv = s[j];
+  const double inv = (sv < 1.0e-20 && sv > -1.0e-20) ? 0.0 : 1.0 / (sv + 1.0e-20);
+  X[i * ld + j] *= inv;
+}
+
+struct RomBufs {
+  corrla_ctx* ctx;
+  cudaStream_t st;
+  // zero-filled pool buffer
+  double* zeros(const char* name, size_t elems) {
+    double* p = static_cast<double*>(ctx->get(name, elems * 8));
+    if (p != nullptr && cudaMemsetAsync(p, 0, elems * 8, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  }
+  double* raw(const char* name, size_t elems) { return static_cast<double*>(ctx->get(name, elems * 8)); }
+};
+
+// Copy one strided block (rows x T) into rows [off, off + rows) of the column-major stack D (pitch ld).
+int stage_block(corrla_ctx* ctx, cudaStream_t st, const double* src, int64_t rows, int64_t T, int64_t rs, int64_t cs,
+                bool on_device, double* D, int64_t ld, int64_t off, double* h2d_ms, int* launches) {
+  if (rows == 0) return CORRLA_OK;
+  cudaError_t e;
+  if (on_device) {
+    e = repack_launch(src, T, rows, cs, rs, D + off, ld, st);      // D[t*ld + off + i] = src[i*rs + t*cs]
+    ++*launches;
+  } else if (rs == 1 && cs >= rows) {
+    Timer t;
+    e = copy_h2d_2d(ctx->bounce, st, D + off, ld * 8, src, cs * 8, rows * 8, T);
+    *h2d_ms += t.ms();
+  } else {
+    MatView v; bool rm = true;
+    ST_TRY(stage_matrix(ctx, st, "rom_raw", src, rows, T, rs, cs, false, &v, &rm, h2d_ms, launches));
+    e = rm ? repack_launch(v.p, T, rows, 1, v.ld, D + off, ld, st) : repack_launch(v.p, T, rows, v.ld, 1, D + off, ld, st);
+    ++*launches;
+  }
+  if (e != cudaSuccess) { set_last_error("staging of the snapshot matrix failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  return CORRLA_OK;
+}
+
+int copy_out(corrla_ctx* ctx, cudaStream_t st, double* dst_host, const double* src_dev, size_t elems) {
+  if (dst_host == nullptr || elems == 0) return CORRLA_OK;
+  CU_TRY(copy_d2h_2d(ctx->bounce, st, dst_host, elems * 8, src_dev, elems * 8, elems * 8, 1));
+  return CORRLA_OK;
+}
+
+void add_timings(corrla_timings* acc, const corrla_timings& t) {
+  acc->device_ms += t.device_ms; acc->gpu_launches += t.gpu_launches; acc->passes_over_a += t.passes_over_a;
+  acc->qr_third_passes += t.qr_third_passes; acc->qr_refills += t.qr_refills; acc->jacobi_sweeps += t.jacobi_sweeps;
+  acc->live_columns = t.live_columns; acc->pass_launches += t.pass_launches; acc->pass_ms += t.pass_ms;
+  acc->pass_flops = t.pass_flops;
+}
+
+int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_cs, const double* u, int64_t n_u,
+              int64_t u_rs, int64_t u_cs, size_t n_modes, size_t n_iters, const corrla_rsvd_opts* opts_in,
+              const double* omega_y, double* a_til, double* b, double* modes_scale, double* s_til, double* u_hat,
+              corrla_timings* tm) {
+  Timer total;
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  corrla_timings acc;
+  memset(&acc, 0, sizeof(acc));
+  if (tm) memset(tm, 0, sizeof(*tm));
+  if (x == nullptr || n_x <= 0 || T < 2 || n_u < 0 || (n_u > 0 && u == nullptr)) { set_last_error("bad snapshot / control matrix"); return CORRLA_ERR_INVALID; }
+  if (o.comm != nullptr) { set_last_error("corrla_dmdc_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  if (o.center != 0) { set_last_error("centring is not part of DMDc"); return CORRLA_ERR_INVALID; }
+  const int64_t M = n_x + n_u, nn = T - 1;
+  const int r = (int)std::min<size_t>(n_modes, 1 << 20);
+  if (r <= 0) { set_last_error("n_modes must be positive"); return CORRLA_ERR_INVALID; }
+  // the reference indexes r columns out of l = min(r + 12, thin columns) (random_svd.rs:77,98): it panics beyond
+  if ((int64_t)r > std::min<int64_t>(n_x, nn)) {
+    set_last_error("n_modes=%d exceeds min(n_x, n_snapshots - 1)=%lld (the reference panics here)", r, (long long)std::min<int64_t>(n_x, nn));
+    return CORRLA_ERR_RANK;
+  }
+
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  RomBufs rb{ctx, st};
+  int launches = 0;
+  double h2d_ms = 0.0;
+  const bool in_dev = o.a_on_device != 0, out_dev = o.out_on_device != 0;
+
+  // ---- the stacked snapshots [x; u], column-major, once (mat_vstack, dmd_rom.rs:66)
+  const int64_t ldD = round_up(M, 2);
+  double* D = rb.raw("rom_stack", (size_t)T * ldD);
+  if (!D) { set_last_error("device allocation for the snapshot stack failed (%lld x %lld)", (long long)M, (long long)T); return CORRLA_ERR_ALLOC; }
+  ST_TRY(stage_block(ctx, st, x, n_x, T, x_rs, x_cs, in_dev, D, ldD, 0, &h2d_ms, &launches));
+  ST_TRY(stage_block(ctx, st, u, n_u, T, u_rs, u_cs, in_dev, D, ldD, n_x, &h2d_ms, &launches));
+  const double* Xv = D;            // _X: all rows, snapshots 0 .. T-2      (:148-153)
+  const double* Yv = D + ldD;      // _Y: state rows, snapshots 1 .. T-1    (:156-162)
+
+  // ---- the two RSVDs (:72, :82), results stay on the device
+  double* Util = rb.raw("rom_util", (size_t)M * r);
+  double* Stil = rb.raw("rom_stil", (size_t)r + 8);
+  double* Vttil = rb.raw("rom_vttil", (size_t)r * nn);
+  double* Uhat = (out_dev && u_hat) ? u_hat : rb.raw("rom_uhat", (size_t)n_x * r);
+  double* Shat = rb.raw("rom_shat", (size_t)r + 8);
+  double* Vthat = rb.raw("rom_vthat", (size_t)r * nn);
+  if (!Util || !Stil || !Vttil || !Uhat || !Shat || !Vthat) { set_last_error("device allocation failed (DMDc factors)"); return CORRLA_ERR_ALLOC; }
+  corrla_rsvd_opts oi = o;
+  oi.a_on_device = 1; oi.out_on_device = 1; oi.ctx = ctx; oi.stream = st; oi.device = ctx->device;
+  corrla_timings t1, t2;
+  ST_TRY(rsvd_impl(Xv, M, nn, 1, ldD, (size_t)r, n_iters, 12, &oi, Util, Stil, Vttil, &t1, false, nullptr));
+  oi.omega = omega_y;
+  oi.seed = o.seed + 1;
+  ST_TRY(rsvd_impl(Yv, n_x, nn, 1, ldD, (size_t)r, n_iters, 12, &oi, Uhat, Shat, Vthat, &t2, false, nullptr));
+  add_timings(&acc, t1);
+  add_timings(&acc, t2);
+
+  // ---- products on the tall side, all with l = r columns
+  Core c;
+  c.ctx = ctx; c.st = st;
+  ST_TRY(c.setup_dims(std::max(n_x, nn), std::min(n_x, nn), r));
+  ST_TRY(c.alloc_workspace(true));
+  const int Lc = c.Lc, ld = c.ld, L16 = c.L16;
+  const int64_t nx16 = round_up(n_x, 16), nn16 = round_up(nn, 16);
+  double* Vs = rb.zeros("rom_vs", (size_t)nn16 * ld);
+  double* G2 = rb.zeros("rom_g2", (size_t)nn16 * ld);
+  double* P1 = rb.zeros("rom_p1", (size_t)nx16 * ld);
+  double* Uh = rb.zeros("rom_uh", (size_t)nx16 * ld);
+  double* U1 = rb.zeros("rom_u1", (size_t)nx16 * ld);
+  double* T0 = rb.zeros("rom_t0", (size_t)L16 * ld);
+  double* C1 = rb.zeros("rom_c1", (size_t)L16 * ld);
+  double* U2t = rb.zeros("rom_u2t", (size_t)L16 * ld);
+  if (!Vs || !G2 || !P1 || !Uh || !U1 || !T0 || !C1 || !U2t) { set_last_error("device allocation failed (DMDc products)"); return CORRLA_ERR_ALLOC; }
+  double* H = P1;   // reused once tmp_op_scale is formed
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](const char* what) -> int {
+    if (e != cudaSuccess) { set_last_error("%s failed: %s", what, cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    return CORRLA_OK;
+  };
+  // Vs = v_til * pinv(diag(s_til))      v_til(i, j) = Vttil[j + i*r]                       (:74, :86-87)
+  e = repack_launch(Vttil, nn, r, r, 1, Vs, ld, st); ST_TRY(chk("repack"));
+  scale_cols_pinv_kernel<<<(unsigned)((nn * r + 255) / 256), 256, 0, st>>>(Vs, nn, r, ld, Stil);
+  e = cudaGetLastError(); ST_TRY(chk("column scaling"));
+  // row-major padded copies of u_hat and u_til_1 (n_x x r)                                  (:75-77)
+  e = repack_launch(Uhat, n_x, r, 1, n_x, Uh, ld, st); ST_TRY(chk("repack"));
+  e = repack_launch(Util, n_x, r, 1, M, U1, ld, st); ST_TRY(chk("repack"));
+  launches += 4;
+  const MatView yv{Yv, n_x, nn, ldD};                       // column-major: inner = state rows
+  // P1 = Y * v_til * s_inv  (one pass over Y);  tmp_op_scale = u_hat^T * P1                 (:90-94)
+  ST_TRY(c.mm(yv, false, Vs, P1, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
+  ST_TRY(c.mm(c.view_rows(Uh, n_x), false, P1, T0, ld, 1, Lc));
+  // C1 = u_til_1^T * u_hat;  a_til = tmp_op_scale * C1                                      (:95-97)
+  ST_TRY(c.mm(c.view_rows(U1, n_x), false, Uh, C1, ld, 1, Lc));
+  double* a_dev = (out_dev && a_til) ? a_til : rb.raw("rom_atil", (size_t)r * r + 8);
+  if (!a_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+  ST_TRY(c.mm(MatView{T0, (int64_t)Lc, (int64_t)r, (int64_t)ld}, true, C1, a_dev, 1, r, r));
+  // modes_scale = Y * (v_til * s_inv * C1)  (second pass over Y)                            (:133-139)
+  double* ms_dev = nullptr;
+  if (modes_scale != nullptr) {
+    ms_dev = out_dev ? modes_scale : rb.raw("rom_modes", (size_t)n_x * r);
+    if (!ms_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+    ST_TRY(c.mm(c.view_rows(Vs, nn), true, C1, G2, ld, 1, Lc));
+    ST_TRY(c.mm(yv, false, G2, ms_dev, 1, n_x, r, nullptr, nullptr, nullptr, 0, true));
+  }
+  // _B = u_hat * (tmp_op_scale * u_til_2^T) = (u_hat * tmp_op_scale) * u_til_2^T            (:100-106)
+  double* b_dev = nullptr;
+  if (b != nullptr && n_u > 0) {
+    b_dev = out_dev ? b : rb.raw("rom_b", (size_t)n_x * n_u);
+    if (!b_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+    ST_TRY(c.mm(c.view_rows(Uh, n_x), true, T0, H, ld, 1, Lc));
+    for (int64_t j0 = 0; j0 < n_u; j0 += Lc) {
+      const int w = (int)std::min<int64_t>(Lc, n_u - j0);
+      if (j0 > 0) CU_TRY(cudaMemsetAsync(U2t, 0, (size_t)L16 * ld * 8, st));
+      e = repack_launch(Util + n_x + j0, r, w, M, 1, U2t, ld, st); ST_TRY(chk("repack"));   // u_til_2^T panel: r x w
+      ++launches;
+      ST_TRY(c.mm(c.view_rows(H, n_x), true, U2t, b_dev + (size_t)j0 * n_x, 1, n_x, w));
+    }
+  }
+  launches += c.launches;
+
+  // ---- results
+  if (out_dev) {
+    if (s_til) CU_TRY(cudaMemcpyAsync(s_til, Stil, (size_t)r * 8, cudaMemcpyDeviceToDevice, st));
+    if (tm) CU_TRY(cudaStreamSynchronize(st));
+  } else {
+    CU_TRY(cudaStreamSynchronize(st));
+    Timer t;
+    if (a_til) CU_TRY(cudaMemcpy(a_til, a_dev, (size_t)r * r * 8, cudaMemcpyDeviceToHost));
+    if (s_til) CU_TRY(cudaMemcpy(s_til, Stil, (size_t)r * 8, cudaMemcpyDeviceToHost));
+    ST_TRY(copy_out(ctx, st, b_dev ? b : nullptr, b_dev, (size_t)n_x * n_u));
+    ST_TRY(copy_out(ctx, st, modes_scale, ms_dev, (size_t)n_x * r));
+    ST_TRY(copy_out(ctx, st, u_hat, Uhat, (size_t)n_x * r));
+    acc.d2h_ms = t.ms();
+  }
+  if (tm) {
+    *tm = acc;
+    tm->h2d_ms = h2d_ms;
+    tm->gpu_launches += launches;
+    tm->passes_over_a += 2;                 // the two extra passes over Y
+    tm->total_ms = total.ms();
+  }
+  return CORRLA_OK;
+}
+
+int pod_impl(const double* x, int64_t n_snap, int64_t n_points, int64_t rs, int64_t cs, size_t n_modes,
+             const corrla_rsvd_opts* opts_in, double* modes, double* weights, double* s, corrla_timings* tm) {
+  Timer total;
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  if (tm) memset(tm, 0, sizeof(*tm));
+  if (x == nullptr || n_snap <= 0 || n_points <= 0) { set_last_error("empty or null snapshot matrix"); return CORRLA_ERR_INVALID; }
+  if (o.comm != nullptr) { set_last_error("corrla_pod_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  if (o.center != 0) { set_last_error("centring is not part of PodI"); return CORRLA_ERR_INVALID; }
+  const int r = (int)std::min<size_t>(n_modes, 1 << 20);
+  const int64_t thin_cols = std::min(n_snap, n_points);
+  if (r <= 0) { set_last_error("n_modes must be positive"); return CORRLA_ERR_INVALID; }
+  if ((int64_t)r > thin_cols) {
+    set_last_error("n_modes=%d exceeds min(n_snapshots, n_points)=%lld (the reference panics here)", r, (long long)thin_cols);
+    return CORRLA_ERR_RANK;
+  }
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  RomBufs rb{ctx, st};
+  int launches = 0;
+  double h2d_ms = 0.0;
+  const bool out_dev = o.out_on_device != 0;
+
+  MatView xv; bool rm = true;
+  ST_TRY(stage_matrix(ctx, st, "rom_stack", x, n_snap, n_points, rs, cs, o.a_on_device != 0, &xv, &rm, &h2d_ms, &launches));
+  const int64_t drs = rm ? xv.ld : 1, dcs = rm ? 1 : xv.ld;
+
+  double* Sd = rb.raw("rom_stil", (size_t)r + 8);
+  double* Vt = rb.raw("rom_vttil", (size_t)r * n_points);
+  if (!Sd || !Vt) { set_last_error("device allocation failed (POD factors)"); return CORRLA_ERR_ALLOC; }
+  corrla_rsvd_opts oi = o;
+  oi.a_on_device = 1; oi.out_on_device = 1; oi.ctx = ctx; oi.stream = st; oi.device = ctx->device;
+  corrla_timings t1;
+  ST_TRY(rsvd_impl(xv.p, n_snap, n_points, drs, dcs, (size_t)r, 10, 10, &oi, nullptr, Sd, Vt, &t1, false, nullptr, true));   // pod_rom.rs:56
+
+  Core c;
+  c.ctx = ctx; c.st = st;
+  ST_TRY(c.setup_dims(std::max(n_snap, n_points), thin_cols, r));
+  ST_TRY(c.alloc_workspace(true));
+  const int64_t np16 = round_up(n_points, 16);
+  double* Mp = rb.zeros("rom_uh", (size_t)np16 * c.ld);
+  double* m_dev = (out_dev && modes) ? modes : rb.raw("rom_modes", (size_t)n_points * r);
+  double* w_dev = (out_dev && weights) ? weights : rb.raw("rom_b", (size_t)n_snap * r);
+  if (!Mp || !m_dev || !w_dev) { set_last_error("device allocation failed (POD products)"); return CORRLA_ERR_ALLOC; }
+  // modes(i, j) = Vt[j + i*r]  (v.transpose().to_owned(), :57)
+  cudaError_t e = repack_launch(Vt, n_points, r, r, 1, Mp, c.ld, st);
+  if (e == cudaSuccess && modes != nullptr) e = scatter_launch(Mp, n_points, r, c.ld, m_dev, 1, n_points, st);
+  launches += 2;
+  if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  // weights = x * modes: one more pass over the snapshots (:61-75)
+  if (weights != nullptr) ST_TRY(c.mm(xv, rm, Mp, w_dev, 1, n_snap, r, nullptr, nullptr, nullptr, 0, true));
+  launches += c.launches;
+
+  double d2h_ms = 0.0;
+  if (out_dev) {
+    if (s) CU_TRY(cudaMemcpyAsync(s, Sd, (size_t)r * 8, cudaMemcpyDeviceToDevice, st));
+    if (tm) CU_TRY(cudaStreamSynchronize(st));
+  } else {
+    CU_TRY(cudaStreamSynchronize(st));
+    Timer t;
+    if (s) CU_TRY(cudaMemcpy(s, Sd, (size_t)r * 8, cudaMemcpyDeviceToHost));
+    ST_TRY(copy_out(ctx, st, modes, m_dev, (size_t)n_points * r));
+    ST_TRY(copy_out(ctx, st, weights, w_dev, (size_t)n_snap * r));
+    d2h_ms = t.ms();
+  }
+  if (tm) {
+    *tm = t1;
+    tm->h2d_ms = h2d_ms; tm->d2h_ms = d2h_ms;
+    tm->gpu_launches += launches;
+    tm->passes_over_a += 1;
+    tm->total_ms = total.ms();
+  }
+  return CORRLA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int64_t x_rs, int64_t x_cs, const double* u, int64_t n_u,
+                    int64_t u_rs, int64_t u_cs, size_t n_modes, size_t n_iters, const corrla_rsvd_opts* opts,
+                    const double* omega_y, double* a_til, double* b, double* modes_scale, double* s_til, double* u_hat,
+                    corrla_timings* timings) {
+  try {
+    return dmdc_impl(x, n_x, n_snap, x_rs, x_cs, u, n_u, u_rs, u_cs, n_modes, n_iters, opts, omega_y, a_til, b,
+                     modes_scale, s_til, u_hat, timings);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+int corrla_pod_f64(const double* x, int64_t n_snap, int64_t n_points, int64_t row_stride, int64_t col_stride,
+                   size_t n_modes, const corrla_rsvd_opts* opts, double* modes, double* weights, double* s,
+                   corrla_timings* timings) {
+  try {
+    return pod_impl(x, n_snap, n_points, row_stride, col_stride, n_modes, opts, modes, weights, s, timings);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+}  // extern "C"

@@ -125,6 +125,36 @@ CORRLA_API int corrla_rpca_f64(const double* a, int64_t nrows, int64_t ncols, in
                     size_t n_rank, const corrla_rsvd_opts* opts, double* s, double* components, double* means,
                     corrla_timings* timings);
 
+/* DMD with control, DMDc::new / _calc_dmdc_modes / _calc_modes (src/lib_math_utils/dmd_rom.rs:46-146) behind the pyo3
+ * PyDMDc (lib_math_utils_py.rs:255-283): every step that touches the tall snapshot matrix.
+ *   x : n_x x n_snap snapshots, u : n_u x n_snap control inputs (element strides; both host or both device,
+ *       opts->a_on_device).  n_u may be 0 (plain DMD; the reference requires a control matrix).
+ *   The two RSVDs (:72, :82; n_oversamples = 12) run on the views [x; u][:, :n_snap-1] and x[:, 1:] of ONE device copy
+ *   of the stacked snapshots -- mat_vstack (:66) and the shifted copies are never materialised twice.
+ *   opts->omega / omega_y (optional, same stride/residency fields) inject the two sketch matrices, shaped
+ *   n_thin x l of the respective view (as corrla_rsvd_f64 takes them); otherwise Philox(seed), Philox(seed + 1).
+ * Outputs (host, or device with opts->out_on_device; all column-major; any may be NULL):
+ *   a_til       r x r      = self._A (:95-97, eq. 29)          r = n_modes
+ *   b           n_x x n_u  = self._B = u_hat * b_til (:100-106, eq. 30)
+ *   modes_scale n_x x r    = tmp_modes_scale (:133-139, eq. 36): modes_re/im = modes_scale * Re/Im(W), W = eigenvectors
+ *                            of a_til.  The r x r eigendecomposition (:116) stays with the caller.
+ *   s_til       r          singular values of the input space;  u_hat  n_x x r  basis of the output space
+ * opts->comm is not supported here (CORRLA_ERR_UNSUPPORTED). */
+CORRLA_API int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int64_t x_rs, int64_t x_cs,
+                    const double* u, int64_t n_u, int64_t u_rs, int64_t u_cs,
+                    size_t n_modes, size_t n_iters, const corrla_rsvd_opts* opts, const double* omega_y,
+                    double* a_til, double* b, double* modes_scale, double* s_til, double* u_hat,
+                    corrla_timings* timings);
+
+/* POD modes and weights, PodI::_modes + PodI::_weights (src/lib_math_utils/pod_rom.rs:53-75) behind the pyo3 PyPodI
+ * (lib_math_utils_py.rs:223-250).  x : n_snap x n_points, one snapshot per row (fat in practice: the RSVD runs on the
+ * transposed view).  modes : n_points x n_modes column-major = V of random_svd(x, n_modes, 10, 10);
+ * weights : n_snap x n_modes column-major = x * modes  (the reference's pinv(modes) * x_row^T per snapshot: the
+ * modes are orthonormal, so the pseudo-inverse is the transpose).  s (optional): n_modes singular values. */
+CORRLA_API int corrla_pod_f64(const double* x, int64_t n_snap, int64_t n_points, int64_t row_stride, int64_t col_stride,
+                   size_t n_modes, const corrla_rsvd_opts* opts, double* modes, double* weights, double* s,
+                   corrla_timings* timings);
+
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
  * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 128.  rank_out (optional) = live columns. */
 CORRLA_API int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,

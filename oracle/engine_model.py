@@ -121,7 +121,7 @@ def hqr_inv(sk: np.ndarray):
 
 
 def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None,
-            refill_a: np.ndarray | None = None):
+            refill_a: np.ndarray | None = None, complete: bool = False):
     """CholeskyQR2 when a Cholesky probe says cond(x) is below ~1e4, else sketch-preconditioned CholeskyQR with refill
     of numerically dependent columns (Core::qr_inplace in engine.cu).
     Returns (x_last, t_fold, second_pass, live): the orthonormal factor is x_last @ t_fold."""
@@ -160,10 +160,20 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
         # the refill stage is the robust (sketch) stage again
         lc = (x.shape[1] + 7) // 8 * 8
         sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), np.random.default_rng(778)))
-        t1, _ = hqr_inv(sk)
+        t1, dead_r = hqr_inv(sk)
         x = x @ t1
         g = distributed_allreduce(x.T @ x)
         tf, _, dead = chol_inv(g, False, global_rows)
+        if refill_a is not None and complete and dead_r.any():
+            # range(A) has fewer than l dimensions: arbitrary vectors in the columns that are still dead, made
+            # orthogonal to the live ones (Householder's completion; the final Q keeps l orthonormal columns)
+            x = x @ tf
+            x[:, dead_r] = rng.standard_normal((x.shape[0], int(dead_r.sum())))
+            sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), np.random.default_rng(779)))
+            t1, _ = hqr_inv(sk)
+            x = x @ t1
+            g = distributed_allreduce(x.T @ x)
+            tf, _, dead = chol_inv(g, False, global_rows)
     return x, tf, second, int(np.sum(~dead))
 
 
@@ -232,7 +242,7 @@ def engine_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: in
             z = allreduce(a.T @ y)
             y = (a @ z) * (1.0 / np.sqrt(nu2))
         nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
-    y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a)
+    y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a, complete=True)
     zb = allreduce(a.T @ y) @ tf                      # B^T, replicated
     qz, tzf, _, _ = qr_fold(zb.copy(), _identity_allreduce, float(n))
     qz = qz @ tzf

@@ -55,6 +55,8 @@ def test_known_answer_lowrank_5x5(cb):
     assert np.max(np.abs(s.ravel() - sigma)) < 1e-3                 # the reference's own tolerance (:182)
     assert np.max(np.abs(s.ravel()[:3] - np.array([3.0, np.sqrt(5.0), 2.0]))) < 1e-12
     assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - a)) < 1e-12
+    # like a Householder QR, the engine completes the basis beyond the numerical rank: U and V stay orthonormal
+    assert np.max(np.abs(u.T @ u - np.eye(5))) < 1e-12 and np.max(np.abs(vt @ vt.T - np.eye(5))) < 1e-12
     u, s, vt = cb.rsvd(a, 3, 12, 10, seed=2)
     assert s.shape == (3, 1)
     assert np.max(np.abs(s.ravel() - sigma[:3])) < 1e-3             # :195

@@ -150,3 +150,60 @@ def test_pca_oracle_matches_direct_svd():
     assert np.allclose(ref_pca.explained_var(p).ravel(), s_ref ** 2 / 799.0)
     s, c = ref_pca.rpca(x, 4, 99, 99, omega=rng.standard_normal((12, 12)))          # extra args ignored (F7)
     assert np.max(np.abs(s.ravel() - s_ref) / s_ref) < 1e-10
+
+
+# ------------------------------------------------------------------ reduced-order models
+@pytest.mark.parametrize("nx", [20, 50, 500])
+def test_dmdc_oracle_passes_the_reference_test(nx):
+    """dmd_rom.rs:236-309 (test_dmdc: fat, skinny and big case): 14 modes, 40 power iterations, the 19th predicted
+    state within 5e-2 of the 20th snapshot, 14 eigenvalues."""
+    from oracle import ref_rom
+    p, u = ref_rom.dmdc_test_snapshots(nx, 40)
+    model = ref_rom.DMDc(p, u, 1.0, 14, 40, rng=np.random.default_rng(nx))
+    assert model.est_a_til().shape == (nx, nx) and model.est_b_til().shape[0] == nx
+    pred = model.predict_multiple(p[:, 0:1], u)
+    assert model.lambdas.shape == (14, 1)
+    assert np.max(np.abs(pred[:, 19] - p[:, 20])) < 5e-2
+    one = model.predict(p[:, 0:1], u[:, 0:1])
+    assert np.allclose(one[:, 0], pred[:, 0])
+
+
+def test_dmdc_oracle_recovers_planted_operators():
+    """x_{t+1} = A x_t + B u_t with a planted rank-6 A: the fitted operator reproduces the snapshots it was built
+    from, and the reduced eigenvalues are those of A."""
+    from oracle import ref_rom
+    rng = np.random.default_rng(3)
+    n_x, n_u, nt, r = 300, 2, 60, 6
+    q, _ = np.linalg.qr(rng.standard_normal((n_x, r)))
+    lam = np.array([0.95, 0.9, 0.8, -0.7, 0.6, 0.5])
+    a = (q * lam) @ q.T
+    bmat = q @ rng.standard_normal((r, n_u))
+    u = rng.standard_normal((n_u, nt))
+    x = np.zeros((n_x, nt))
+    x[:, 0] = q @ rng.standard_normal(r)
+    for t in range(nt - 1):
+        x[:, t + 1] = a @ x[:, t] + bmat @ u[:, t]
+    model = ref_rom.DMDc(x, u, 1.0, r + n_u, 6, rng=rng)      # the input space [x; u] has rank r + n_u
+    ev = np.sort(model.lambdas.real.ravel())
+    assert np.allclose(ev, np.sort(np.concatenate([lam, np.zeros(n_u)])), atol=1e-8)
+    assert np.max(np.abs(model.est_b_til() - bmat)) < 1e-8
+    pred = model.predict_multiple(x[:, 0:1], u[:, :-1])
+    assert np.max(np.abs(pred - x[:, 1:])) < 1e-7
+
+
+def test_pod_oracle_runs_the_reference_generator():
+    """pod_rom.rs:125-155 asserts nothing; the restatement must reproduce the snapshots at the abscissae (4 modes of a
+    travelling bump leave a visible residual, so only the interpolation property of the weights is checked) and
+    mat_linspace's quirk (values i*delta, start not added)."""
+    from oracle import ref_rom
+    x, t = ref_rom.pod_test_snapshots()
+    assert x.shape == (20, 100) and t.shape == (20, 1) and t[0, 0] == 0.0 and np.isclose(t[1, 0], 0.4)
+    pod = ref_rom.PodI(x, t, 4, rng=np.random.default_rng(0))
+    assert pod.modes.shape == (100, 4) and pod.mode_weights.shape == (20, 4)
+    assert np.max(np.abs(pod.modes.T @ pod.modes - np.eye(4))) < 1e-12
+    for j in (3, 11):
+        assert np.allclose(pod.weights_at(t[j:j + 1]).ravel(), pod.mode_weights[j], atol=1e-8)
+    y = pod.predict(np.array([[5.2]]))
+    assert y.shape == (100, 1) and np.all(np.isfinite(y))
+    full = ref_rom.PodI(x, t, 20, rng=np.random.default_rng(1))      # all modes: snapshots reproduced exactly
+    assert np.max(np.abs(full.predict(t[7:8]).ravel() - x[7])) < 1e-8
