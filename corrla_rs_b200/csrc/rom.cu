@@ -37,7 +37,9 @@ int stage_block(corrla_ctx* ctx, cudaStream_t st, const double* src, int64_t row
                 bool on_device, double* D, int64_t ld, int64_t off, double* h2d_ms, int* launches) {
   if (rows == 0) return CORRLA_OK;
   cudaError_t e;
-  if (on_device) {
+  if (on_device && rs == 1 && cs >= rows) {
+    e = cudaMemcpy2DAsync(D + off, ld * 8, src, cs * 8, rows * 8, T, cudaMemcpyDeviceToDevice, st);   // already column-major
+  } else if (on_device) {
     e = repack_launch(src, T, rows, cs, rs, D + off, ld, st);      // D[t*ld + off + i] = src[i*rs + t*cs]
     ++*launches;
   } else if (rs == 1 && cs >= rows) {
