@@ -2,6 +2,7 @@
 // (random_svd.rs:15-110) as a sequence of skinny DMMA GEMMs, CholeskyQR and a Jacobi SVD, all on one
 // CUDA stream, with NCCL all-reduces of the small replicated factors when the rows are sharded.
 #include "engine_core.cuh"
+#include "wide.cuh"
 
 namespace corrla_eng {
 
@@ -39,7 +40,12 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   c.ctx = sc.ctx; c.st = sc.st; c.comm = o.comm;
   c.refill_seed = o.seed ^ 0x9e3779b97f4a7c15ull;
   c.refill_stream = o.comm ? (uint64_t)o.comm->rank : 0;
-  ST_TRY(c.setup_dims(m, n, l));
+  // more than 128 sketch columns: P column panels of padded width w <= 128 (wide.cuh); c then describes ONE panel
+  const bool wide = l > 8 * kMaxNblk;
+  if (wide && l > 2048) { set_last_error("n_rank + n_oversamples = %d exceeds the supported 2048 sketch columns", l); return CORRLA_ERR_UNSUPPORTED; }
+  int wide_P = 1, wide_w = l;
+  if (wide) Wide::plan(l, &wide_P, &wide_w);
+  ST_TRY(c.setup_dims(m, n, wide ? wide_w : l));
 
   const bool want_center = (o.center != 0) && !power_only;
   if (want_center && fat && o.comm != nullptr) { set_last_error("centring of a fat matrix is not supported with a communicator"); return CORRLA_ERR_UNSUPPORTED; }
@@ -49,7 +55,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   // starts without a QR and no other rank is involved) runs chunk by chunk behind the host->device copies.
   const bool host_rowmajor = (tcs == 1 && trs >= n), host_colmajor = !host_rowmajor && (trs == 1 && tcs >= m);
   int64_t stream_rows = 0;
-  if (!o.a_on_device && !want_center && (host_rowmajor || host_colmajor)) {
+  if (!o.a_on_device && !want_center && !wide && (host_rowmajor || host_colmajor)) {
     int64_t rows = ((int64_t)512 << 20) / (n * 8) / 128 * 128;
     if (const char* env = getenv("CORRLA_B200_STREAM_ROWS")) rows = atoll(env) / 128 * 128;   // 0 disables
     if (rows >= 128 && m > rows) stream_rows = rows;
@@ -99,8 +105,10 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     CU_TRY(cudaMemcpyAsync(means_out, c.mu, (size_t)cnt * 8, o.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sc.st));
   }
 
+  Wide wd(c);
+  if (wide) ST_TRY(wd.alloc(l));
   const double* omega_packed = nullptr;
-  if (o.omega != nullptr) {
+  if (o.omega != nullptr && !wide) {
     ST_TRY(pack_small(sc.ctx, sc.st, o.omega, n, l, o.omega_rs, o.omega_cs, o.omega_on_device != 0, c.Za, c.ld, 1.0, &c.launches));
     omega_packed = c.Za;
   }
@@ -130,7 +138,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     c.profile_passes = true;
     CU_TRY(cudaEventRecord(ev0, sc.st));
   }
-  ST_TRY(c.power_iter(omega_packed, o.seed, (int)n_iter, o.schedule, resume));
+  if (wide) ST_TRY(wd.power_iter(o, (int)n_iter));
+  else ST_TRY(c.power_iter(omega_packed, o.seed, (int)n_iter, o.schedule, resume));
 
   const bool out_dev = o.out_on_device != 0;
   double d2h_ms = 0.0;
@@ -138,7 +147,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     // Q = Y * Tf, column-major m x l
     double* qd = out_dev ? q_out : static_cast<double*>(sc.ctx->get("Uout", (size_t)m * l * 8));
     if (!qd) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-    ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.Tf, qd, 1, m, l));
+    if (wide) ST_TRY(wd.scatter_q(qd));
+    else ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.Tf, qd, 1, m, l));
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
     if (!out_dev) {
       CU_TRY(cudaStreamSynchronize(sc.st));
@@ -146,21 +156,23 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       Timer t; CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, q_out, (size_t)m * l * 8, qd, (size_t)m * l * 8, (size_t)m * l * 8, 1)); d2h_ms = t.ms();
     }
   } else {
-    // B^T = Z_B = (A^T Y) Tf                                       random_svd.rs:80
-    ST_TRY(c.mm_AtY(c.Y, c.Zb));
-    ST_TRY(c.mm(c.view_rows(c.Zb, n), true, c.Tf, c.Za, c.ld, 1, c.Lc));
-    // SVD of B (:89): QR-precondition Z_B, Jacobi on the l x l core W = Qz^T Z_B
-    CU_TRY(cudaMemcpyAsync(c.Qz, c.Za, (size_t)c.n16 * c.ld * 8, cudaMemcpyDeviceToDevice, sc.st));
-    ST_TRY(c.qr_inplace(c.Qz, n, false, (double)n, c.Tzf));
-    ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Tzf, c.Qz, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 1));
-    ST_TRY(c.mm(c.view_rows(c.Qz, n), false, c.Za, c.Wm, c.ld, 1, c.Lc));
-    {
-      cudaError_t e = jacobi_svd_launch(c.Wm, c.ld, l, c.sig, c.Vr, c.Ur, c.L16, c.ld, c.jscratch, c.flags + 4, sc.st);
-      ++c.launches;
-      if (e != cudaSuccess) { set_last_error("jacobi launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    if (!wide) {
+      // B^T = Z_B = (A^T Y) Tf                                       random_svd.rs:80
+      ST_TRY(c.mm_AtY(c.Y, c.Zb));
+      ST_TRY(c.mm(c.view_rows(c.Zb, n), true, c.Tf, c.Za, c.ld, 1, c.Lc));
+      // SVD of B (:89): QR-precondition Z_B, Jacobi on the l x l core W = Qz^T Z_B
+      CU_TRY(cudaMemcpyAsync(c.Qz, c.Za, (size_t)c.n16 * c.ld * 8, cudaMemcpyDeviceToDevice, sc.st));
+      ST_TRY(c.qr_inplace(c.Qz, n, false, (double)n, c.Tzf));
+      ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Tzf, c.Qz, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 1));
+      ST_TRY(c.mm(c.view_rows(c.Qz, n), false, c.Za, c.Wm, c.ld, 1, c.Lc));
+      {
+        cudaError_t e = jacobi_svd_launch(c.Wm, c.ld, l, c.sig, c.Vr, c.Ur, c.L16, c.ld, c.jscratch, c.flags + 4, sc.st);
+        ++c.launches;
+        if (e != cudaSuccess) { set_last_error("jacobi launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      }
     }
     // W = Ur S Vr^T  =>  B = Vr S (Qz Ur)^T : U_thin = Q Vr[:, :k] = Y (Tf Vr)   (:92),  V_thin = Qz Ur[:, :k]
-    ST_TRY(c.mm(MatView{c.Tf, (int64_t)c.Lc, (int64_t)c.Lc, (int64_t)c.ld}, true, c.Vr, c.M1, c.ld, 1, c.Lc));
+    if (!wide) ST_TRY(c.mm(MatView{c.Tf, (int64_t)c.Lc, (int64_t)c.Lc, (int64_t)c.ld}, true, c.Vr, c.M1, c.ld, 1, c.Lc));
     const int kk = (int)k;
     // output placement (:96-109): thin-U is m x k, thin-V is n x k
     //   tall input : u <- U (col-major m x k),  vt <- V^T (col-major k x n  == V row-major n x k)
@@ -168,15 +180,20 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     const bool want_u = (u != nullptr);
     double* ud = !want_u ? nullptr : (out_dev ? u : static_cast<double*>(sc.ctx->get("Uout", (size_t)nrows * kk * 8)));
     double* vd = out_dev ? vt : static_cast<double*>(sc.ctx->get("Vout", (size_t)ncols * kk * 8));
-    double* sd = out_dev ? s : c.sig;
+    const double* sig_dev = wide ? wd.sig : c.sig;
+    double* sd = out_dev ? s : const_cast<double*>(sig_dev);
     if ((want_u && !ud) || !vd) { set_last_error("device allocation of outputs failed"); return CORRLA_ERR_ALLOC; }
     double* Uthin_dst = fat ? vd : ud;
     double* Vthin_dst = fat ? ud : vd;
     const int64_t u_rs = fat ? kk : 1, u_cs = fat ? 1 : m;
     const int64_t v_rs = fat ? 1 : kk, v_cs = fat ? n : 1;
-    if (Uthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.M1, Uthin_dst, u_rs, u_cs, kk));
-    if (Vthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Ur, Vthin_dst, v_rs, v_cs, kk));
-    if (out_dev) CU_TRY(cudaMemcpyAsync(s, c.sig, (size_t)kk * 8, cudaMemcpyDeviceToDevice, sc.st));
+    if (wide) {
+      ST_TRY(wd.finish(kk, Uthin_dst, u_rs, u_cs, Vthin_dst, v_rs, v_cs));
+    } else {
+      if (Uthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.M1, Uthin_dst, u_rs, u_cs, kk));
+      if (Vthin_dst != nullptr) ST_TRY(c.mm(c.view_rows(c.Qz, n), true, c.Ur, Vthin_dst, v_rs, v_cs, kk));
+    }
+    if (out_dev) CU_TRY(cudaMemcpyAsync(s, sig_dev, (size_t)kk * 8, cudaMemcpyDeviceToDevice, sc.st));
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
     if (!out_dev) {
       CU_TRY(cudaStreamSynchronize(sc.st));
@@ -200,7 +217,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       if (cudaEventElapsedTime(&pm, sc.ctx->event(2 + 2 * (size_t)i), sc.ctx->event(3 + 2 * (size_t)i)) == cudaSuccess) pass_ms += pm;
       else cudaGetLastError();
     }
-    tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l;
+    tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l / (double)wide_P;
     tm->p2p_exchanges = c.p2p_exchanges;
     tm->streamed_chunks = n_chunks;
     if (o.comm != nullptr && o.comm->p2p) {
@@ -209,8 +226,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       if (herr != 0) { set_last_error("peer-memory exchange timed out: a rank never published its epoch"); return CORRLA_ERR_COMM; }
     }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
-    tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
-    tm->qr_third_passes = c.n_robust; tm->qr_refills = c.n_refill; tm->jacobi_sweeps = hflags[4]; tm->live_columns = hflags[1] ? hflags[1] : l;
+    tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);     // each pass is wide_P launches when the sketch is cut into panels
+    tm->qr_third_passes = c.n_robust; tm->qr_refills = c.n_refill; tm->jacobi_sweeps = hflags[4]; tm->live_columns = wide ? l : (hflags[1] ? hflags[1] : l);
     tm->total_ms = total.ms();
   } else if (out_dev) {
     // nothing to wait for: results are ordered on the caller's stream

@@ -596,3 +596,76 @@ def test_streamed_host_input_drawn_omega_and_power_iter(cb, monkeypatch):
     assert cb.last_timings()["streamed_chunks"] == 6
     assert ref_rsvd.subspace_sine(qb, qs) < 1e-10
     assert np.max(np.abs(qs.T @ qs - np.eye(16))) < 1e-12
+
+
+# ------------------------------------------------------------------ sketches wider than one 128-column GEMM tile
+@pytest.mark.parametrize("shape,kqp,kind", [
+    ((3000, 400), (150, 4, 10), "lowrank"),       # l = 160: 2 panels of 80
+    ((2000, 300), (250, 2, 20), "gauss"),         # l = 270: 3 panels of 96, the last one with 78 live columns
+    ((300, 2500), (140, 3, 10), "lowrank"),       # fat input
+    ((1500, 200), (190, 5, 30), "lowrank"),       # l clamps to n = 200: the sketch spans the whole row space
+    ((5000, 520), (129, 1, 0), "gauss"),          # l = 129: just over the single-panel limit
+])
+def test_wide_sketch_matches_oracle(cb, shape, kqp, kind):
+    """n_rank + n_oversamples > 128 runs in column panels (csrc/wide.cuh): same parity bar as the single-panel path."""
+    m, n = shape
+    k, q, p = kqp
+    rng = np.random.default_rng(m + n + k)
+    if kind == "gauss":
+        a = rng.standard_normal((m, n))
+    else:
+        r = min(m, n)
+        u, _ = np.linalg.qr(rng.standard_normal((m, r)))
+        v, _ = np.linalg.qr(rng.standard_normal((n, r)))
+        a = (u * (10.0 * 0.985 ** np.arange(r))) @ v.T
+    l = min(k + p, min(m, n))
+    omega = rng.standard_normal((min(m, n), l))
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    out = cb.rsvd(a, k, q, p, omega=omega)
+    t = cb.last_timings()
+    assert t["pass_launches"] == (2 + 2 * q) * (-(-(8 * (-(-l // 8))) // 128))
+    assert_parity(out, ref, k)
+    assert np.max(np.abs((out[0] * out[1].ravel()) @ out[2] - (ref[0] * ref[1].ravel()) @ ref[2])) < 1e-9 * ref[1][0, 0]
+
+
+def test_wide_sketch_device_seeded_stabilised_and_power_iter(cb):
+    import torch
+    rng = np.random.default_rng(91)
+    m, n, k, p, q = 6000, 384, 180, 12, 3
+    uu, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    vv, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    a = (uu * (10.0 * 0.99 ** np.arange(n))) @ vv.T                     # slow decay: inside the parity class (SURVEY F9)
+    ad = torch.from_numpy(a).cuda()
+    omega = cb.random_mat_normal(n, k + p, seed=17)                      # the Omega the engine draws for this seed
+    ref = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    out = cb.rsvd(ad, k, q, p, seed=17)
+    torch.cuda.synchronize()
+    assert_parity(tuple(x.cpu().numpy() for x in out), ref, k)
+    stab = cb.rsvd(ad, k, q, p, seed=17, schedule="stabilised")
+    assert ref_rsvd.sigma_rel_err(ref[1], stab[1].cpu().numpy()) < 1e-9
+    qd = cb.power_iter(ad, k + p, q, seed=17).cpu().numpy()
+    assert qd.shape == (m, k + p)
+    assert np.max(np.abs(qd.T @ qd - np.eye(k + p))) < 1e-12
+    qref = ref_rsvd.power_iter(a, k + p, q, omega=omega)
+    assert ref_rsvd.subspace_sine(qref, qd) < 1e-8
+
+
+def test_wide_sketch_rank_deficient_and_pca(cb):
+    """Exactly rank-60 input with a 160-column sketch (whole panels are numerically dependent), and the fused centring
+    through the panel path (rpca with n_rank = 130 => l = 140)."""
+    from oracle import ref_pca
+    rng = np.random.default_rng(92)
+    m, n = 2500, 300
+    a = rng.standard_normal((m, 60)) @ rng.standard_normal((60, n))
+    u, s, vt = cb.rsvd(a, 150, 4, 10, seed=3)
+    s0 = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s.ravel()[:60] - s0[:60])) < 1e-10 * s0[0]
+    assert np.max(np.abs(s.ravel()[60:])) < 1e-9 * s0[0]
+    assert np.max(np.abs((u * s.ravel()) @ vt - a)) < 1e-9 * s0[0]
+    x = lowrank_noise(rng, 3000, 260, 180, 1e-6) + rng.standard_normal((1, 260))
+    sv, comps = cb.rpca(x, 130, seed=4)
+    xc = x - x.mean(axis=0)
+    sc0 = np.linalg.svd(xc, compute_uv=False)
+    assert np.max(np.abs(sv.ravel() - sc0[:130]) / sc0[:130]) < 1e-9
+    _, vt0 = ref_pca.rpca(x, 130, omega=rng.standard_normal((260, 140)))
+    assert ref_rsvd.subspace_sine(vt0.T, comps.T) < 1e-7
