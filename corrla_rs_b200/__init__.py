@@ -323,7 +323,7 @@ def power_iter(a_mat, omega_rank: int, n_iter: int, *, omega=None, seed: int | N
 
 
 def par_matmul(lhs, rhs, beta: float = 1.0, *, ctx: Context | None = None):
-    """res = beta * lhs @ rhs with a skinny rhs (<= 128 columns): par_matmul_helper with alpha=None
+    """res = beta * lhs @ rhs with a skinny rhs (128-column panels above that): par_matmul_helper with alpha=None
     (mat_utils.rs:20-33).  Returns a new array where the inputs live."""
     a = _Mat(lhs, "lhs")
     b = _Mat(rhs, "rhs")
@@ -369,8 +369,9 @@ def random_mat_normal(n_rows: int, n_cols: int, seed: int | None = None, *, devi
 
 def thin_q(a_mat, *, ctx: Context | None = None, comm: ShardComm | None = None, global_rows: int | None = None,
            return_rank: bool = False):
-    """Thin Q of a tall matrix with <= 128 columns by adaptive CholeskyQR2/3: the engine's stand-in for faer's
-    `qr().compute_thin_q()` (random_svd.rs:38, :57).  Rank-deficient columns come back as exact zeros."""
+    """Thin Q of a tall matrix by adaptive CholeskyQR2/3 (column panels above 128 columns): the engine's stand-in for
+    faer's `qr().compute_thin_q()` (random_svd.rs:38, :57).  Numerically dependent columns are replaced by an
+    orthonormal completion, as a Householder QR would."""
     a = _Mat(a_mat)
     lib = _ffi.load()
     device = a.device if a.on_device else (comm.device if comm is not None else None)

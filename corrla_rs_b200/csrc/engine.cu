@@ -283,25 +283,30 @@ int corrla_par_matmul_f64(double* res, int64_t res_rs, int64_t res_cs, const dou
                           int64_t lhs_cols, int64_t lhs_rs, int64_t lhs_cs, const double* rhs, int64_t rhs_cols,
                           int64_t rhs_rs, int64_t rhs_cs, double beta, int on_device, const corrla_rsvd_opts* opts) {
   try {
-    if (!res || !lhs || !rhs || lhs_rows <= 0 || lhs_cols <= 0 || rhs_cols <= 0) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
+    if (!res || !lhs || !rhs || lhs_rows <= 0 || lhs_cols <= 0 || rhs_cols <= 0 || rhs_cols > (1 << 20)) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
     Scope sc;
     ST_TRY(open_scope(opts, &sc));
     Core c; c.ctx = sc.ctx; c.st = sc.st;
-    ST_TRY(c.setup_dims(lhs_rows, lhs_cols, (int)std::min<int64_t>(rhs_cols, 1 << 20)));
+    // more than 128 right-hand columns run as column panels of equal width, one launch each
+    int P = 1, w = (int)rhs_cols;
+    if (rhs_cols > 8 * kMaxNblk) Wide::plan((int)rhs_cols, &P, &w);
+    ST_TRY(c.setup_dims(lhs_rows, lhs_cols, w));
     ST_TRY(stage_matrix(sc.ctx, sc.st, "A", lhs, lhs_rows, lhs_cols, lhs_rs, lhs_cs, on_device != 0, &c.av, &c.a_rowmajor, nullptr, &c.launches));
     ST_TRY(c.alloc_workspace(false));
     double* X = static_cast<double*>(sc.ctx->get("Za", (size_t)c.n16 * c.ld * 8));
-    if (!X) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-    CU_TRY(cudaMemsetAsync(X, 0, (size_t)c.n16 * c.ld * 8, sc.st));
-    ST_TRY(pack_small(sc.ctx, sc.st, rhs, lhs_cols, rhs_cols, rhs_rs, rhs_cs, on_device != 0, X, c.ld, beta, &c.launches));
     const int nc = (int)rhs_cols;
+    double* out = on_device ? nullptr : static_cast<double*>(sc.ctx->get("Uout", (size_t)lhs_rows * nc * 8));
+    if (!X || (!on_device && !out)) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+    for (int p = 0; p < P; ++p) {
+      const int c0 = p * w, wc = std::min(w, nc - c0);
+      CU_TRY(cudaMemsetAsync(X, 0, (size_t)c.n16 * c.ld * 8, sc.st));
+      ST_TRY(pack_small(sc.ctx, sc.st, rhs + (int64_t)c0 * rhs_cs, lhs_cols, wc, rhs_rs, rhs_cs, on_device != 0, X, c.ld, beta, &c.launches));
+      if (on_device) ST_TRY(c.mm(c.av, c.a_rowmajor, X, res + (int64_t)c0 * res_cs, res_rs, res_cs, wc));
+      else ST_TRY(c.mm(c.av, c.a_rowmajor, X, out + c0, nc, 1, wc));
+    }
     if (on_device) {
-      ST_TRY(c.mm(c.av, c.a_rowmajor, X, res, res_rs, res_cs, nc));
       CU_TRY(cudaStreamSynchronize(sc.st));
     } else {
-      double* out = static_cast<double*>(sc.ctx->get("Uout", (size_t)lhs_rows * nc * 8));
-      if (!out) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-      ST_TRY(c.mm(c.av, c.a_rowmajor, X, out, nc, 1, nc));
       std::vector<double> tmp((size_t)lhs_rows * nc);
       CU_TRY(cudaMemcpyAsync(tmp.data(), out, tmp.size() * 8, cudaMemcpyDeviceToHost, sc.st));
       CU_TRY(cudaStreamSynchronize(sc.st));
@@ -336,21 +341,34 @@ int corrla_random_mat_normal_f64(uint64_t seed, int64_t n_rows, int64_t n_cols, 
 int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
                       int on_device, const corrla_rsvd_opts* opts, double* q, int* rank_out) {
   try {
-    if (!a || !q || nrows <= 0 || ncols <= 0) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
+    if (!a || !q || nrows <= 0 || ncols <= 0 || ncols > 2048) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
     Scope sc;
     ST_TRY(open_scope(opts, &sc));
     Core c; c.ctx = sc.ctx; c.st = sc.st; c.comm = opts ? opts->comm : nullptr;
-    ST_TRY(c.setup_dims(nrows, ncols, (int)std::min<int64_t>(ncols, 1 << 20)));
+    const bool wide = ncols > 8 * kMaxNblk;
+    int P = 1, w = (int)ncols;
+    if (wide) Wide::plan((int)ncols, &P, &w);
+    ST_TRY(c.setup_dims(nrows, ncols, w));
     c.grows = (opts && opts->global_rows > 0) ? (double)opts->global_rows : (double)nrows;
-    ST_TRY(c.alloc_workspace(false));
-    ST_TRY(c.alloc_buffers(false));
-    ST_TRY(pack_small(sc.ctx, sc.st, a, nrows, ncols, row_stride, col_stride, on_device != 0, c.Y, c.ld, 1.0, &c.launches));
-    ST_TRY(c.qr_inplace(c.Y, nrows, c.comm != nullptr, c.grows, c.Tf));
+    ST_TRY(c.alloc_workspace(wide));
+    ST_TRY(c.alloc_buffers(wide));
     double* qd = on_device ? q : static_cast<double*>(sc.ctx->get("Uout", (size_t)nrows * ncols * 8));
     if (!qd) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-    ST_TRY(c.mm(c.view_rows(c.Y, nrows), true, c.Tf, qd, 1, nrows, (int)ncols));
     int hinfo[4] = {0, 0, 0, 0};
-    CU_TRY(cudaMemcpyAsync(hinfo, c.flags + 1, 8, cudaMemcpyDeviceToHost, sc.st));
+    if (wide) {
+      Wide wd(c);
+      ST_TRY(wd.alloc((int)ncols));
+      for (int p = 0; p < P; ++p)
+        ST_TRY(pack_small(sc.ctx, sc.st, a + (int64_t)p * w * col_stride, nrows, wd.lp(p), row_stride, col_stride, on_device != 0,
+                          wd.Y[p], c.ld, 1.0, &c.launches));
+      ST_TRY(wd.block_qr(wd.Y, nrows, c.comm != nullptr, c.grows, false, false));
+      ST_TRY(wd.scatter_q(qd));
+    } else {
+      ST_TRY(pack_small(sc.ctx, sc.st, a, nrows, ncols, row_stride, col_stride, on_device != 0, c.Y, c.ld, 1.0, &c.launches));
+      ST_TRY(c.qr_inplace(c.Y, nrows, c.comm != nullptr, c.grows, c.Tf));
+      ST_TRY(c.mm(c.view_rows(c.Y, nrows), true, c.Tf, qd, 1, nrows, (int)ncols));
+      CU_TRY(cudaMemcpyAsync(hinfo, c.flags + 1, 8, cudaMemcpyDeviceToHost, sc.st));
+    }
     if (!on_device) CU_TRY(cudaMemcpyAsync(q, qd, (size_t)nrows * ncols * 8, cudaMemcpyDeviceToHost, sc.st));
     CU_TRY(cudaStreamSynchronize(sc.st));
     if (rank_out) *rank_out = hinfo[0] ? hinfo[0] : (int)ncols;   // 0: the probe passed, plain CholeskyQR2, full rank

@@ -389,6 +389,54 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
     out_ux[(int64_t)i * ldo + r] = sj > 0.0 ? Xc[j * lp + i] / sj : 0.0;
     out_va[(int64_t)i * ldo + r] = Vc[j * lp + i];
   }
+  // Exactly zero singular values leave zero columns in Ux: complete them to an orthonormal basis (unit vectors, two
+  // Gram-Schmidt passes against everything before them), as the full SVD of the reference would (random_svd.rs:89).
+  __syncthreads();
+  if (tid == 0) { int nzc = 0; for (int j = 0; j < l; ++j) nzc += (nrm[j] > 0.0) ? 1 : 0; *anyflag = nzc; }
+  __syncthreads();
+  const int nz = *anyflag;
+  if (nz < l) {
+    double* coef = nrm;                  // sigma is already in sigma_out; coef[r] doubles as the norm slot of column r
+    int cand = 0;
+    for (int r = nz; r < l; ++r) {
+      for (; cand < l; ++cand) {
+        __syncthreads();
+        for (int i = tid; i < l; i += nt) out_ux[(int64_t)i * ldo + r] = (i == cand) ? 1.0 : 0.0;
+        __syncthreads();
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int q = grp; q < r; q += ngrp) {
+            double a = 0.0;
+            for (int i = sub; i < l; i += LP) a += out_ux[(int64_t)i * ldo + q] * out_ux[(int64_t)i * ldo + r];
+#pragma unroll
+            for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
+            if (sub == 0) coef[q] = a;
+          }
+          __syncthreads();
+          for (int i = tid; i < l; i += nt) {
+            double a = out_ux[(int64_t)i * ldo + r];
+            for (int q = 0; q < r; ++q) a -= coef[q] * out_ux[(int64_t)i * ldo + q];
+            out_ux[(int64_t)i * ldo + r] = a;
+          }
+          __syncthreads();
+        }
+        if (tid < 32) {
+          double a = 0.0;
+          for (int i = tid; i < l; i += 32) { const double x = out_ux[(int64_t)i * ldo + r]; a += x * x; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (tid == 0) coef[r] = a;
+        }
+        __syncthreads();
+        const double n2 = coef[r];
+        if (n2 > 0.25) {
+          const double inv = rsqrt(n2);
+          for (int i = tid; i < l; i += nt) out_ux[(int64_t)i * ldo + r] *= inv;
+          ++cand;
+          break;
+        }
+      }
+    }
+  }
   if (tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = converged; }
 }
 

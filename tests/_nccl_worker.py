@@ -22,13 +22,20 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     comm = cb.ShardComm(device=local)
     results = {}
+    os.environ["CORRLA_B200_STREAM_ROWS"] = "0"       # the bitwise host-vs-device checks below need the unstreamed host path
     cases = {"gauss_rowmajor": (20011, 512, 30, 5, 10, "C"), "lowrank_colmajor": (16384, 300, 20, 4, 10, "F"),
              "tiny_rank_deficient": (64, 16, 8, 12, 8, "C"),
              # Z = n16 x ld = 16000 x 36 doubles exceeds the 4 MiB peer-memory half: this case takes the NCCL fallback
-             "wide_nccl_fallback": (18000, 16000, 20, 2, 8, "C")}
+             "wide_nccl_fallback": (18000, 16000, 20, 2, 8, "C"),
+             # l = 160 > 128: the column-panel path (csrc/wide.cuh), cross-panel projections summed over the ranks
+             "panels_l160": (12000, 400, 150, 3, 10, "C")}
     for name, (m, n, k, q, p, order) in cases.items():
         rng = np.random.default_rng(77)
-        if name.startswith("lowrank"):
+        if name.startswith("panels"):
+            u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
+            v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            a = (u0 * (10.0 * 0.99 ** np.arange(n))) @ v0.T
+        elif name.startswith("lowrank"):
             u0, _ = np.linalg.qr(rng.standard_normal((m, 40)))
             v0, _ = np.linalg.qr(rng.standard_normal((n, 40)))
             a = (u0 * (10.0 * 0.95 ** np.arange(40))) @ v0.T + 1e-2 * rng.standard_normal((m, n))
@@ -62,6 +69,24 @@ def main():
                 "orth_u": float(np.max(np.abs(u.T @ u - np.eye(k)))),
                 "device_vs_host_sigma": float(np.max(np.abs(sd.cpu().numpy() - s))),
                 "device_vs_host_u": float(np.max(np.abs(u2 - u))), "k_checked": kk, "p2p_exchanges": p2p_used}
+    # streamed host input on every rank (first product behind the copies): same factors up to summation order
+    rng = np.random.default_rng(78)
+    m, n, k, q, p = 20011, 256, 24, 4, 8
+    a = rng.standard_normal((m, n))
+    omega = rng.standard_normal((n, k + p))
+    per = (m + world - 1) // world
+    r0, r1 = rank * per, min(m, (rank + 1) * per)
+    base = cb.rsvd(a[r0:r1].copy(), k, q, p, omega=omega, comm=comm, global_rows=m, seed=9)
+    os.environ["CORRLA_B200_STREAM_ROWS"] = "1024"
+    strm = cb.rsvd(a[r0:r1].copy(), k, q, p, omega=omega, comm=comm, global_rows=m, seed=9)
+    chunks = cb.last_timings()["streamed_chunks"]
+    os.environ["CORRLA_B200_STREAM_ROWS"] = "0"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (float(np.max(np.abs(base[0] - strm[0]))), chunks))
+    if rank == 0:
+        results["streamed"] = {"u_diff": max(g[0] for g in gathered), "min_chunks": min(g[1] for g in gathered),
+                               "sigma_rel": float(np.max(np.abs(base[1] - strm[1]) / base[1])),
+                               "vt_diff": float(np.max(np.abs(base[2] - strm[2])))}
     # thin_q sharded
     rng = np.random.default_rng(5)
     a = rng.standard_normal((9000, 48))

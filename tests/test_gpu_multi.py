@@ -38,7 +38,7 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     res = json.loads((tmp_path / "result.json").read_text())
-    for name in ("gauss_rowmajor", "lowrank_colmajor", "tiny_rank_deficient", "wide_nccl_fallback"):
+    for name in ("gauss_rowmajor", "lowrank_colmajor", "tiny_rank_deficient", "wide_nccl_fallback", "panels_l160"):
         c = res[name]
         assert c["sigma_rel"] < 1e-10, (name, c)
         assert c["sin_u"] < 1e-8 and c["sin_v"] < 1e-8, (name, c)
@@ -46,4 +46,6 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
         assert c["sigma_tail_abs"] < 1e-9, (name, c)
         assert c["device_vs_host_sigma"] == 0.0 and c["device_vs_host_u"] == 0.0, (name, c)
     assert res["gauss_rowmajor"]["p2p_exchanges"] > 0            # sums fused into the reduction kernel over peer memory
+    st = res["streamed"]
+    assert st["min_chunks"] >= 2 and st["sigma_rel"] < 1e-12 and st["u_diff"] < 1e-10 and st["vt_diff"] < 1e-10, st
     assert res["thin_q"]["orth"] < 1e-13 and res["thin_q"]["span"] < 1e-13

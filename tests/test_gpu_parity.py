@@ -205,9 +205,15 @@ def test_rank_panic_and_limits(cb):
         cb.rsvd(a, 10, 2, 10)
     out = cb.rsvd(a, 6, 5, 10, seed=3)                   # l clamps to 9
     assert out[0].shape == (64, 6) and out[2].shape == (6, 9)
-    with pytest.raises(cb.CorrlaError) as ei:            # round-1 limit
-        cb.rsvd(np.zeros((400, 300)), 120, 1, 10)
+    with pytest.raises(cb.CorrlaError) as ei:            # sketch width limit of the panel path (2048 columns)
+        cb.rsvd(np.zeros((3000, 2500)), 2040, 1, 10)
     assert ei.value.status == -4
+    # all-zero input without power iterations (with them the reference divides 0 by ||Y|| = 0): sigma = 0, U and V are
+    # whatever orthonormal completion the QR returns -- single-panel and panel path
+    for k in (20, 120):
+        u, s, vt = cb.rsvd(np.zeros((400, 300)), k, 0, 10, seed=1)
+        assert np.all(s == 0.0) and np.all(np.isfinite(u)) and np.all(np.isfinite(vt))
+        assert np.max(np.abs(u.T @ u - np.eye(k))) < 1e-12
 
 
 def test_input_is_not_modified_and_deterministic(cb):
@@ -669,3 +675,18 @@ def test_wide_sketch_rank_deficient_and_pca(cb):
     assert np.max(np.abs(sv.ravel() - sc0[:130]) / sc0[:130]) < 1e-9
     _, vt0 = ref_pca.rpca(x, 130, omega=rng.standard_normal((260, 140)))
     assert ref_rsvd.subspace_sine(vt0.T, comps.T) < 1e-7
+
+
+def test_wide_par_matmul_and_thin_q(cb):
+    rng = np.random.default_rng(93)
+    lhs, rhs = rng.standard_normal((1500, 77)), rng.standard_normal((77, 300))
+    out = cb.par_matmul(lhs, rhs, beta=-1.5)
+    assert out.shape == (1500, 300)
+    assert np.max(np.abs(out - (-1.5) * (lhs @ rhs))) < 1e-11
+    x = rng.standard_normal((4000, 200)) * (0.97 ** np.arange(200))
+    q = cb.thin_q(x)
+    assert q.shape == (4000, 200)
+    assert np.max(np.abs(q.T @ q - np.eye(200))) < 1e-12
+    assert ref_rsvd.subspace_sine(np.linalg.qr(x)[0], q) < 1e-9
+    q0, _ = np.linalg.qr(x[:, :90])
+    assert ref_rsvd.subspace_sine(q0, q[:, :90]) < 1e-9          # nested: leading columns span the leading columns
