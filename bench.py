@@ -34,6 +34,7 @@ WORKLOADS = {
     "c3": (4_194_304, 1024, 100, 4, 10),      # BASELINE.json configs[2], the north-star target
     "c2": (20_000, 20_000, 100, 4, 10),       # configs[1]
     "c5": (1_048_576, 64, 8, 8, 10),          # configs[4]
+    "wide": (1_048_576, 1024, 240, 4, 16),    # not a BASELINE config: l = 256 runs as 2 column panels (csrc/wide.cuh)
     "c1": (100, 100, 10, 12, 8),              # configs[0] (README example)
 }
 BLOCK_ROWS = 1 << 19      # A is generated in fixed row blocks so that every GPU count sees the same matrix
@@ -282,6 +283,7 @@ def run_ours(args):
         out = cb.rsvd(a, k, q, p, seed=args.seed + 100, ctx=ctx, comm=comm, global_rows=rows)
         return out, cb.last_timings()
 
+    out = None
     for i in range(args.warmup):
         out, _ = step_device(i)
     del out

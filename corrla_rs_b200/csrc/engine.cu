@@ -416,7 +416,7 @@ const char* corrla_status_str(int status) {
     case CORRLA_ERR_INVALID: return "invalid argument";
     case CORRLA_ERR_RANK: return "n_rank exceeds min(n_rank + n_oversamples, ncols of the thin matrix)";
     case CORRLA_ERR_CUDA: return "CUDA error";
-    case CORRLA_ERR_UNSUPPORTED: return "unsupported size (n_rank + n_oversamples > 128)";
+    case CORRLA_ERR_UNSUPPORTED: return "unsupported size or option combination";
     case CORRLA_ERR_ALLOC: return "allocation failed";
     case CORRLA_ERR_COMM: return "communicator (NCCL) error";
     case CORRLA_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback exists)";

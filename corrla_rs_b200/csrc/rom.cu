@@ -79,13 +79,17 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
   memset(&acc, 0, sizeof(acc));
   if (tm) memset(tm, 0, sizeof(*tm));
   if (x == nullptr || n_x <= 0 || T < 2 || n_u < 0 || (n_u > 0 && u == nullptr)) { set_last_error("bad snapshot / control matrix"); return CORRLA_ERR_INVALID; }
-  if (o.comm != nullptr) { set_last_error("corrla_dmdc_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
   if (o.center != 0) { set_last_error("centring is not part of DMDc"); return CORRLA_ERR_INVALID; }
+  // With a communicator every rank passes its block of state rows of x and the whole u; the control rows are stacked
+  // under the LAST rank's block, so the global input-space matrix is [x; u] exactly as in the reference.
+  corrla_comm* comm = (o.comm != nullptr && o.comm->nranks > 1) ? o.comm : nullptr;
+  const int64_t n_u_all = n_u;
+  if (comm != nullptr && comm->rank != comm->nranks - 1) n_u = 0;
   const int64_t M = n_x + n_u, nn = T - 1;
   const int r = (int)std::min<size_t>(n_modes, 1 << 20);
   if (r <= 0) { set_last_error("n_modes must be positive"); return CORRLA_ERR_INVALID; }
   // the reference indexes r columns out of l = min(r + 12, thin columns) (random_svd.rs:77,98): it panics beyond
-  if ((int64_t)r > std::min<int64_t>(n_x, nn)) {
+  if (comm == nullptr && (int64_t)r > std::min<int64_t>(n_x, nn)) {
     set_last_error("n_modes=%d exceeds min(n_x, n_snapshots - 1)=%lld (the reference panics here)", r, (long long)std::min<int64_t>(n_x, nn));
     return CORRLA_ERR_RANK;
   }
@@ -119,19 +123,22 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
   corrla_rsvd_opts oi = o;
   oi.a_on_device = 1; oi.out_on_device = 1; oi.ctx = ctx; oi.stream = st; oi.device = ctx->device;
   corrla_timings t1, t2;
+  if (comm != nullptr && o.global_rows > 0) oi.global_rows = o.global_rows + n_u_all;     // o.global_rows counts state rows
   ST_TRY(rsvd_impl(Xv, M, nn, 1, ldD, (size_t)r, n_iters, 12, &oi, Util, Stil, Vttil, &t1, false, nullptr));
   oi.omega = omega_y;
   oi.seed = o.seed + 1;
+  oi.global_rows = o.global_rows;
   ST_TRY(rsvd_impl(Yv, n_x, nn, 1, ldD, (size_t)r, n_iters, 12, &oi, Uhat, Shat, Vthat, &t2, false, nullptr));
   add_timings(&acc, t1);
   add_timings(&acc, t2);
 
   // ---- products on the tall side, all with l = r columns
   Core c;
-  c.ctx = ctx; c.st = st;
+  c.ctx = ctx; c.st = st; c.comm = comm;
   ST_TRY(c.setup_dims(std::max(n_x, nn), std::min(n_x, nn), r));
   ST_TRY(c.alloc_workspace(true));
   const int Lc = c.Lc, ld = c.ld, L16 = c.L16;
+  const size_t gx = comm ? (size_t)Lc * ld : 0;            // r x r cross products are summed over the ranks
   const int64_t nx16 = round_up(n_x, 16), nn16 = round_up(nn, 16);
   double* Vs = rb.zeros("rom_vs", (size_t)nn16 * ld);
   double* G2 = rb.zeros("rom_g2", (size_t)nn16 * ld);
@@ -159,9 +166,9 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
   const MatView yv{Yv, n_x, nn, ldD};                       // column-major: inner = state rows
   // P1 = Y * v_til * s_inv  (one pass over Y);  tmp_op_scale = u_hat^T * P1                 (:90-94)
   ST_TRY(c.mm(yv, false, Vs, P1, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
-  ST_TRY(c.mm(c.view_rows(Uh, n_x), false, P1, T0, ld, 1, Lc));
+  ST_TRY(c.mm(c.view_rows(Uh, n_x), false, P1, T0, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
   // C1 = u_til_1^T * u_hat;  a_til = tmp_op_scale * C1                                      (:95-97)
-  ST_TRY(c.mm(c.view_rows(U1, n_x), false, Uh, C1, ld, 1, Lc));
+  ST_TRY(c.mm(c.view_rows(U1, n_x), false, Uh, C1, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
   double* a_dev = (out_dev && a_til) ? a_til : rb.raw("rom_atil", (size_t)r * r + 8);
   if (!a_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
   ST_TRY(c.mm(MatView{T0, (int64_t)Lc, (int64_t)r, (int64_t)ld}, true, C1, a_dev, 1, r, r));
@@ -175,15 +182,18 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
   }
   // _B = u_hat * (tmp_op_scale * u_til_2^T) = (u_hat * tmp_op_scale) * u_til_2^T            (:100-106)
   double* b_dev = nullptr;
-  if (b != nullptr && n_u > 0) {
-    b_dev = out_dev ? b : rb.raw("rom_b", (size_t)n_x * n_u);
+  if (b != nullptr && n_u_all > 0) {
+    b_dev = out_dev ? b : rb.raw("rom_b", (size_t)n_x * n_u_all);
     if (!b_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
     ST_TRY(c.mm(c.view_rows(Uh, n_x), true, T0, H, ld, 1, Lc));
-    for (int64_t j0 = 0; j0 < n_u; j0 += Lc) {
-      const int w = (int)std::min<int64_t>(Lc, n_u - j0);
-      if (j0 > 0) CU_TRY(cudaMemsetAsync(U2t, 0, (size_t)L16 * ld * 8, st));
-      e = repack_launch(Util + n_x + j0, r, w, M, 1, U2t, ld, st); ST_TRY(chk("repack"));   // u_til_2^T panel: r x w
-      ++launches;
+    for (int64_t j0 = 0; j0 < n_u_all; j0 += Lc) {
+      const int w = (int)std::min<int64_t>(Lc, n_u_all - j0);
+      if (j0 > 0 || comm != nullptr) CU_TRY(cudaMemsetAsync(U2t, 0, (size_t)L16 * ld * 8, st));
+      if (n_u > 0) {                                                                          // the rank that holds u_til_2
+        e = repack_launch(Util + n_x + j0, r, w, M, 1, U2t, ld, st); ST_TRY(chk("repack"));   // u_til_2^T panel: r x w
+        ++launches;
+      }
+      if (comm != nullptr) ST_TRY(c.allreduce(U2t, (size_t)L16 * ld));                        // zeros elsewhere: a broadcast
       ST_TRY(c.mm(c.view_rows(H, n_x), true, U2t, b_dev + (size_t)j0 * n_x, 1, n_x, w));
     }
   }
@@ -198,7 +208,7 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
     Timer t;
     if (a_til) CU_TRY(cudaMemcpy(a_til, a_dev, (size_t)r * r * 8, cudaMemcpyDeviceToHost));
     if (s_til) CU_TRY(cudaMemcpy(s_til, Stil, (size_t)r * 8, cudaMemcpyDeviceToHost));
-    ST_TRY(copy_out(ctx, st, b_dev ? b : nullptr, b_dev, (size_t)n_x * n_u));
+    ST_TRY(copy_out(ctx, st, b_dev ? b : nullptr, b_dev, (size_t)n_x * n_u_all));
     ST_TRY(copy_out(ctx, st, modes_scale, ms_dev, (size_t)n_x * r));
     ST_TRY(copy_out(ctx, st, u_hat, Uhat, (size_t)n_x * r));
     acc.d2h_ms = t.ms();
@@ -219,12 +229,14 @@ int pod_impl(const double* x, int64_t n_snap, int64_t n_points, int64_t rs, int6
   corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
   if (tm) memset(tm, 0, sizeof(*tm));
   if (x == nullptr || n_snap <= 0 || n_points <= 0) { set_last_error("empty or null snapshot matrix"); return CORRLA_ERR_INVALID; }
-  if (o.comm != nullptr) { set_last_error("corrla_pod_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
   if (o.center != 0) { set_last_error("centring is not part of PodI"); return CORRLA_ERR_INVALID; }
+  // With a communicator every rank passes its block of POINTS (columns of x): n_points is the local count, the modes
+  // come back for those points, the weights (n_snap x r) are summed over the ranks and replicated.
+  corrla_comm* comm = (o.comm != nullptr && o.comm->nranks > 1) ? o.comm : nullptr;
   const int r = (int)std::min<size_t>(n_modes, 1 << 20);
   const int64_t thin_cols = std::min(n_snap, n_points);
   if (r <= 0) { set_last_error("n_modes must be positive"); return CORRLA_ERR_INVALID; }
-  if ((int64_t)r > thin_cols) {
+  if ((int64_t)r > (comm ? n_snap : thin_cols)) {
     set_last_error("n_modes=%d exceeds min(n_snapshots, n_points)=%lld (the reference panics here)", r, (long long)thin_cols);
     return CORRLA_ERR_RANK;
   }
@@ -247,24 +259,46 @@ int pod_impl(const double* x, int64_t n_snap, int64_t n_points, int64_t rs, int6
   corrla_rsvd_opts oi = o;
   oi.a_on_device = 1; oi.out_on_device = 1; oi.ctx = ctx; oi.stream = st; oi.device = ctx->device;
   corrla_timings t1;
-  ST_TRY(rsvd_impl(xv.p, n_snap, n_points, drs, dcs, (size_t)r, 10, 10, &oi, nullptr, Sd, Vt, &t1, false, nullptr, true));   // pod_rom.rs:56
+  double* m_col = nullptr;     // communicator path: the thin matrix is x_local^T, its left vectors ARE the local modes
+  if (comm == nullptr) {
+    ST_TRY(rsvd_impl(xv.p, n_snap, n_points, drs, dcs, (size_t)r, 10, 10, &oi, nullptr, Sd, Vt, &t1, false, nullptr, true));   // pod_rom.rs:56
+  } else {
+    m_col = (out_dev && modes) ? modes : rb.raw("rom_modes", (size_t)n_points * r);
+    double* vt_small = rb.raw("rom_vthat", (size_t)r * n_snap);
+    if (!m_col || !vt_small) { set_last_error("device allocation failed (POD factors)"); return CORRLA_ERR_ALLOC; }
+    ST_TRY(rsvd_impl(xv.p, n_points, n_snap, dcs, drs, (size_t)r, 10, 10, &oi, m_col, Sd, vt_small, &t1, false, nullptr));
+  }
 
   Core c;
-  c.ctx = ctx; c.st = st;
+  c.ctx = ctx; c.st = st; c.comm = comm;
   ST_TRY(c.setup_dims(std::max(n_snap, n_points), thin_cols, r));
   ST_TRY(c.alloc_workspace(true));
   const int64_t np16 = round_up(n_points, 16);
   double* Mp = rb.zeros("rom_uh", (size_t)np16 * c.ld);
-  double* m_dev = (out_dev && modes) ? modes : rb.raw("rom_modes", (size_t)n_points * r);
+  double* m_dev = m_col ? m_col : ((out_dev && modes) ? modes : rb.raw("rom_modes", (size_t)n_points * r));
   double* w_dev = (out_dev && weights) ? weights : rb.raw("rom_b", (size_t)n_snap * r);
   if (!Mp || !m_dev || !w_dev) { set_last_error("device allocation failed (POD products)"); return CORRLA_ERR_ALLOC; }
-  // modes(i, j) = Vt[j + i*r]  (v.transpose().to_owned(), :57)
-  cudaError_t e = repack_launch(Vt, n_points, r, r, 1, Mp, c.ld, st);
-  if (e == cudaSuccess && modes != nullptr) e = scatter_launch(Mp, n_points, r, c.ld, m_dev, 1, n_points, st);
+  cudaError_t e;
+  if (comm == nullptr) {
+    // modes(i, j) = Vt[j + i*r]  (v.transpose().to_owned(), :57)
+    e = repack_launch(Vt, n_points, r, r, 1, Mp, c.ld, st);
+    if (e == cudaSuccess && modes != nullptr) e = scatter_launch(Mp, n_points, r, c.ld, m_dev, 1, n_points, st);
+  } else {
+    e = repack_launch(m_col, n_points, r, 1, n_points, Mp, c.ld, st);
+  }
   launches += 2;
   if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-  // weights = x * modes: one more pass over the snapshots (:61-75)
-  if (weights != nullptr) ST_TRY(c.mm(xv, rm, Mp, w_dev, 1, n_snap, r, nullptr, nullptr, nullptr, 0, true));
+  // weights = x * modes: one more pass over the snapshots (:61-75); summed over the point blocks of the ranks
+  if (weights != nullptr && comm == nullptr) ST_TRY(c.mm(xv, rm, Mp, w_dev, 1, n_snap, r, nullptr, nullptr, nullptr, 0, true));
+  if (weights != nullptr && comm != nullptr) {
+    const int64_t ns16 = round_up(n_snap, 16);
+    double* Wt = rb.zeros("rom_p1", (size_t)ns16 * c.ld);
+    if (!Wt) { set_last_error("device allocation failed (POD weights)"); return CORRLA_ERR_ALLOC; }
+    ST_TRY(c.mm(xv, rm, Mp, Wt, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 0, true, nullptr, (size_t)ns16 * c.ld));
+    e = scatter_launch(Wt, n_snap, r, c.ld, w_dev, 1, n_snap, st);
+    ++launches;
+    if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  }
   launches += c.launches;
 
   double d2h_ms = 0.0;

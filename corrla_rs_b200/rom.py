@@ -28,9 +28,12 @@ def _api():
 # --------------------------------------------------------------------------------------------
 # thin wrappers over the two C entry points
 # --------------------------------------------------------------------------------------------
-def dmdc_operators(x_data, u_data, n_modes: int, n_iters: int, *, omegas=(None, None), seed=None, ctx=None):
+def dmdc_operators(x_data, u_data, n_modes: int, n_iters: int, *, omegas=(None, None), seed=None, ctx=None, comm=None,
+                   global_rows=None):
     """corrla_dmdc_f64: returns dict(a_til (r, r), b (n_x, n_u), modes_scale (n_x, r), s_til (r, 1), u_hat (n_x, r)).
-    x_data: n_x x n_snapshots, u_data: n_u x n_snapshots; numpy (host) or torch CUDA tensors (device)."""
+    x_data: n_x x n_snapshots, u_data: n_u x n_snapshots; numpy (host) or torch CUDA tensors (device).
+    With `comm` (one process per GPU) x_data is this rank's block of state rows and u_data the whole control matrix;
+    a_til and s_til come back replicated, b / modes_scale / u_hat for the local rows; `global_rows` = total state rows."""
     api = _api()
     lib = _ffi.load()
     x = api._Mat(x_data, "x_data")
@@ -42,11 +45,11 @@ def dmdc_operators(x_data, u_data, n_modes: int, n_iters: int, *, omegas=(None, 
     n_x, n_snap = x.shape
     n_u = u.shape[0]
     r = int(n_modes)
-    device = x.device if x.on_device else None
+    device = x.device if x.on_device else (comm.device if comm is not None else None)
     ctx = ctx or api._context_for(device)
     stream = api._current_stream(device) if x.on_device else None
     o, keep = api._make_opts(ctx=ctx, on_device=x.on_device, out_on_device=x.on_device, omega=omegas[0], seed=seed,
-                             schedule="reference", comm=None, global_rows=None, stream=stream, device=device)
+                             schedule="reference", comm=comm, global_rows=global_rows, stream=stream, device=device)
     oy = None
     if omegas[1] is not None:
         oy = api._Mat(omegas[1], "omega_y")
@@ -70,18 +73,20 @@ def dmdc_operators(x_data, u_data, n_modes: int, n_iters: int, *, omegas=(None, 
     return {"a_til": a_til, "b": b[:, :n_u], "modes_scale": modes_scale, "s_til": s_til, "u_hat": u_hat}
 
 
-def pod_modes_weights(x_data, n_modes: int, *, omega=None, seed=None, ctx=None):
-    """corrla_pod_f64: (modes (n_points, r), weights (n_snapshots, r), s (r, 1)); x_data is n_snapshots x n_points."""
+def pod_modes_weights(x_data, n_modes: int, *, omega=None, seed=None, ctx=None, comm=None, global_rows=None):
+    """corrla_pod_f64: (modes (n_points, r), weights (n_snapshots, r), s (r, 1)); x_data is n_snapshots x n_points.
+    With `comm` x_data is this rank's block of POINTS (columns); modes come back for those points, weights and s
+    replicated; `global_rows` = total number of points."""
     api = _api()
     lib = _ffi.load()
     x = api._Mat(x_data, "x_data")
     n_snap, n_points = x.shape
     r = int(n_modes)
-    device = x.device if x.on_device else None
+    device = x.device if x.on_device else (comm.device if comm is not None else None)
     ctx = ctx or api._context_for(device)
     stream = api._current_stream(device) if x.on_device else None
     o, keep = api._make_opts(ctx=ctx, on_device=x.on_device, out_on_device=x.on_device, omega=omega, seed=seed,
-                             schedule="reference", comm=None, global_rows=None, stream=stream, device=device)
+                             schedule="reference", comm=comm, global_rows=global_rows, stream=stream, device=device)
     modes = api._colmajor_empty_like(x, n_points, max(r, 1))
     weights = api._colmajor_empty_like(x, n_snap, max(r, 1))
     s = api._colmajor_empty_like(x, max(r, 1), 1)

@@ -39,7 +39,7 @@ typedef enum corrla_status {
   CORRLA_ERR_RANK = -2,         /* n_rank > min(n_rank + n_oversamples, ncols(thin a)): the reference panics here
                                    (out-of-range get at random_svd.rs:98-107) */
   CORRLA_ERR_CUDA = -3,         /* a CUDA call failed; see corrla_last_error() */
-  CORRLA_ERR_UNSUPPORTED = -4,  /* n_rank + n_oversamples > 128 (round-1 limit of the register-tiled kernels) */
+  CORRLA_ERR_UNSUPPORTED = -4,  /* n_rank + n_oversamples > 2048, or an option combination that is not provided */
   CORRLA_ERR_ALLOC = -5,        /* device or host allocation failed */
   CORRLA_ERR_COMM = -6,         /* NCCL failure or libnccl not loadable */
   CORRLA_ERR_NO_DEVICE = -7     /* no CUDA device / driver */
@@ -105,7 +105,7 @@ CORRLA_API int corrla_power_iter_f64(const double* a, int64_t nrows, int64_t nco
                           size_t omega_rank, size_t n_iter, const corrla_rsvd_opts* opts, double* q,
                           corrla_timings* timings);
 
-/* res = beta * lhs * rhs (alpha = None: the destination is overwritten), rhs_cols <= 128.
+/* res = beta * lhs * rhs (alpha = None: the destination is overwritten); rhs is skinny (column panels of <= 128).
  * lhs is m x kk, rhs is kk x rhs_cols, res is m x rhs_cols; all strided, all on the host or all on the device
  * (on_device).  opts may be NULL (defaults) -- only device/stream/ctx are read. */
 CORRLA_API int corrla_par_matmul_f64(double* res, int64_t res_rs, int64_t res_cs,
@@ -139,7 +139,8 @@ CORRLA_API int corrla_rpca_f64(const double* a, int64_t nrows, int64_t ncols, in
  *   modes_scale n_x x r    = tmp_modes_scale (:133-139, eq. 36): modes_re/im = modes_scale * Re/Im(W), W = eigenvectors
  *                            of a_til.  The r x r eigendecomposition (:116) stays with the caller.
  *   s_til       r          singular values of the input space;  u_hat  n_x x r  basis of the output space
- * opts->comm is not supported here (CORRLA_ERR_UNSUPPORTED). */
+ * With opts->comm every rank passes its block of state rows of x (n_x = local rows, opts->global_rows = all of them)
+ * and the whole u; a_til and s_til are replicated, b / modes_scale / u_hat hold the local rows. */
 CORRLA_API int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int64_t x_rs, int64_t x_cs,
                     const double* u, int64_t n_u, int64_t u_rs, int64_t u_cs,
                     size_t n_modes, size_t n_iters, const corrla_rsvd_opts* opts, const double* omega_y,
@@ -150,13 +151,16 @@ CORRLA_API int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int
  * (lib_math_utils_py.rs:223-250).  x : n_snap x n_points, one snapshot per row (fat in practice: the RSVD runs on the
  * transposed view).  modes : n_points x n_modes column-major = V of random_svd(x, n_modes, 10, 10);
  * weights : n_snap x n_modes column-major = x * modes  (the reference's pinv(modes) * x_row^T per snapshot: the
- * modes are orthonormal, so the pseudo-inverse is the transpose).  s (optional): n_modes singular values. */
+ * modes are orthonormal, so the pseudo-inverse is the transpose).  s (optional): n_modes singular values.
+ * With opts->comm every rank passes its block of points (columns of x; n_points = local count, opts->global_rows = all
+ * of them): modes holds the local points, weights and s are replicated. */
 CORRLA_API int corrla_pod_f64(const double* x, int64_t n_snap, int64_t n_points, int64_t row_stride, int64_t col_stride,
                    size_t n_modes, const corrla_rsvd_opts* opts, double* modes, double* weights, double* s,
                    corrla_timings* timings);
 
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
- * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 128.  rank_out (optional) = live columns. */
+ * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 2048 (column panels above 128).  rank_out (optional) =
+ * live columns found before the orthonormal completion. */
 CORRLA_API int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
                       int on_device, const corrla_rsvd_opts* opts, double* q, int* rank_out);
 

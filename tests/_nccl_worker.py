@@ -87,6 +87,54 @@ def main():
         results["streamed"] = {"u_diff": max(g[0] for g in gathered), "min_chunks": min(g[1] for g in gathered),
                                "sigma_rel": float(np.max(np.abs(base[1] - strm[1]) / base[1])),
                                "vt_diff": float(np.max(np.abs(base[2] - strm[2])))}
+    # DMDc with the state rows sharded, POD with the points sharded: against the single-process oracle
+    from oracle import ref_rom
+    rng = np.random.default_rng(79)
+    n_x, n_u, nt, r_true = 6001, 2, 70, 5
+    qq, _ = np.linalg.qr(rng.standard_normal((n_x, r_true)))
+    lam = np.array([0.95, 0.9, -0.8, 0.7, 0.5])
+    amat, bmat = (qq * lam) @ qq.T, qq @ rng.standard_normal((r_true, n_u))
+    uu = rng.standard_normal((n_u, nt))
+    xx = np.zeros((n_x, nt)); xx[:, 0] = qq @ rng.standard_normal(r_true)
+    for t in range(nt - 1):
+        xx[:, t + 1] = amat @ xx[:, t] + bmat @ uu[:, t]
+    r = r_true + n_u
+    omegas = (rng.standard_normal((nt - 1, r + 12)), rng.standard_normal((nt - 1, r + 12)))
+    per = (n_x + world - 1) // world
+    r0, r1 = rank * per, min(n_x, (rank + 1) * per)
+    ops = cb.dmdc_operators(xx[r0:r1].copy(), uu, r, 5, omegas=omegas, comm=comm, global_rows=n_x)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (r0, r1, np.asarray(ops["b"]), np.asarray(ops["u_hat"]), np.asarray(ops["a_til"])))
+    if rank == 0:
+        ref = ref_rom.DMDc(xx, uu, 1.0, r, 5, omegas=omegas)
+        bfull, uh = np.zeros((n_x, n_u)), np.zeros((n_x, r))
+        for g0, g1, bb, hh, _ in gathered:
+            bfull[g0:g1] = bb; uh[g0:g1] = hh
+        a0 = gathered[0][4]
+        results["dmdc"] = {"b_err": float(np.max(np.abs(bfull - bmat))), "b_vs_oracle": float(np.max(np.abs(bfull - ref.b))),
+                           "eig_err": float(np.max(np.abs(np.sort(np.linalg.eigvals(a0).real) - np.sort(np.concatenate([lam, np.zeros(n_u)]))))),
+                           "op_err": float(np.max(np.abs(uh @ a0 @ uh.T - ref.u_hat @ ref.a_til @ ref.u_hat.T))),
+                           "a_til_replicated": float(max(np.max(np.abs(g[4] - a0)) for g in gathered)),
+                           "sigma_rel": float(np.max(np.abs(np.asarray(ops["s_til"]) - ref.s_til) / ref.s_til))}
+    n_snap, n_points, r = 40, 9000, 6
+    base = rng.standard_normal((n_snap, 8)) * (5.0 * 0.6 ** np.arange(8))
+    xp = base @ np.linalg.qr(rng.standard_normal((n_points, 8)))[0].T + 1e-6 * rng.standard_normal((n_snap, n_points))
+    omega = rng.standard_normal((n_snap, r + 10))
+    per = (n_points + world - 1) // world
+    c0, c1 = rank * per, min(n_points, (rank + 1) * per)
+    modes, weights, sv = cb.pod_modes_weights(np.ascontiguousarray(xp[:, c0:c1]), r, omega=omega, comm=comm, global_rows=n_points)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (c0, c1, np.asarray(modes), np.asarray(weights)))
+    if rank == 0:
+        ref = ref_rom.PodI(xp, np.arange(n_snap, dtype=np.float64).reshape(-1, 1), r, omega=omega)
+        mfull = np.zeros((n_points, r))
+        for g0, g1, mm_, _ in gathered:
+            mfull[g0:g1] = mm_
+        w0 = gathered[0][3]
+        results["pod"] = {"sin_modes": ref_rsvd.subspace_sine(ref.modes, mfull), "orth": float(np.max(np.abs(mfull.T @ mfull - np.eye(r)))),
+                          "weights_err": float(np.max(np.abs(w0 - xp @ mfull))),
+                          "recon_err": float(np.max(np.abs(w0 @ mfull.T - ref.mode_weights @ ref.modes.T))),
+                          "weights_replicated": float(max(np.max(np.abs(g[3] - w0)) for g in gathered))}
     # thin_q sharded
     rng = np.random.default_rng(5)
     a = rng.standard_normal((9000, 48))

@@ -46,6 +46,12 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
         assert c["sigma_tail_abs"] < 1e-9, (name, c)
         assert c["device_vs_host_sigma"] == 0.0 and c["device_vs_host_u"] == 0.0, (name, c)
     assert res["gauss_rowmajor"]["p2p_exchanges"] > 0            # sums fused into the reduction kernel over peer memory
+    d = res["dmdc"]
+    assert d["b_err"] < 1e-8 and d["b_vs_oracle"] < 1e-8 and d["eig_err"] < 1e-8 and d["op_err"] < 1e-8, d
+    assert d["a_til_replicated"] == 0.0 and d["sigma_rel"] < 1e-10, d
+    pd_ = res["pod"]
+    assert pd_["sin_modes"] < 1e-8 and pd_["orth"] < 1e-12 and pd_["weights_err"] < 1e-10 and pd_["recon_err"] < 1e-8, pd_
+    assert pd_["weights_replicated"] == 0.0, pd_
     st = res["streamed"]
     assert st["min_chunks"] >= 2 and st["sigma_rel"] < 1e-12 and st["u_diff"] < 1e-10 and st["vt_diff"] < 1e-10, st
     assert res["thin_q"]["orth"] < 1e-13 and res["thin_q"]["span"] < 1e-13
