@@ -72,6 +72,13 @@ extern "C" {
                                  opts: *const corrla_rsvd_opts) -> c_int;
     pub fn corrla_random_mat_normal_f64(seed: u64, n_rows: i64, n_cols: i64, out: *mut f64, out_on_device: c_int,
                                         opts: *const corrla_rsvd_opts) -> c_int;
+    pub fn corrla_dmdc_f64(x: *const f64, n_x: i64, n_snap: i64, x_rs: i64, x_cs: i64, u: *const f64, n_u: i64,
+                           u_rs: i64, u_cs: i64, n_modes: usize, n_iters: usize, opts: *const corrla_rsvd_opts,
+                           omega_y: *const f64, a_til: *mut f64, b: *mut f64, modes_scale: *mut f64, s_til: *mut f64,
+                           u_hat: *mut f64, timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_pod_f64(x: *const f64, n_snap: i64, n_points: i64, row_stride: i64, col_stride: i64, n_modes: usize,
+                          opts: *const corrla_rsvd_opts, modes: *mut f64, weights: *mut f64, s: *mut f64,
+                          timings: *mut corrla_timings) -> c_int;
     pub fn corrla_thin_q_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                              on_device: c_int, opts: *const corrla_rsvd_opts, q: *mut f64, rank_out: *mut c_int) -> c_int;
     pub fn corrla_host_alloc(bytes: usize) -> *mut c_void;

@@ -69,6 +69,48 @@ pub fn par_matmul_helper(mut res: MatMut<f64>, lhs: MatRef<f64>, rhs: MatRef<f64
     check(st);
 }
 
+/// The device-side part of `DMDc::_calc_dmdc_modes` / `_calc_modes` (dmd_rom.rs:64-109, :128-139): returns
+/// (`_A` r x r, `_B` n_x x n_u, `tmp_modes_scale` n_x x r, `s_til` r x 1, `u_hat` n_x x r).  `_calc_eigs` stays with the
+/// caller: `modes_re = tmp_modes_scale * w_re`, `modes_im = tmp_modes_scale * w_im` (two `par_matmul_helper` calls).
+pub fn dmdc_operators(x_data: MatRef<f64>, u_data: MatRef<f64>, n_modes: usize, n_iters: usize)
+    -> (Mat<f64>, Mat<f64>, Mat<f64>, Mat<f64>, Mat<f64>)
+{
+    assert_eq!(x_data.ncols(), u_data.ncols());
+    let (n_x, n_snap, n_u) = (x_data.nrows(), x_data.ncols(), u_data.nrows());
+    let mut a_til = Mat::<f64>::zeros(n_modes, n_modes);
+    let mut b = Mat::<f64>::zeros(n_x, n_u);
+    let mut modes_scale = Mat::<f64>::zeros(n_x, n_modes);
+    let mut s_til = Mat::<f64>::zeros(n_modes, 1);
+    let mut u_hat = Mat::<f64>::zeros(n_x, n_modes);
+    let mut opts = default_opts();
+    opts.seed = rand_seed();
+    let st = unsafe {
+        sys::corrla_dmdc_f64(x_data.as_ptr(), n_x as i64, n_snap as i64, x_data.row_stride() as i64,
+                             x_data.col_stride() as i64, u_data.as_ptr(), n_u as i64, u_data.row_stride() as i64,
+                             u_data.col_stride() as i64, n_modes, n_iters, &opts, std::ptr::null(),
+                             a_til.as_mut().as_ptr_mut(), b.as_mut().as_ptr_mut(), modes_scale.as_mut().as_ptr_mut(),
+                             s_til.as_mut().as_ptr_mut(), u_hat.as_mut().as_ptr_mut(), std::ptr::null_mut())
+    };
+    check(st);
+    (a_til, b, modes_scale, s_til, u_hat)
+}
+
+/// `PodI::_modes` + `PodI::_weights` (pod_rom.rs:53-75): (modes n_points x n_modes, mode_weights n_snap x n_modes).
+pub fn pod_modes_weights(x_data: MatRef<f64>, n_modes: usize) -> (Mat<f64>, Mat<f64>) {
+    let (n_snap, n_points) = (x_data.nrows(), x_data.ncols());
+    let mut modes = Mat::<f64>::zeros(n_points, n_modes);
+    let mut weights = Mat::<f64>::zeros(n_snap, n_modes);
+    let mut opts = default_opts();
+    opts.seed = rand_seed();
+    let st = unsafe {
+        sys::corrla_pod_f64(x_data.as_ptr(), n_snap as i64, n_points as i64, x_data.row_stride() as i64,
+                            x_data.col_stride() as i64, n_modes, &opts, modes.as_mut().as_ptr_mut(),
+                            weights.as_mut().as_ptr_mut(), std::ptr::null_mut(), std::ptr::null_mut())
+    };
+    check(st);
+    (modes, weights)
+}
+
 fn rand_seed() -> u64 {
     // the reference draws Omega from thread_rng() (mat_utils.rs:166-173): unseeded, different every call
     use std::time::{SystemTime, UNIX_EPOCH};
