@@ -23,7 +23,8 @@ from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 
 __all__ = ["rsvd", "random_svd", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
            "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings",
-           "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights"]
+           "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights",
+           "cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd"]
 
 _SCHEDULES = {"reference": 0, "stabilised": 1, "stabilized": 1, 0: 0, 1: 1}
 _tls = threading.local()
@@ -189,8 +190,12 @@ def _make_opts(*, ctx, on_device, out_on_device, omega, seed, schedule, comm, gl
 
 
 def _current_stream(device):
+    """Handle of torch's current stream on `device`.  The legacy default stream has handle 0, which the C ABI reads as
+    "no stream given" (it would then use the context's own non-blocking stream, unordered with the producer of the
+    tensor): it is passed as cudaStreamLegacy (0x1) instead."""
     import torch
-    return torch.cuda.current_stream(device).cuda_stream
+    h = torch.cuda.current_stream(device).cuda_stream
+    return h if h != 0 else 1
 
 
 def _colmajor_empty_like(a: _Mat, rows: int, cols: int):
@@ -388,3 +393,4 @@ def thin_q(a_mat, *, ctx: Context | None = None, comm: ShardComm | None = None, 
 
 
 from .rom import DMDc, PodI, RbfInterp, dmdc_operators, pod_modes_weights  # noqa: E402,F401
+from .stats import ActiveSsRsvd, FittedActiveSsRsvd, cov, mat_cov_centered, pearson_corr  # noqa: E402,F401

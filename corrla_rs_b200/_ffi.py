@@ -74,6 +74,8 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
     "corrla_pod_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
                                  C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
+    "corrla_cov_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                 C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "corrla_thin_q_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                     C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(C.c_int)]),
     "corrla_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -20,6 +20,34 @@ scale_cols_pinv_kernel(double* __restrict__ X, int64_t rows, int r, int64_t ld, 
   X[i * ld + j] *= inv;
 }
 
+// X[i][j] -= mu[j]
+__global__ void __launch_bounds__(256)
+sub_col_means_kernel(double* __restrict__ X, int64_t rows, int cols, int64_t ld, const double* __restrict__ mu) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t i = idx / cols;
+  const int j = (int)(idx - i * cols);
+  X[i * ld + j] -= mu[j];
+}
+
+// G holds the upper triangle of a symmetric product (pitch ld): S (pitch ld, both triangles) and out (column-major d x d)
+// = scale * G, or the correlation matrix G_ij / sqrt(G_ii G_jj) when normalise is set
+__global__ void __launch_bounds__(256)
+finish_cov_kernel(const double* __restrict__ G, int d, int64_t ld, double scale, int normalise, double* __restrict__ S,
+                  double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d * d) return;
+  const int i = idx / d, j = idx - i * d;
+  const double g = (i <= j) ? G[(int64_t)i * ld + j] : G[(int64_t)j * ld + i];
+  double v = g * scale;
+  if (normalise) {
+    const double den = sqrt(G[(int64_t)i * ld + i]) * sqrt(G[(int64_t)j * ld + j]);
+    v = den > 0.0 ? g / den : 0.0;
+  }
+  S[(int64_t)i * ld + j] = v;
+  if (out != nullptr) out[(int64_t)j * d + i] = v;
+}
+
 struct RomBufs {
   corrla_ctx* ctx;
   cudaStream_t st;
@@ -323,9 +351,117 @@ int pod_impl(const double* x, int64_t n_snap, int64_t n_points, int64_t rs, int6
   return CORRLA_OK;
 }
 
+int cov_impl(const double* x, int64_t nrows, int64_t ncols, int64_t rs, int64_t cs, int kind, double scale,
+             const corrla_rsvd_opts* opts_in, double* out, double* means, double* evals, double* evecs) {
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  if (x == nullptr || out == nullptr || nrows <= 0 || ncols <= 0 || kind < 0 || kind > 2 || ((evals == nullptr) != (evecs == nullptr))) {
+    set_last_error("bad argument");
+    return CORRLA_ERR_INVALID;
+  }
+  const int d = (int)std::min<int64_t>(ncols, 1 << 20);
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  RomBufs rb{ctx, st};
+  Core c;
+  c.ctx = ctx; c.st = st; c.comm = (o.comm != nullptr && o.comm->nranks > 1) ? o.comm : nullptr;
+  ST_TRY(c.setup_dims(nrows, ncols, d));                       // d > 128: CORRLA_ERR_UNSUPPORTED
+  ST_TRY(c.alloc_workspace(false));
+  const int Lc = c.Lc, ld = c.ld, L16 = c.L16;
+  const bool out_dev = o.out_on_device != 0;
+  int launches = 0;
+
+  // samples in the engine's padded row-major layout
+  MatView xv; bool rm = true;
+  ST_TRY(stage_matrix(ctx, st, "A", x, nrows, ncols, rs, cs, o.a_on_device != 0, &xv, &rm, nullptr, &launches));
+  double* Xp = rb.zeros("cov_xp", (size_t)c.m16 * ld);
+  double* G = rb.zeros("cov_g", (size_t)L16 * ld);
+  double* S = rb.zeros("cov_s", (size_t)L16 * ld);
+  double* mu = rb.zeros("cov_mu", (size_t)Lc + 8);
+  double* part = rb.raw("cov_part", (size_t)sum_blocks(nrows) * Lc + 128);
+  double* out_dev_buf = out_dev ? out : rb.raw("cov_out", (size_t)d * d);
+  if (!Xp || !G || !S || !mu || !part || !out_dev_buf) { set_last_error("device allocation failed (covariance)"); return CORRLA_ERR_ALLOC; }
+  cudaError_t e = rm ? repack_launch(xv.p, nrows, d, xv.ld, 1, Xp, ld, st) : repack_launch(xv.p, nrows, d, 1, xv.ld, Xp, ld, st);
+  if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+
+  double n_total = (double)nrows;
+  if (c.comm != nullptr) {
+    if (o.global_rows > 0) n_total = (double)o.global_rows;
+    else {
+      CU_TRY(cudaMemcpyAsync(mu + Lc, &n_total, 8, cudaMemcpyHostToDevice, st));
+      ST_TRY(c.allreduce(mu + Lc, 1));
+      CU_TRY(cudaMemcpyAsync(&n_total, mu + Lc, 8, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  if (kind != CORRLA_COV_GRAM) {
+    // column means (mat_mean axis 1), then the explicit centred copy the reference also takes (center_mat_col)
+    e = sum_over_outer_launch(Xp, Lc, nrows, ld, part, mu, st);
+    if (e != cudaSuccess) { set_last_error("mean launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    ST_TRY(c.allreduce(mu, (size_t)Lc));
+    e = scale_vec_launch(mu, Lc, 1.0 / n_total, st);
+    if (e == cudaSuccess) {
+      sub_col_means_kernel<<<(unsigned)((nrows * d + 255) / 256), 256, 0, st>>>(Xp, nrows, d, ld, mu);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { set_last_error("centring launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    if (n_total < 2.0) { set_last_error("covariance needs at least two samples"); return CORRLA_ERR_INVALID; }
+    scale = 1.0 / (n_total - 1.0);
+  }
+  // upper triangle of X^T X (symmetric-output mode of the GEMM), summed over the ranks
+  ST_TRY(c.mm(c.view_rows(Xp, nrows), false, Xp, G, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr,
+              c.comm ? (size_t)Lc * ld : 0, 0, false, 1));
+  finish_cov_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(G, d, ld, scale, kind == CORRLA_COV_PEARSON ? 1 : 0, S, out_dev_buf);
+  CU_TRY(cudaGetLastError());
+
+  double *sig = nullptr, *Ur = nullptr;
+  if (evals != nullptr) {
+    // symmetric positive semi-definite: the SVD is the eigendecomposition, already sorted in descending order
+    sig = rb.zeros("cov_sig", (size_t)L16);
+    Ur = rb.zeros("cov_ur", (size_t)L16 * ld);
+    double* Vr = rb.zeros("cov_vr", (size_t)L16 * ld);
+    double* js = rb.zeros("cov_js", 2 * (size_t)d * (d + 2) + 8);
+    int* info = reinterpret_cast<int*>(rb.zeros("cov_info", 8));
+    if (!sig || !Ur || !Vr || !js || !info) { set_last_error("device allocation failed (eigendecomposition)"); return CORRLA_ERR_ALLOC; }
+    e = jacobi_svd_launch(S, ld, d, sig, Vr, Ur, L16, ld, js, info, st);
+    if (e != cudaSuccess) { set_last_error("jacobi launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  }
+  if (out_dev) {
+    if (means && kind != CORRLA_COV_GRAM) CU_TRY(cudaMemcpyAsync(means, mu, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
+    if (evals) {
+      CU_TRY(cudaMemcpyAsync(evals, sig, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
+      e = scatter_launch(Ur, d, d, ld, evecs, 1, d, st);
+      if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    }
+    CU_TRY(cudaStreamSynchronize(st));      // small results: return them complete (the context stream is not the caller's)
+  } else {
+    if (evals) {
+      double* ev_cm = rb.raw("cov_evcm", (size_t)d * d);
+      if (!ev_cm) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+      e = scatter_launch(Ur, d, d, ld, ev_cm, 1, d, st);
+      if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      CU_TRY(cudaMemcpyAsync(evecs, ev_cm, (size_t)d * d * 8, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(evals, sig, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(out, out_dev_buf, (size_t)d * d * 8, cudaMemcpyDeviceToHost, st));
+    if (means && kind != CORRLA_COV_GRAM) CU_TRY(cudaMemcpyAsync(means, mu, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  return CORRLA_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int corrla_cov_f64(const double* x, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride, int kind,
+                   double scale, const corrla_rsvd_opts* opts, double* out, double* means, double* evals, double* evecs) {
+  try {
+    return cov_impl(x, nrows, ncols, row_stride, col_stride, kind, scale, opts, out, means, evals, evecs);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
 
 int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int64_t x_rs, int64_t x_cs, const double* u, int64_t n_u,
                     int64_t u_rs, int64_t u_cs, size_t n_modes, size_t n_iters, const corrla_rsvd_opts* opts,

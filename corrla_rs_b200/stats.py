@@ -1,0 +1,124 @@
+"""Second-moment statistics and the active-subspace fit on the Gram kernel: host-side mirrors of `mat_cov_centered`,
+`pearson_corr` (src/lib_math_utils/stats_corr.rs:14-43) and of `ActiveSsRsvd::fit` / `fit_svd` / `FittedActiveSsRsvd`
+(src/lib_math_utils/active_subspaces.rs:147-278) over `corrla_cov_f64` and `corrla_rsvd_f64`.
+
+The gradient matrix itself (kd-tree neighbours + local polynomial fits, active_subspaces.rs:66-141) is irregular scalar
+work outside the scope of the engine: `ActiveSsRsvd` takes either a precomputed gradient matrix or any estimator object
+with the reference's `grad_at(x0)` interface."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+__all__ = ["cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd"]
+
+_KINDS = {"gram": 0, "centered": 1, "pearson": 2}
+
+
+def _api():
+    import corrla_rs_b200 as api
+    return api
+
+
+def cov(x, kind: str = "centered", *, scale: float = 1.0, evd: bool = False, ctx=None, comm=None, global_rows=None):
+    """corrla_cov_f64 on a samples-by-features matrix (numpy or torch CUDA tensor, <= 128 features).
+    Returns `out` (d, d), or (out, means (1, d), evals (d, 1), evecs (d, d)) with evd=True."""
+    api = _api()
+    lib = _ffi.load()
+    a = api._Mat(x, "x")
+    n, d = a.shape
+    device = a.device if a.on_device else (comm.device if comm is not None else None)
+    ctx = ctx or api._context_for(device)
+    stream = api._current_stream(device) if a.on_device else None
+    o, _ = api._make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=None, seed=0,
+                          schedule="reference", comm=comm, global_rows=global_rows, stream=stream, device=device)
+    out = api._colmajor_empty_like(a, d, d)
+    means = api._colmajor_empty_like(a, 1, d)
+    evals = api._colmajor_empty_like(a, d, 1) if evd else None
+    evecs = api._colmajor_empty_like(a, d, d) if evd else None
+    st = lib.corrla_cov_f64(a.ptr, n, d, a.strides[0], a.strides[1], _KINDS[kind], float(scale), C.byref(o),
+                            api._ptr(out), api._ptr(means), api._ptr(evals) if evd else None,
+                            api._ptr(evecs) if evd else None)
+    _ffi.check(st)
+    if a.on_device:
+        import torch
+        torch.cuda.current_stream(device).synchronize()
+    return (out, means, evals, evecs) if evd else out
+
+
+def mat_cov_centered(x, **kw):
+    """(x - mean)^T (x - mean) / (N - 1)  (stats_corr.rs:32-43)."""
+    return cov(x, "centered", **kw)
+
+
+def pearson_corr(x, **kw):
+    """Linear correlation coefficients between the columns of x (stats_corr.rs:14-28)."""
+    return cov(x, "pearson", **kw)
+
+
+class FittedActiveSsRsvd:
+    """active_subspaces.rs:147-212: `components_` (k, k) one direction per column, `singular_vals_` (k, k) diagonal."""
+
+    def __init__(self, components, singular_vals, n_comps: int):
+        self.components_ = np.asarray(components)
+        self.singular_vals_ = np.asarray(singular_vals)
+        self.n_comps = int(n_comps)
+
+    def var_diag_evd_sensi(self):
+        m = self.components_.T @ self.singular_vals_ @ self.components_          # :163-170
+        return [float(m[i, i]) for i in range(self.singular_vals_.shape[0])]
+
+    def components(self):
+        return self.components_[:, :self.n_comps]
+
+    def singular_vals(self):
+        return self.singular_vals_[:, :self.n_comps]
+
+    def transform(self, x_mat):
+        return np.asarray(x_mat) @ self.components()                             # :175-181
+
+    def inv_transform(self, x_mat):
+        x_mat = np.asarray(x_mat)
+        assert x_mat.shape[1] == self.n_comps                                    # :187
+        return x_mat @ self.components().T
+
+
+class ActiveSsRsvd:
+    """active_subspaces.rs:215-278.  `grad_est` is an object with `grad_at(x0) -> (1, k)` like the reference's `GradEst`
+    trait; the `*_gradients` methods take the k x N gradient matrix directly (torch CUDA tensors stay on the device)."""
+
+    def __init__(self, grad_est=None, n_comps: int = 1):
+        self.grad_est, self.n_comps = grad_est, int(n_comps)
+
+    def create_grad_mat(self, x_mat):
+        x_mat = np.asarray(x_mat, dtype=np.float64)                              # :226-238 (host loop over the estimator)
+        g = np.zeros((x_mat.shape[1], x_mat.shape[0]))
+        for i in range(x_mat.shape[0]):
+            g[:, i] = np.asarray(self.grad_est.grad_at(list(x_mat[i]))).reshape(-1)
+        return g
+
+    def fit(self, x_mat):
+        return self.fit_gradients(self.create_grad_mat(x_mat))
+
+    def fit_svd(self, x_mat, n_iter=None, n_oversamples=None):
+        return self.fit_svd_gradients(self.create_grad_mat(x_mat), n_iter, n_oversamples)
+
+    def fit_gradients(self, grad_mat, **kw):
+        """Sorted eigendecomposition of grad_mat grad_mat^T / N (:248-278): Gram and Jacobi on the device."""
+        k, n = grad_mat.shape
+        gt = grad_mat.t() if hasattr(grad_mat, "detach") else np.asarray(grad_mat).T    # N x k view, no copy
+        _out, _mu, evals, evecs = cov(gt, "gram", scale=1.0 / n, evd=True, **kw)
+        evals, evecs = (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v) for v in (evals, evecs))
+        return FittedActiveSsRsvd(evecs, np.diag(evals.ravel()), self.n_comps)
+
+    def fit_svd_gradients(self, grad_mat, n_iter=None, n_oversamples=None, **kw):
+        """RSVD of grad_mat / sqrt(N) (:231-246); the 1/sqrt(N) is applied to the k singular values, not to a copy."""
+        api = _api()
+        k, n = grad_mat.shape
+        ur, sr, _vr = api.rsvd(grad_mat, min(k, self.n_comps), 8 if n_iter is None else n_iter,
+                               10 if n_oversamples is None else n_oversamples, **kw)
+        ur, sr = (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v) for v in (ur, sr))
+        return FittedActiveSsRsvd(ur, np.diag(sr.ravel() / np.sqrt(n)), self.n_comps)

@@ -61,7 +61,8 @@ typedef struct corrla_rsvd_opts {
   int a_on_device;         /* 0: `a` is a host pointer (copied in, counted in timings.h2d_ms); 1: device pointer */
   int out_on_device;       /* 0: outputs are host pointers; 1: device pointers */
   int device;              /* CUDA ordinal, or -1 for the current device */
-  void* stream;            /* cudaStream_t to enqueue on, or NULL for the context's own stream */
+  void* stream;            /* cudaStream_t to enqueue on, or NULL for the context's own (non-blocking) stream; the
+                              legacy default stream must be named as cudaStreamLegacy, not as NULL */
   corrla_ctx* ctx;         /* reuse buffers across calls; NULL => a temporary context per call */
   corrla_comm* comm;       /* NULL => single GPU.  Else `a` is this rank's block of rows of the thin matrix */
   int64_t global_rows;     /* with comm: total rows over all ranks (0 => computed with an all-reduce) */
@@ -157,6 +158,23 @@ CORRLA_API int corrla_dmdc_f64(const double* x, int64_t n_x, int64_t n_snap, int
 CORRLA_API int corrla_pod_f64(const double* x, int64_t n_snap, int64_t n_points, int64_t row_stride, int64_t col_stride,
                    size_t n_modes, const corrla_rsvd_opts* opts, double* modes, double* weights, double* s,
                    corrla_timings* timings);
+
+/* Second-moment matrices of a tall sample matrix on the Gram kernel (the part that is a GEMM):
+ *   kind 0  out = scale * x^T x                       ActiveSsRsvd::fit's grad_mat * grad_mat^T / N
+ *                                                     (src/lib_math_utils/active_subspaces.rs:253; pass grad_mat^T as x)
+ *   kind 1  out = (x - mean)^T (x - mean) / (N - 1)   mat_cov_centered (src/lib_math_utils/stats_corr.rs:32-43)
+ *   kind 2  the same on z-scored columns              pearson_corr (stats_corr.rs:14-28; std with N - 1, mat_utils.rs:122-160)
+ * x : nrows x ncols samples-by-features (element strides; host, or device with opts->a_on_device), ncols <= 128.
+ * out : ncols x ncols (symmetric).  means (optional) : ncols column means (kinds 1, 2).
+ * evals / evecs (optional, both or neither): eigenvalues in descending order and eigenvectors (ncols x ncols,
+ * column-major, one per column) of `out` by one-sided Jacobi -- the sorted decomposition ActiveSsRsvd::fit takes from
+ * faer (active_subspaces.rs:259-271).  With opts->comm the rows are sharded and every output is replicated. */
+#define CORRLA_COV_GRAM 0
+#define CORRLA_COV_CENTERED 1
+#define CORRLA_COV_PEARSON 2
+CORRLA_API int corrla_cov_f64(const double* x, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                   int kind, double scale, const corrla_rsvd_opts* opts, double* out, double* means,
+                   double* evals, double* evecs);
 
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
  * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 2048 (column panels above 128).  rank_out (optional) =

@@ -79,6 +79,9 @@ extern "C" {
     pub fn corrla_pod_f64(x: *const f64, n_snap: i64, n_points: i64, row_stride: i64, col_stride: i64, n_modes: usize,
                           opts: *const corrla_rsvd_opts, modes: *mut f64, weights: *mut f64, s: *mut f64,
                           timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_cov_f64(x: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64, kind: c_int,
+                          scale: f64, opts: *const corrla_rsvd_opts, out: *mut f64, means: *mut f64, evals: *mut f64,
+                          evecs: *mut f64) -> c_int;
     pub fn corrla_thin_q_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                              on_device: c_int, opts: *const corrla_rsvd_opts, q: *mut f64, rank_out: *mut c_int) -> c_int;
     pub fn corrla_host_alloc(bytes: usize) -> *mut c_void;

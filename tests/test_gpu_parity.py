@@ -690,3 +690,20 @@ def test_wide_par_matmul_and_thin_q(cb):
     assert ref_rsvd.subspace_sine(np.linalg.qr(x)[0], q) < 1e-9
     q0, _ = np.linalg.qr(x[:, :90])
     assert ref_rsvd.subspace_sine(q0, q[:, :90]) < 1e-9          # nested: leading columns span the leading columns
+
+
+def test_device_input_is_ordered_after_its_producer(cb):
+    """A tensor that is still being written by kernels queued on torch's current (legacy default) stream: the engine
+    must enqueue behind them (cudaStreamLegacy), not on its own unordered stream."""
+    import torch
+    torch.manual_seed(5)
+    base = torch.randn(300_000, 128, dtype=torch.float64, device="cuda")
+    u0, s0, v0 = cb.rsvd(base * 3.0 + 1.0, 10, 2, 6, seed=2)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        a = base.clone()
+        for _ in range(20):                       # a queue of cheap in-place kernels that nets out to 3*base + 1
+            a.mul_(2.0).mul_(0.5)
+        a.mul_(3.0).add_(1.0)
+        u, s, vt = cb.rsvd(a, 10, 2, 6, seed=2)   # no synchronize in between
+        assert torch.equal(s, s0) and torch.equal(u, u0)

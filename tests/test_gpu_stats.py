@@ -1,0 +1,83 @@
+"""GPU parity (-m gpu) of the Gram-kernel statistics and the active-subspace fit (corrla_cov_f64)
+against oracle/ref_stats.py."""
+import numpy as np
+import pytest
+
+from oracle import ref_rsvd, ref_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import corrla_rs_b200
+    corrla_rs_b200._ffi.load()
+    return corrla_rs_b200
+
+
+@pytest.mark.parametrize("shape,order", [((10000, 5), "C"), ((4097, 64), "F"), ((50, 128), "C"), ((3, 2), "C")])
+def test_cov_and_pearson_match_oracle(cb, shape, order):
+    rng = np.random.default_rng(shape[0])
+    mix = rng.standard_normal((shape[1], shape[1]))
+    x = rng.standard_normal(shape) @ mix + 50.0 * rng.standard_normal((1, shape[1]))       # large means: centring matters
+    x = np.asfortranarray(x) if order == "F" else x
+    c0, p0 = ref_stats.mat_cov_centered(x), ref_stats.pearson_corr(x)
+    c1, p1 = cb.mat_cov_centered(x), cb.pearson_corr(x)
+    assert c1.shape == c0.shape and np.max(np.abs(c1 - c0)) < 1e-11 * np.max(np.abs(c0))
+    assert np.max(np.abs(p1 - p0)) < 1e-11 and np.max(np.abs(np.diag(p1) - 1.0)) < 1e-14
+    assert np.array_equal(c1, c1.T) and np.array_equal(p1, p1.T)
+    out, mu, evals, evecs = cb.cov(x, "centered", evd=True)
+    assert np.max(np.abs(mu.ravel() - x.mean(axis=0))) < 1e-12 * np.max(np.abs(x))
+    w = np.linalg.eigvalsh(c0)[::-1]
+    assert np.max(np.abs(evals.ravel() - w)) < 1e-11 * w[0]
+    assert np.max(np.abs(evecs.T @ evecs - np.eye(shape[1]))) < 1e-12
+    assert np.max(np.abs((evecs * evals.ravel()) @ evecs.T - c0)) < 1e-10 * w[0]
+
+
+def test_reference_statistical_tests_and_device_input(cb):
+    import torch
+    x = cb.random_mat_normal(10000, 5, seed=3)                       # stats_corr.rs:259-298 with the engine's own generator
+    assert np.max(np.abs(cb.pearson_corr(x) - np.eye(5))) < 1e-1
+    assert np.max(np.abs(cb.mat_cov_centered(x) - np.eye(5))) < 1e-1
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    cd = cb.mat_cov_centered(xd)
+    assert cd.is_cuda and np.max(np.abs(cd.cpu().numpy() - ref_stats.mat_cov_centered(x))) < 1e-12
+    with pytest.raises(cb.CorrlaError):
+        cb.pearson_corr(np.zeros((10, 200)))                         # more than 128 features
+
+
+def test_active_subspace_fit_from_gradients(cb):
+    """active_subspaces.rs:326-384 with the gradients from the oracle's estimator; `fit` (EVD of G G^T / N on the
+    Gram + Jacobi kernels) and `fit_svd` (RSVD) against the oracle on the same gradient matrix."""
+    rng = np.random.default_rng(1)
+    cov3 = np.full((3, 3), 0.5) + 0.4 * np.eye(3)
+    x3 = (cov3 @ rng.standard_normal((3, 100))).T
+    y3 = 0.2 * x3[:, 0] + 0.5 * x3[:, 1] ** 2 + 0.10 * x3[:, 2] * x3[:, 0]
+    est = ref_stats.PolyGradientEstimator(x3, y3, 2, 14)
+    act = cb.ActiveSsRsvd(est, 2)
+    fit = act.fit(x3)                                                # host loop over the estimator, device Gram + EVD
+    assert abs(fit.components()[0, 0]) < abs(fit.components()[1, 0])
+    assert fit.singular_vals()[0, 0] > fit.singular_vals()[1, 1]
+    sens = fit.var_diag_evd_sensi()
+    assert len(sens) == 3 and sens[1] > sens[0] and sens[1] > sens[2]
+    tr = fit.transform(x3)
+    assert tr.shape == (100, 2) and fit.inv_transform(tr).shape == (100, 3)
+    g = act.create_grad_mat(x3)
+    ref = ref_stats.ActiveSsRsvd(est, 2).fit_gradients(g)
+    assert np.max(np.abs(np.diag(fit.singular_vals_) - np.diag(ref.singular_vals_))) < 1e-12 * ref.singular_vals_[0, 0]
+    assert ref_rsvd.subspace_sine(ref.components(), fit.components()) < 1e-10
+    # a larger gradient matrix (k = 64 features, 20 000 samples, dominant 8-dimensional active subspace)
+    k, n = 64, 20000
+    basis, _ = np.linalg.qr(rng.standard_normal((k, 8)))
+    g = basis @ (rng.standard_normal((8, n)) * (3.0 * 0.7 ** np.arange(8))[:, None]) + 1e-3 * rng.standard_normal((k, n))
+    ref = ref_stats.ActiveSsRsvd(None, 8).fit_gradients(g)
+    fit = cb.ActiveSsRsvd(None, 8).fit_gradients(g)
+    assert np.max(np.abs(np.diag(fit.singular_vals_) - np.diag(ref.singular_vals_))) < 1e-11 * ref.singular_vals_[0, 0]
+    assert ref_rsvd.subspace_sine(ref.components(), fit.components()) < 1e-9
+    omega = rng.standard_normal((k, 18))
+    refs = ref_stats.ActiveSsRsvd(None, 8).fit_svd_gradients(g, omega=omega)
+    fits = cb.ActiveSsRsvd(None, 8).fit_svd_gradients(g, omega=omega)
+    assert ref_rsvd.sigma_rel_err(np.diag(refs.singular_vals_)[:, None], np.diag(fits.singular_vals_)[:, None]) < 1e-10
+    assert ref_rsvd.subspace_sine(refs.components(), fits.components()) < 1e-8
+    # the two routes agree: sigma(G / sqrt(N))^2 are the eigenvalues of G G^T / N
+    assert np.allclose(np.diag(fits.singular_vals_)[:8] ** 2, np.diag(fit.singular_vals_)[:8], rtol=1e-8)

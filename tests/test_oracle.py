@@ -207,3 +207,31 @@ def test_pod_oracle_runs_the_reference_generator():
     assert y.shape == (100, 1) and np.all(np.isfinite(y))
     full = ref_rom.PodI(x, t, 20, rng=np.random.default_rng(1))      # all modes: snapshots reproduced exactly
     assert np.max(np.abs(full.predict(t[7:8]).ravel() - x[7])) < 1e-8
+
+
+# ------------------------------------------------------------------ statistics / active subspaces
+def test_stats_oracle_passes_the_reference_tests():
+    """stats_corr.rs:259-298 (identity within 1e-1 on 10 000 x 5 Gaussian samples) and active_subspaces.rs:281-384
+    (gradient estimates and the ordering of the active directions for f = 0.2 x1 + 0.5 x2^2 + 0.1 x3 x1)."""
+    from oracle import ref_stats
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((10000, 5))
+    assert np.max(np.abs(ref_stats.pearson_corr(x) - np.eye(5))) < 1e-1
+    assert np.max(np.abs(ref_stats.mat_cov_centered(x) - np.eye(5))) < 1e-1
+    assert np.allclose(ref_stats.mat_cov_centered(x), np.cov(x.T)) and np.allclose(ref_stats.pearson_corr(x), np.corrcoef(x.T))
+    cov2 = np.array([[0.9, 0.5], [0.5, 0.9]])
+    x2 = (cov2 @ rng.standard_normal((2, 100))).T                    # sample_mv_normal: cov * z
+    y2 = x2[:, 0] ** 2 + x2[:, 1] ** 2
+    ge = ref_stats.PolyGradientEstimator(x2, y2, 2, 14)
+    assert np.max(np.abs(ge.grad_at([0.0, 0.0]))) < 1e-2
+    assert np.max(np.abs(ge.grad_at([1.0, 0.0]) - np.array([[2.0, 0.0]]))) < 1e-2
+    cov3 = np.full((3, 3), 0.5) + 0.4 * np.eye(3)
+    x3 = (cov3 @ rng.standard_normal((3, 100))).T
+    y3 = 0.2 * x3[:, 0] + 0.5 * x3[:, 1] ** 2 + 0.10 * x3[:, 2] * x3[:, 0]
+    act = ref_stats.ActiveSsRsvd(ref_stats.PolyGradientEstimator(x3, y3, 2, 14), 2)
+    fit = act.fit(x3)
+    assert abs(fit.components()[0, 0]) < abs(fit.components()[1, 0])
+    assert fit.singular_vals()[0, 0] > fit.singular_vals()[1, 1]
+    sens = fit.var_diag_evd_sensi()
+    assert len(sens) == 3 and sens[1] > sens[0] and sens[1] > sens[2]
+    assert np.max(np.abs(act.grad_est.grad_at([0.0, 1.0, 0.0]) - np.array([[0.2, 1.0, 0.0]]))) < 1e-1
