@@ -707,3 +707,31 @@ def test_device_input_is_ordered_after_its_producer(cb):
         a.mul_(3.0).add_(1.0)
         u, s, vt = cb.rsvd(a, 10, 2, 6, seed=2)   # no synchronize in between
         assert torch.equal(s, s0) and torch.equal(u, u0)
+
+
+def test_concurrent_callers(cb):
+    """The boundary is synchronous and re-entrant: threads sharing the default context are serialised
+    by its lock, threads with their own context run concurrently; every result equals the sequential one bit for bit."""
+    import threading
+    rng = np.random.default_rng(94)
+    mats = [rng.standard_normal((3000 + 500 * i, 96 + 8 * i)) for i in range(4)]
+    seq = [cb.rsvd(a, 12, 3, 6, seed=40 + i) for i, a in enumerate(mats)]
+    for own_ctx in (False, True):
+        res, errs = [None] * 4, []
+
+        def work(i):
+            try:
+                ctx = cb.Context(0) if own_ctx else None
+                for _ in range(3):
+                    res[i] = cb.rsvd(mats[i], 12, 3, 6, seed=40 + i, ctx=ctx)
+                if ctx is not None:
+                    ctx.close()
+            except Exception as exc:          # noqa: BLE001
+                errs.append(exc)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for (u0, s0, v0), (u, s, v) in zip(seq, res):
+            assert np.array_equal(s0, s) and np.array_equal(u0, u) and np.array_equal(v0, v)
