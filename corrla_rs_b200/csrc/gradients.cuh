@@ -1,0 +1,31 @@
+// Gradient-matrix build for active subspaces: the reference walks a kd-tree and takes one
+// pseudo-inverse per sample, serially (active_subspaces.rs:66-141, :226-238).  Here: one exact brute-force
+// k-nearest-neighbour kernel over all samples, and one batched local least-squares kernel (a CTA per sample).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace corrla {
+
+constexpr int kKnnMaxK = 128;        // neighbours per sample the selection lists hold
+constexpr int kGradMaxCoef = 136;    // fitted coefficients per sample (without the intercept)
+
+// idx[i*k + r] = index of the r-th nearest row of X to row i (squared Euclidean distance accumulated as sum (a-b)^2 in
+// the order of the features, like kdtree::distance::squared_euclidean; ties go to the lower index; the sample itself is
+// its own nearest neighbour).  X: n x d row-major with pitch ldx.  k <= min(n, kKnnMaxK).
+cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, cudaStream_t s);
+
+// Local polynomial fit through the k neighbours of every sample and its gradient at the sample:
+//   order 1: y ~ b.x + b0                      gradient = b                     (jac_from_lin, stats_corr.rs:164-169)
+//   order 2: y ~ b.x + sum_{a<=b} c_ab x_a x_b + b0, gradient taken analytically at x_i (jac_from_quad differentiates
+//            the same polynomial by a forward difference with eps = 1e-10, stats_corr.rs:230-249)
+// Least squares by Householder QR of the column-centred design matrix (same slopes as the fit with an intercept).
+// G: n x ldg row-major, row i = gradient at sample i (d entries).  info[0] counts samples whose design matrix was
+// numerically rank deficient (their dependent coefficients are set to zero).
+size_t poly_grad_smem_bytes(int d, int k, int order);
+int poly_grad_num_coef(int d, int order);
+cudaError_t poly_grad_launch(const double* X, const double* y, int64_t n, int d, int64_t ldx, const int* idx, int k,
+                             int order, double* G, int64_t ldg, int* info, cudaStream_t s);
+
+}  // namespace corrla

@@ -3,6 +3,7 @@
 // runs through the same skinny DMMA GEMM as the RSVD passes; the r x r eigendecomposition (DMDc) and the
 // n_snap x n_snap RBF interpolation (POD) stay with the caller, as they are negligible and not data-parallel.
 #include "engine_core.cuh"
+#include "gradients.cuh"
 
 using namespace corrla_eng;
 
@@ -451,9 +452,101 @@ int cov_impl(const double* x, int64_t nrows, int64_t ncols, int64_t rs, int64_t 
   return CORRLA_OK;
 }
 
+int active_ss_impl(const double* x, int64_t n, int64_t nfeat, int64_t x_rs, int64_t x_cs, const double* y, int64_t y_stride,
+                   int order, int n_nbr, const corrla_rsvd_opts* opts_in, double* evals, double* evecs, double* grad_mat,
+                   int* n_deficient) {
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  if (x == nullptr || y == nullptr || evals == nullptr || evecs == nullptr || n <= 0 || nfeat <= 0) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
+  if (o.comm != nullptr) { set_last_error("corrla_active_ss_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  if (order != 1 && order != 2) { set_last_error("Not implemented est order: %d (the reference panics here)", order); return CORRLA_ERR_INVALID; }
+  const int d = (int)std::min<int64_t>(nfeat, 1 << 20);
+  // the reference's asserts (active_subspaces.rs:115-116, :127-128)
+  const int64_t need = (order == 1) ? (int64_t)d + 1 : (int64_t)d * (d + 3) / 2;
+  if (!(n > need) || !(n_nbr > need)) {
+    set_last_error("order %d fit in %d dimensions needs more than %lld samples and neighbours (got %lld, %d)", order, d,
+                   (long long)need, (long long)n, n_nbr);
+    return CORRLA_ERR_INVALID;
+  }
+  const int k = (int)std::min<int64_t>(n_nbr, n);                 // KdTree::nearest returns at most all points
+  if (k > kKnnMaxK || poly_grad_num_coef(d, order) > kGradMaxCoef || poly_grad_smem_bytes(d, k, order) > 200 * 1024) {
+    set_last_error("active subspace fit of order %d with %d features and %d neighbours exceeds the kernel limits "
+                   "(<= %d neighbours, <= %d coefficients)", order, d, k, kKnnMaxK, kGradMaxCoef);
+    return CORRLA_ERR_UNSUPPORTED;
+  }
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  RomBufs rb{ctx, st};
+  Core c;
+  c.ctx = ctx; c.st = st;
+  ST_TRY(c.setup_dims(n, nfeat, d));
+  ST_TRY(c.alloc_workspace(false));
+  const int Lc = c.Lc, ld = c.ld, L16 = c.L16;
+  const bool in_dev = o.a_on_device != 0, out_dev = o.out_on_device != 0;
+  int launches = 0;
+
+  MatView xv; bool rm = true;
+  ST_TRY(stage_matrix(ctx, st, "A", x, n, nfeat, x_rs, x_cs, in_dev, &xv, &rm, nullptr, &launches));
+  double* Xp = rb.zeros("cov_xp", (size_t)c.m16 * ld);
+  double* Gp = rb.zeros("as_grad", (size_t)c.m16 * ld);
+  double* yd = rb.raw("as_y", (size_t)n + 8);
+  int* idx = reinterpret_cast<int*>(ctx->get("as_idx", (size_t)n * k * sizeof(int)));
+  double* Gm = rb.zeros("cov_g", (size_t)L16 * ld);
+  double* S = rb.zeros("cov_s", (size_t)L16 * ld);
+  double* sig = rb.zeros("cov_sig", (size_t)L16);
+  double* Ur = rb.zeros("cov_ur", (size_t)L16 * ld);
+  double* Vr = rb.zeros("cov_vr", (size_t)L16 * ld);
+  double* js = rb.zeros("cov_js", 2 * (size_t)d * (d + 2) + 8);
+  int* info = reinterpret_cast<int*>(rb.zeros("cov_info", 8));
+  if (!Xp || !Gp || !yd || !idx || !Gm || !S || !sig || !Ur || !Vr || !js || !info) { set_last_error("device allocation failed (active subspace)"); return CORRLA_ERR_ALLOC; }
+  cudaError_t e = rm ? repack_launch(xv.p, n, d, xv.ld, 1, Xp, ld, st) : repack_launch(xv.p, n, d, 1, xv.ld, Xp, ld, st);
+  if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  ST_TRY(pack_small(ctx, st, y, n, 1, y_stride, 1, in_dev, yd, 1, 1.0, &launches));
+
+  // neighbours, local fits, gradient matrix (row i = gradient at sample i)
+  e = knn_launch(Xp, n, d, ld, k, idx, st);
+  if (e == cudaSuccess) e = poly_grad_launch(Xp, yd, n, d, ld, idx, k, order, Gp, ld, info + 2, st);
+  if (e != cudaSuccess) { set_last_error("gradient kernels failed to launch: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  // grad_mat grad_mat^T / N (:253) on the symmetric-output GEMM, sorted eigendecomposition (:259-271) by Jacobi
+  ST_TRY(c.mm(c.view_rows(Gp, n), false, Gp, Gm, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, false, 1));
+  finish_cov_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(Gm, d, ld, 1.0 / (double)n, 0, S, nullptr);
+  CU_TRY(cudaGetLastError());
+  e = jacobi_svd_launch(S, ld, d, sig, Vr, Ur, L16, ld, js, info, st);
+  if (e != cudaSuccess) { set_last_error("jacobi launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+
+  double* ev_cm = out_dev ? evecs : rb.raw("cov_evcm", (size_t)d * d);
+  double* g_cm = grad_mat == nullptr ? nullptr : (out_dev ? grad_mat : rb.raw("as_gout", (size_t)n * d));
+  if (!ev_cm || (grad_mat != nullptr && !g_cm)) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
+  e = scatter_launch(Ur, d, d, ld, ev_cm, 1, d, st);
+  if (e == cudaSuccess && g_cm != nullptr) e = scatter_launch(Gp, n, d, ld, g_cm, d, 1, st);   // k x N column-major
+  if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  int hinfo[4] = {0, 0, 0, 0};
+  if (out_dev) {
+    CU_TRY(cudaMemcpyAsync(evals, sig, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    CU_TRY(cudaMemcpyAsync(evals, sig, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(evecs, ev_cm, (size_t)d * d * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CU_TRY(cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (!out_dev && grad_mat != nullptr) ST_TRY(copy_out(ctx, st, grad_mat, g_cm, (size_t)n * d));
+  if (n_deficient) *n_deficient = hinfo[2];
+  return CORRLA_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int corrla_active_ss_f64(const double* x, int64_t n_samples, int64_t n_features, int64_t x_rs, int64_t x_cs, const double* y,
+                         int64_t y_stride, int order, int n_nbr, const corrla_rsvd_opts* opts, double* evals, double* evecs,
+                         double* grad_mat, int* n_deficient) {
+  try {
+    return active_ss_impl(x, n_samples, n_features, x_rs, x_cs, y, y_stride, order, n_nbr, opts, evals, evecs, grad_mat, n_deficient);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
 
 int corrla_cov_f64(const double* x, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride, int kind,
                    double scale, const corrla_rsvd_opts* opts, double* out, double* means, double* evals, double* evecs) {

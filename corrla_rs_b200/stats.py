@@ -2,9 +2,10 @@
 `pearson_corr` (src/lib_math_utils/stats_corr.rs:14-43) and of `ActiveSsRsvd::fit` / `fit_svd` / `FittedActiveSsRsvd`
 (src/lib_math_utils/active_subspaces.rs:147-278) over `corrla_cov_f64` and `corrla_rsvd_f64`.
 
-The gradient matrix itself (kd-tree neighbours + local polynomial fits, active_subspaces.rs:66-141) is irregular scalar
-work outside the scope of the engine: `ActiveSsRsvd` takes either a precomputed gradient matrix or any estimator object
-with the reference's `grad_at(x0)` interface."""
+The gradient matrix of the reference's `PolyGradientEstimator` (kd-tree neighbours + one local polynomial fit per sample,
+active_subspaces.rs:66-141, :226-238) is built on the device by `corrla_active_ss_f64` (exact brute-force neighbour
+search + batched least squares): `active_ss_fit` / `active_ss`.  `ActiveSsRsvd` additionally takes a precomputed
+gradient matrix or any estimator object with the reference's `grad_at(x0)` interface."""
 from __future__ import annotations
 
 import ctypes as C
@@ -13,7 +14,7 @@ import numpy as np
 
 from . import _ffi
 
-__all__ = ["cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd"]
+__all__ = ["cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "active_ss_fit", "active_ss"]
 
 _KINDS = {"gram": 0, "centered": 1, "pearson": 2}
 
@@ -57,6 +58,59 @@ def mat_cov_centered(x, **kw):
 def pearson_corr(x, **kw):
     """Linear correlation coefficients between the columns of x (stats_corr.rs:14-28)."""
     return cov(x, "pearson", **kw)
+
+
+def active_ss_fit(x, y, order: int, n_nbr: int, n_comps: int, *, return_gradients: bool = False, ctx=None):
+    """Gradient matrix from the samples (x: (N, k), y: (N,) or (N, 1)) and the fit of `ActiveSsRsvd::fit`, in one device
+    call.  Returns a FittedActiveSsRsvd (plus the k x N gradient matrix with return_gradients=True); its attribute
+    `n_deficient` counts samples whose neighbourhood gave a rank-deficient local fit."""
+    api = _api()
+    lib = _ffi.load()
+    a = api._Mat(x, "a_mat")
+    if api._is_torch(y):
+        yy = y.reshape(-1, 1)
+    else:
+        yy = np.asarray(y)
+        if yy.dtype != np.float64:
+            raise TypeError("y must be a float64 array")
+        yy = yy.reshape(-1, 1)
+    b = api._Mat(yy, "y")
+    if a.on_device != b.on_device:
+        raise ValueError("a_mat and y must both be on the host or both on the device")
+    n, k = a.shape
+    if b.shape[0] != n:
+        raise ValueError(f"a_mat has {n} samples, y has {b.shape[0]}")
+    for name, v in (("order", order), ("n_nbr", n_nbr), ("n_comps", n_comps)):
+        if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
+            raise TypeError(f"{name} must be an int")
+        if v < 0:
+            raise OverflowError(f"can't convert negative int to unsigned ({name})")
+    device = a.device if a.on_device else None
+    ctx = ctx or api._context_for(device)
+    stream = api._current_stream(device) if a.on_device else None
+    o, _ = api._make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=None, seed=0,
+                          schedule="reference", comm=None, global_rows=None, stream=stream, device=device)
+    evals = api._colmajor_empty_like(a, k, 1)
+    evecs = api._colmajor_empty_like(a, k, k)
+    grads = api._colmajor_empty_like(a, k, n) if return_gradients else None
+    ndef = C.c_int(0)
+    st = lib.corrla_active_ss_f64(a.ptr, n, k, a.strides[0], a.strides[1], b.ptr, b.strides[0], int(order), int(n_nbr),
+                                  C.byref(o), api._ptr(evals), api._ptr(evecs),
+                                  api._ptr(grads) if return_gradients else None, C.byref(ndef))
+    _ffi.check(st)
+    ev, vec = (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v) for v in (evals, evecs))
+    fit = FittedActiveSsRsvd(vec, np.diag(ev.ravel()), n_comps)
+    fit.n_deficient = int(ndef.value)
+    return (fit, grads) if return_gradients else fit
+
+
+def active_ss(a_mat, y, order: int, n_nbr: int, n_comps: int):
+    """Drop-in for the pyo3 `corrla_rs.active_ss(a_mat, y, order, n_nbr, n_comps)` (lib_math_utils_py.rs:56-86):
+    returns (components (k, n_comps), singular_vals (k, n_comps) -- the leading columns of the diagonal eigenvalue
+    matrix, as the reference slices it --, var_sensi (k,))."""
+    fit = active_ss_fit(a_mat, y, order, n_nbr, n_comps)
+    return (np.ascontiguousarray(fit.components()), np.ascontiguousarray(fit.singular_vals()),
+            np.asarray(fit.var_diag_evd_sensi()))
 
 
 class FittedActiveSsRsvd:

@@ -176,6 +176,22 @@ CORRLA_API int corrla_cov_f64(const double* x, int64_t nrows, int64_t ncols, int
                    int kind, double scale, const corrla_rsvd_opts* opts, double* out, double* means,
                    double* evals, double* evecs);
 
+/* Active subspace from samples: the gradient matrix of PolyGradientEstimator + ActiveSsRsvd::create_grad_mat
+ * (src/lib_math_utils/active_subspaces.rs:66-141, :226-238) and the sorted eigendecomposition of grad grad^T / N of
+ * ActiveSsRsvd::fit (:248-278), behind the pyo3 active_ss (lib_math_utils_py.rs:56-86).
+ *   x : n_samples x n_features (element strides), y : n_samples values (element stride y_stride); host, or device with
+ *       opts->a_on_device.  order 1 (linear fit) or 2 (quadratic fit); n_nbr nearest samples per fit (<= 128).
+ *   The kd-tree walk becomes one exact brute-force nearest-neighbour kernel over all samples, the per-sample
+ *   pseudo-inverse a batched Householder least-squares kernel; order 2 differentiates the fitted polynomial analytically
+ *   where the reference takes a forward difference with eps = 1e-10.
+ *   evals : n_features eigenvalues, descending; evecs : n_features x n_features column-major (components_);
+ *   grad_mat (optional) : n_features x n_samples column-major; n_deficient (optional) : samples whose neighbourhood
+ *   gave a numerically rank-deficient design matrix.  n_features <= 128 (order 1) / 14 (order 2).
+ * CORRLA_ERR_INVALID where the reference asserts (too few samples or neighbours for the fit). */
+CORRLA_API int corrla_active_ss_f64(const double* x, int64_t n_samples, int64_t n_features, int64_t x_rs, int64_t x_cs,
+                         const double* y, int64_t y_stride, int order, int n_nbr, const corrla_rsvd_opts* opts,
+                         double* evals, double* evecs, double* grad_mat, int* n_deficient);
+
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
  * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 2048 (column panels above 128).  rank_out (optional) =
  * live columns found before the orthonormal completion. */

@@ -55,8 +55,9 @@ def test_type_errors_like_pyo3(built_lib):
     with pytest.raises(OverflowError):
         corrla_rs.rsvd(np.zeros((4, 4)), -1, 1, 1)                        # usize extraction
     with pytest.raises(NotImplementedError):
-        corrla_rs.active_ss
+        corrla_rs.cs_dirichlet_sample
     assert callable(corrla_rs.PyDMDc) and callable(corrla_rs.PyPodI) and callable(corrla_rs.PyRbfInterp)
+    assert callable(corrla_rs.active_ss)
 
 
 def test_no_cpu_fallback_without_gpu(built_lib):
@@ -72,7 +73,8 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     a = np.random.default_rng(0).standard_normal((32, 8))
     for call in (lambda: cb.rsvd(a, 2, 2, 2), lambda: cb.power_iter(a, 3, 2), lambda: cb.par_matmul(a, a.T.copy()[:, :4]),
                  lambda: cb.random_mat_normal(4, 4, 1), lambda: cb.thin_q(a),
-                 lambda: cb.DMDc(a, np.ones((1, 8)), 1.0, 2, 2), lambda: cb.PodI(a.T.copy(), np.arange(8.0).reshape(8, 1), 2)):
+                 lambda: cb.DMDc(a, np.ones((1, 8)), 1.0, 2, 2), lambda: cb.PodI(a.T.copy(), np.arange(8.0).reshape(8, 1), 2),
+                 lambda: cb.mat_cov_centered(a), lambda: cb.active_ss(a, a[:, :1].copy(), 1, 12, 2)):
         with pytest.raises(cb.CorrlaError) as ei:
             call()
         assert ei.value.status == -7

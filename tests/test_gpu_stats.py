@@ -81,3 +81,87 @@ def test_active_subspace_fit_from_gradients(cb):
     assert ref_rsvd.subspace_sine(refs.components(), fits.components()) < 1e-8
     # the two routes agree: sigma(G / sqrt(N))^2 are the eigenvalues of G G^T / N
     assert np.allclose(np.diag(fits.singular_vals_)[:8] ** 2, np.diag(fit.singular_vals_)[:8], rtol=1e-8)
+
+
+# ------------------------------------------------------------------ gradient matrix + active subspace from samples
+def oracle_grad_mat(x, y, order, n_nbr, rows=None):
+    est = ref_stats.PolyGradientEstimator(x, y, order, n_nbr)
+    rows = range(x.shape[0]) if rows is None else rows
+    return np.stack([est.grad_at(x[i]).ravel() for i in rows], axis=1)
+
+
+def test_active_ss_readme_example(cb):
+    """readme.md:100-107: x 1000 x 10, y 1000 x 1 Gaussian, linear fits through 30 neighbours, 8 components."""
+    import corrla_rs
+    rng = np.random.default_rng(11)
+    x, y = rng.standard_normal((1000, 10)), rng.standard_normal((1000, 1))
+    comps, vals, sensi = corrla_rs.active_ss(x, y, 1, 30, 8)
+    assert comps.shape == (10, 8) and vals.shape == (10, 8) and sensi.shape == (10,)
+    fit, g = cb.active_ss_fit(x, y, 1, 30, 8, return_gradients=True)
+    g0 = oracle_grad_mat(x, y, 1, 30)
+    assert g.shape == (10, 1000) and fit.n_deficient == 0
+    assert np.max(np.abs(g - g0)) < 1e-10 * np.max(np.abs(g0))               # same neighbours, same least-squares fits
+    ref = ref_stats.ActiveSsRsvd(None, 8).fit_gradients(g0)
+    assert np.max(np.abs(np.diag(vals[:8, :8]) - np.diag(ref.singular_vals_)[:8])) < 1e-10 * ref.singular_vals_[0, 0]
+    assert ref_rsvd.subspace_sine(ref.components()[:, :3], comps[:, :3]) < 1e-8
+    assert np.allclose(sensi, ref.var_diag_evd_sensi(), rtol=1e-8, atol=1e-12)
+
+
+def test_active_ss_reference_test_quadratic_fit(cb):
+    """active_subspaces.rs:326-384 end to end on the device (quadratic local fits through 14 neighbours in 3-D).  The
+    reference differentiates the fitted quadratic by a forward difference with eps = 1e-10 (noise ~1e-6); the kernel
+    differentiates it analytically, hence the 1e-4 tolerance against the oracle."""
+    rng = np.random.default_rng(1)
+    cov3 = np.full((3, 3), 0.5) + 0.4 * np.eye(3)
+    x3 = (cov3 @ rng.standard_normal((3, 100))).T.copy()
+    y3 = 0.2 * x3[:, 0] + 0.5 * x3[:, 1] ** 2 + 0.10 * x3[:, 2] * x3[:, 0]
+    fit, g = cb.active_ss_fit(x3, y3, 2, 14, 2, return_gradients=True)
+    exact = np.stack([0.2 + 0.1 * x3[:, 2], x3[:, 1], 0.1 * x3[:, 0]])    # the function IS a quadratic: fits are exact
+    assert np.max(np.abs(g - exact)) < 1e-9
+    g0 = oracle_grad_mat(x3, y3, 2, 14)
+    assert np.max(np.abs(g - g0)) < 1e-4
+    assert abs(fit.components()[0, 0]) < abs(fit.components()[1, 0])
+    assert fit.singular_vals()[0, 0] > fit.singular_vals()[1, 1]
+    sens = fit.var_diag_evd_sensi()
+    assert len(sens) == 3 and sens[1] > sens[0] and sens[1] > sens[2]
+
+
+def test_gradient_matrix_larger_and_device(cb):
+    import torch
+    rng = np.random.default_rng(12)
+    n, d = 20000, 16
+    x = rng.standard_normal((n, d))
+    w = rng.standard_normal((d, 3))
+    y = np.sin(x @ w[:, 0]) + 0.5 * (x @ w[:, 1]) ** 2 + x @ w[:, 2]
+    fit, g = cb.active_ss_fit(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), 1, 40, 3, return_gradients=True)
+    g = g.cpu().numpy()
+    rows = list(range(0, n, 97))
+    g0 = oracle_grad_mat(x, y, 1, 40, rows)
+    assert np.max(np.abs(g[:, rows] - g0)) < 1e-9 * np.max(np.abs(g0))
+    ref = ref_stats.ActiveSsRsvd(None, 3).fit_gradients(g)           # the fit itself, on the same gradient matrix
+    ev, ev0 = np.diag(fit.singular_vals_), np.diag(ref.singular_vals_)
+    assert np.max(np.abs(ev - ev0)) < 1e-11 * ev0[0]
+    assert ref_rsvd.subspace_sine(ref.components(), fit.components()) < 1e-8
+
+
+def test_active_ss_asserts_ties_and_limits(cb):
+    rng = np.random.default_rng(13)
+    x, y = rng.standard_normal((200, 4)), rng.standard_normal(200)
+    with pytest.raises(cb.CorrlaError) as ei:
+        cb.active_ss(x, y, 1, 5, 2)                      # n_nbrs > k + 1 is asserted by the reference (:116)
+    assert ei.value.status == -1
+    with pytest.raises(cb.CorrlaError):
+        cb.active_ss(x, y, 3, 20, 2)                     # "Not implemented est order"
+    with pytest.raises(cb.CorrlaError) as ei:
+        cb.active_ss(x, y, 1, 150, 2)                    # more neighbours than the selection lists hold
+    assert ei.value.status == -4
+    # duplicated samples: zero distances and ties, neighbourhoods of identical points give rank-deficient fits
+    xd = np.repeat(x[:20], 10, axis=0)
+    yd = np.repeat(y[:20], 10)
+    fit = cb.active_ss_fit(xd, yd, 1, 8, 2)
+    assert fit.n_deficient > 0 and np.all(np.isfinite(fit.components_)) and np.all(np.isfinite(fit.singular_vals_))
+    # every neighbour (n_nbr >= N): the fit is the global regression, identical at every sample
+    xs, ys = x[:40], x[:40] @ np.array([1.0, -2.0, 0.5, 3.0]) + 0.7
+    fit, g = cb.active_ss_fit(xs, ys, 1, 64, 1, return_gradients=True)
+    assert np.max(np.abs(g - np.array([[1.0], [-2.0], [0.5], [3.0]]))) < 1e-11
+    assert abs(np.diag(fit.singular_vals_)[0] - 14.25) < 1e-9 and np.max(np.abs(np.diag(fit.singular_vals_)[1:])) < 1e-12
