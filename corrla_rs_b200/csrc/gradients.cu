@@ -16,6 +16,43 @@ constexpr int kDC = 32;           // features per staged chunk
 constexpr int kKnnThreads = 256;
 constexpr int kQPitch = kQT + 1, kCPitch = kCT + 1;   // odd pitches: the transposing stores are conflict free
 
+// Warp-collective insertion of the lanes flagged in `mask` (lowest lane first = increasing candidate index) into the
+// sorted list (ld, li) of length k; returns the new k-th best distance.  Equal distances keep the lower index first.
+__device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dist, int cand, double thr, unsigned mask,
+                                          int lane) {
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    const double dv = __shfl_sync(0xffffffffu, dist, src);
+    const int iv = __shfl_sync(0xffffffffu, cand, src);
+    if (dv < thr) {
+      int cnt = 0;
+      for (int p = lane; p < k; p += 32) cnt += (ld[p] <= dv) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      const int pos = cnt;
+      double td[4]; int ti[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = lane + 32 * j;
+        td[j] = 0.0; ti[j] = 0;
+        if (p > pos && p < k) { td[j] = ld[p - 1]; ti[j] = li[p - 1]; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = lane + 32 * j;
+        if (p > pos && p < k) { ld[p] = td[j]; li[p] = ti[j]; }
+        else if (p == pos && p < k) { ld[p] = dv; li[p] = iv; }
+      }
+      __syncwarp();
+      thr = ld[k - 1];
+    }
+    mask &= mask - 1;
+    mask &= __ballot_sync(0xffffffffu, dist < thr);
+  }
+  return thr;
+}
+
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, int* __restrict__ idx_out) {
   extern __shared__ __align__(16) double smk[];
@@ -59,48 +96,21 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
           for (int b = 0; b < 4; ++b) { const double t = qv[a] - cv[b]; acc[a][b] = fma(t, t, acc[a][b]); }
       }
     }
-    // selection: warp w owns queries 8w .. 8w+7; candidates are visited in increasing index order
+    // selection: warp w owns queries 8w .. 8w+7; candidates are visited in increasing index order.  Only the threshold
+    // test is unrolled; the (rare) insertion is one out-of-line routine, which keeps the hot loop in the instruction cache
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int ql = 8 * warp + a;
-      if (q0 + ql >= n) break;                                        // uniform in the warp
-      double* ld = Ld + (size_t)ql * k;
-      int* li = Li + (size_t)ql * k;
-      double thr = ld[k - 1];
+      if (q0 + ql < n) {                                              // uniform in the warp
+        double* ld = Ld + (size_t)ql * k;
+        int* li = Li + (size_t)ql * k;
+        double thr = ld[k - 1];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int64_t cg = c0 + lane + 32 * b;
-        const double dist = (cg < n) ? acc[a][b] : DBL_MAX;
-        unsigned mask = __ballot_sync(0xffffffffu, dist < thr);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          const double dv = __shfl_sync(0xffffffffu, dist, src);
-          const int iv = (int)__shfl_sync(0xffffffffu, (int)cg, src);
-          if (dv < thr) {
-            int cnt = 0;
-            for (int p = lane; p < k; p += 32) cnt += (ld[p] <= dv) ? 1 : 0;     // equal distances keep the lower index first
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            const int pos = cnt;
-            double td[4]; int ti[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int p = lane + 32 * j;
-              td[j] = 0.0; ti[j] = 0;
-              if (p > pos && p < k) { td[j] = ld[p - 1]; ti[j] = li[p - 1]; }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int p = lane + 32 * j;
-              if (p > pos && p < k) { ld[p] = td[j]; li[p] = ti[j]; }
-              else if (p == pos && p < k) { ld[p] = dv; li[p] = iv; }
-            }
-            __syncwarp();
-            thr = ld[k - 1];
-          }
-          mask &= mask - 1;
-          mask &= __ballot_sync(0xffffffffu, dist < thr);
+        for (int b = 0; b < 4; ++b) {
+          const int64_t cg = c0 + lane + 32 * b;
+          const double dist = (cg < n) ? acc[a][b] : DBL_MAX;
+          const unsigned mask = __ballot_sync(0xffffffffu, dist < thr);
+          if (mask) thr = knn_insert(ld, li, k, dist, (int)cg, thr, mask, lane);
         }
       }
     }
