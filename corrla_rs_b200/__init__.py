@@ -128,6 +128,9 @@ class _Mat:
     """(pointer, shape, element strides, residency) of a 2-D f64 array, numpy or torch."""
 
     def __init__(self, x, name="a_mat"):
+        if not _is_torch(x) and not isinstance(x, np.ndarray) and hasattr(x, "__cuda_array_interface__"):
+            import torch                      # cupy / numba device arrays: zero-copy view (SURVEY H5)
+            x = torch.as_tensor(x, device="cuda")
         if _is_torch(x):
             import torch
             if x.dtype != torch.float64 or x.dim() != 2:

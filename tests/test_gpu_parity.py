@@ -735,3 +735,22 @@ def test_concurrent_callers(cb):
         assert not errs, errs
         for (u0, s0, v0), (u, s, v) in zip(seq, res):
             assert np.array_equal(s0, s) and np.array_equal(u0, u) and np.array_equal(v0, v)
+
+
+def test_cuda_array_interface_input(cb):
+    """Device arrays from other libraries (cupy, numba) are accepted through __cuda_array_interface__ without a copy."""
+    import torch
+
+    class Foreign:
+        def __init__(self, t):
+            self._t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    rng = np.random.default_rng(95)
+    a = rng.standard_normal((4000, 64))
+    omega = rng.standard_normal((64, 20))
+    t = torch.from_numpy(a).cuda()
+    u, s, vt = cb.rsvd(Foreign(t), 12, 3, 8, omega=omega)
+    torch.cuda.synchronize()
+    assert u.is_cuda
+    assert_parity(tuple(x.cpu().numpy() for x in (u, s, vt)), ref_rsvd.random_svd(a, 12, 3, 8, omega=omega), 12)
