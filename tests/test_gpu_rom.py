@@ -182,3 +182,68 @@ def test_pypodi_reference_generator_and_device_input(cb):
     modes, weights, _s = cb.pod_modes_weights(xd, 4, seed=2)
     assert modes.is_cuda and tuple(modes.shape) == (100, 4) and tuple(weights.shape) == (20, 4)
     assert float((weights - xd @ modes).abs().max()) < 1e-11
+
+
+# ------------------------------------------------------------------ randomised shapes / layouts / residency
+def test_rom_fuzz(cb):
+    """Random sizes, layouts (C / Fortran / strided views / device tensors) and mode counts for DMDc, POD, covariance
+    and the active-subspace gradients, each checked against the oracle on basis-independent quantities."""
+    import torch
+    from oracle import ref_stats
+    rng = np.random.default_rng(2024)
+
+    def relayout(a, kind):
+        if kind == 1:
+            return np.asfortranarray(a)
+        if kind == 2:
+            wide = np.zeros((a.shape[0], 2 * a.shape[1])); wide[:, ::2] = a
+            return wide[:, ::2]
+        if kind == 3:
+            wide = np.zeros((a.shape[0] + 1, a.shape[1] + 3)); wide[1:, 1:a.shape[1] + 1] = a
+            return wide[1:, 1:a.shape[1] + 1]
+        return a
+
+    for trial in range(10):
+        # --- DMDc on an exactly low-rank controlled system
+        n_x, n_u, nt, r_true = int(rng.integers(30, 900)), int(rng.integers(1, 4)), int(rng.integers(24, 80)), int(rng.integers(2, 6))
+        x, u, _a, bmat, lam = planted_system(rng, n_x, n_u, nt, r_true)
+        r = r_true + n_u
+        omegas = dmd_omegas(rng, n_x, n_u, nt, r)
+        ref = ref_rom.DMDc(x, u, 1.0, r, 4, omegas=omegas)
+        kind = int(rng.integers(0, 5))
+        if kind == 4:
+            ops = cb.dmdc_operators(torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda(), r, 4, omegas=omegas)
+            ops = {k_: v.cpu().numpy() for k_, v in ops.items()}
+        else:
+            ops = cb.dmdc_operators(relayout(x, kind), u, r, 4, omegas=omegas)
+        tag = (trial, n_x, n_u, nt, r_true, kind)
+        assert np.max(np.abs(ops["b"] - ref.b)) < 1e-7 * max(1.0, np.max(np.abs(ref.b))), tag
+        ev, ev0 = np.sort_complex(np.linalg.eigvals(ops["a_til"])), np.sort_complex(np.linalg.eigvals(ref.a_til))
+        assert np.max(np.abs(ev - ev0)) < 1e-7, tag
+        # --- POD
+        n_snap, n_points, r = int(rng.integers(8, 60)), int(rng.integers(40, 3000)), int(rng.integers(1, 6))
+        base = rng.standard_normal((n_snap, 7)) * (4.0 * 0.5 ** np.arange(7))
+        xs = base @ np.linalg.qr(rng.standard_normal((n_points, 7)))[0].T + 1e-7 * rng.standard_normal((n_snap, n_points))
+        n_thin = min(n_snap, n_points)
+        omega = rng.standard_normal((n_thin, min(r + 10, n_thin)))
+        refp = ref_rom.PodI(xs, np.arange(n_snap, dtype=np.float64).reshape(-1, 1), r, omega=omega)
+        modes, weights, _s = cb.pod_modes_weights(relayout(xs, int(rng.integers(0, 4))), r, omega=omega)
+        assert np.max(np.abs(weights @ modes.T - refp.mode_weights @ refp.modes.T)) < 1e-8 * np.max(np.abs(xs)), (trial, n_snap, n_points, r)
+        # --- covariance / correlation
+        n, d = int(rng.integers(3, 5000)), int(rng.integers(1, 129))
+        xc = rng.standard_normal((n, d)) * rng.uniform(0.1, 10.0, d) + rng.uniform(-100.0, 100.0, d)
+        lay = relayout(xc, int(rng.integers(0, 4)))
+        c0 = ref_stats.mat_cov_centered(xc)
+        assert np.max(np.abs(cb.mat_cov_centered(lay) - c0)) < 1e-10 * np.max(np.abs(c0)), (trial, n, d)
+        if n > 3:
+            assert np.max(np.abs(cb.pearson_corr(lay) - ref_stats.pearson_corr(xc))) < 1e-9, (trial, n, d)
+        # --- gradients of local linear fits
+        n, d = int(rng.integers(60, 1500)), int(rng.integers(1, 12))
+        k = int(rng.integers(d + 2, min(n, 60) + 1))
+        xg = rng.standard_normal((n, d))
+        yg = np.sin(xg @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+        _fit, g = cb.active_ss_fit(relayout(xg, int(rng.integers(0, 4))), yg, 1, k, 1, return_gradients=True)
+        est = ref_stats.PolyGradientEstimator(xg, yg, 1, k)
+        rows = rng.choice(n, size=12, replace=False)
+        g0 = np.stack([est.grad_at(xg[i]).ravel() for i in rows], axis=1)
+        assert np.max(np.abs(g[:, rows] - g0)) < 1e-8 * max(1.0, np.max(np.abs(g0))), (trial, n, d, k)
