@@ -337,9 +337,16 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
         const double a = nrm[p], b = nrm[q];
         if (c * c > tol2 * a * b) {
           // t = sign(d) * 2c / (|d| + sqrt(d^2 + 4c^2)), d = b - a  (== sign(zeta)/(|zeta| + sqrt(1 + zeta^2)))
+          // division- and sqrt-free form (two rsqrt): cos(2 theta) = |d| r, r = 1/sqrt(d^2 + 4c^2); cs = sqrt(u) with
+          // u = (1 + cos 2theta)/2; sn = |c| r / cs; t = sn / cs = |c| r / u, signs from d*c
           const double d = b - a;
-          const double t = copysign(2.0 * c, d * c) / (fabs(d) + sqrt(d * d + 4.0 * c * c));
-          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+          const double rr = rsqrt(fma(d, d, 4.0 * c * c));
+          const double u = fma(0.5 * fabs(d), rr, 0.5);
+          const double icu = rsqrt(u);
+          const double cr = fabs(c) * rr;
+          const double cs = u * icu;
+          const double sn = copysign(cr * icu, d * c);
+          const double t = copysign(cr * icu * icu, d * c);
           double2* vp = reinterpret_cast<double2*>(Vc + p * lp);
           double2* vq = reinterpret_cast<double2*>(Vc + q * lp);
 #pragma unroll 4
@@ -935,6 +942,11 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose) {
+  {
+    const cudaError_t ce = jacobi_svd_cluster_launch(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, info, s, transpose);
+    if (ce == cudaSuccess) return ce;
+    if (ce != cudaErrorNotSupported) cudaGetLastError();     // launch refused: fall back to the single-CTA kernel
+  }
   const int lp = (l + 1) & ~1;
   const size_t mat = (size_t)l * lp * 8;
   const size_t small = (size_t)l * 8 + (size_t)(l + 4) * 4 + 16;

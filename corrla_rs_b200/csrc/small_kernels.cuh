@@ -40,6 +40,12 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose = 1);
 
+// Cluster variant (jacobi_cluster.cu): row slabs of X and V in the shared memory of 4 or 8 CTAs, partial dot products
+// exchanged through DSMEM.  cudaErrorNotSupported when it does not apply (l < 32, slabs too large, or
+// CORRLA_B200_JACOBI_CLUSTER=0); jacobi_svd_launch tries it first.
+cudaError_t jacobi_svd_cluster_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
+                                      int ldo, int* info, cudaStream_t s, int transpose);
+
 // dst[i*ldd + j] = scale * src[i*rs + j*cs] for i < rows, j < cols (any strides, device pointers).
 cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double* dst,
                           int64_t ldd, cudaStream_t s, double scale = 1.0);
