@@ -23,7 +23,40 @@ constexpr int kCJThreads = 512;          // 64 groups of 8 lanes: every pair of 
 constexpr int kCJLanes = 8;
 constexpr int kCJMaxSweeps = 60;
 constexpr int kCJMaxCluster = 8;
+constexpr unsigned kCJSpinLimit = 1u << 26;   // bounded waits: a lost transaction becomes an error flag, not a hang
 
+__device__ __forceinline__ uint32_t cj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cj_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 8-byte store into a peer's shared memory that completes 8 bytes of the transaction count of the peer's mbarrier
+__device__ __forceinline__ void cj_st_async(uint32_t raddr, double v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cj_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cj_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool cj_mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// kAsync: the partial sums travel as st.async stores that complete transaction bytes on the RECEIVER's mbarrier, and a
+// CTA waits only on its own mbarrier -- no cluster-wide barrier and no release fence per round.  Two buffers / two
+// mbarriers alternate; a CTA re-arms the one it has just consumed, which always happens before any peer can send the
+// exchange after next (a peer sends exchange e+2 only after it has received this CTA's exchange e+1).
+template <bool kAsync>
 __global__ void __launch_bounds__(kCJThreads)
 jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                       double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, int transpose,
@@ -42,7 +75,8 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   double2* rot = reinterpret_cast<double2*>(Vs + (size_t)l * lr);   // [h]  (cos, sin) of the round's rotations
   double* nrm = reinterpret_cast<double*>(rot + h);                 // [l]  squared column norms (replicated, updated identically)
   double* recv = nrm + l;                  // [2][C][l] partial sums received from every rank, double buffered
-  int* rnk = reinterpret_cast<int*>(recv + (size_t)2 * C * l);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(recv + (size_t)2 * C * l);   // [2] mbarriers (kAsync)
+  int* rnk = reinterpret_cast<int*>(bars + 2);
   int* anyflag = rnk + l;
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int LP = kCJLanes;
@@ -51,7 +85,19 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   const int glead = (tid & 31) & ~(LP - 1);
   // lane `sub` of every group pushes to rank `sub` (C <= lanes per group)
   double* const peer_recv = (sub < C) ? cluster.map_shared_rank(recv, sub) : recv;
-
+  const uint32_t peer_recv_a = cj_mapa(cj_smem_u32(recv), (uint32_t)(sub < C ? sub : rank));
+  const uint32_t peer_bar_a = cj_mapa(cj_smem_u32(bars), (uint32_t)(sub < C ? sub : rank));
+  const uint32_t my_bar_a = cj_smem_u32(bars);
+  const uint32_t bytes_cols = (uint32_t)(C * l * 8), bytes_pairs = (uint32_t)(C * h * 8);
+  unsigned uses0 = 0, uses1 = 0;              // completed uses of the two mbarriers (phase parity)
+  int failed = 0;
+  if (kAsync && tid == 0) {
+    cj_mbar_init(my_bar_a, 1);
+    cj_mbar_init(my_bar_a + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cj_mbar_expect(my_bar_a, bytes_cols);         // exchange 0: the column norms of the first sweep
+    cj_mbar_expect(my_bar_a + 8, bytes_pairs);    // exchange 1: the dot products of round 0
+  }
   // squared norms of the source columns (all rows; every CTA computes the same numbers), descending rank
   for (int j = grp; j < l; j += ngrp) {
     double a = 0.0;
@@ -89,6 +135,26 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   const double tol2 = tol * tol;
   const int lr2 = lr >> 1;
   int par = 0, sweeps = 0, converged = 0;
+  // lane sub < C: store one partial sum into slot `slot` of buffer `par` on rank `sub`
+  auto push = [&](int slot, double v) {
+    const size_t idx = ((size_t)par * C + rank) * l + slot;
+    if (kAsync) cj_st_async(peer_recv_a + (uint32_t)(idx * 8), v, peer_bar_a + (uint32_t)(par * 8));
+    else peer_recv[idx] = v;
+  };
+  // all partial sums of the current exchange have arrived in buffer `par`.  next2_cols: the exchange after next (which
+  // reuses this buffer and its mbarrier) carries column sums (l values per rank) rather than dot products (h values)
+  auto arrived = [&](bool next2_cols) {
+    if (kAsync) {
+      const uint32_t bar = my_bar_a + (uint32_t)(par * 8);
+      const unsigned phase = (par == 0 ? uses0 : uses1) & 1u;
+      unsigned spins = 0;
+      while (!cj_mbar_try_wait(bar, phase)) { if (++spins > kCJSpinLimit) { failed = 1; break; } }
+      if (par == 0) ++uses0; else ++uses1;
+      if (tid == 0) cj_mbar_expect(bar, next2_cols ? bytes_cols : bytes_pairs);
+    } else {
+      cluster.sync();
+    }
+  };
   // sum over the ranks of one value per column: partial over my rows -> every peer -> fixed-order sum
   auto column_sums = [&](bool take_sqrt) {
     for (int j = grp; j < l; j += ngrp) {
@@ -97,9 +163,9 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       for (int i = sub; i < lr2; i += LP) { const double2 x = xj[i]; a += x.x * x.x + x.y * x.y; }
 #pragma unroll
       for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
-      if (sub < C) peer_recv[((size_t)par * C + rank) * l + j] = a;      // the butterfly left the total in every lane
+      if (sub < C) push(j, a);                              // the butterfly left the total in every lane
     }
-    cluster.sync();
+    arrived(false);                                         // two exchanges later: round 1 of this sweep (or nothing)
     for (int j = tid; j < l; j += nt) {
       double a = 0.0;
       for (int src = 0; src < C; ++src) a += recv[((size_t)par * C + src) * l + j];
@@ -118,18 +184,20 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
         if (pi == 0) { p = N1; q = r; }
         else { p = r + pi; if (p >= N1) p -= N1; q = r - pi; if (q < 0) q += N1; }
         if (p > q) { const int tmp = p; p = q; q = tmp; }
-        if (q >= l) continue;                             // bye
-        const double2* xp = reinterpret_cast<const double2*>(Xs + (size_t)p * lr);
-        const double2* xq = reinterpret_cast<const double2*>(Xs + (size_t)q * lr);
-        double c0 = 0.0, c1 = 0.0;
-        for (int i = sub; i < lr2; i += LP) { const double2 x = xp[i], y = xq[i]; c0 += x.x * y.x; c1 += x.y * y.y; }
-        double c = c0 + c1;
+        double c = 0.0;                                   // a bye sends 0: every exchange has a fixed byte count
+        if (q < l) {
+          const double2* xp = reinterpret_cast<const double2*>(Xs + (size_t)p * lr);
+          const double2* xq = reinterpret_cast<const double2*>(Xs + (size_t)q * lr);
+          double c0 = 0.0, c1 = 0.0;
+          for (int i = sub; i < lr2; i += LP) { const double2 x = xp[i], y = xq[i]; c0 += x.x * y.x; c1 += x.y * y.y; }
+          c = c0 + c1;
 #pragma unroll
-        for (int o = LP / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
-        c = __shfl_sync(gmask, c, glead);
-        if (sub < C) peer_recv[((size_t)par * C + rank) * l + pi] = c;
+          for (int o = LP / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
+          c = __shfl_sync(gmask, c, glead);
+        }
+        if (sub < C) push(pi, c);
       }
-      cluster.sync();
+      arrived(r == N1 - 2);                               // exchange after next: column sums iff this is round N1 - 2
       // rotation parameters: ONE thread per pair (the fp64 divide / square roots cost ~150 instructions; done by all
       // lanes of every group they would occupy the FP64 pipe for longer than everything else in the round)
       for (int pi = tid; pi < h; pi += nt) {
@@ -211,7 +279,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
     out_ux[(int64_t)i * ldo + r] = sj > 0.0 ? Xs[(size_t)j * lr + il] / sj : 0.0;
     out_va[(int64_t)i * ldo + r] = Vs[(size_t)j * lr + il];
   }
-  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = converged; }
+  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = failed ? -1 : converged; }
   // exactly zero singular values leave zero columns in Ux: rank 0 completes them to an orthonormal basis (unit
   // vectors, two Gram-Schmidt passes), like the single-CTA kernel
   __syncthreads();
@@ -279,9 +347,12 @@ cudaError_t jacobi_svd_cluster_launch(const double* W, int ldw, int l, double* s
   const int C = (req == 2 || req == 4) ? req : kCJMaxCluster;
   int lr = (l + C - 1) / C;
   lr = (lr + 1) & ~1;
-  const size_t smem = ((size_t)2 * l * lr + (size_t)l + (size_t)2 * C * l + (size_t)(l + 1)) * 8 + ((size_t)l + 4) * 4;
+  const size_t smem = ((size_t)2 * l * lr + (size_t)l + (size_t)2 * C * l + (size_t)(l + 1) + 2) * 8 + ((size_t)l + 4) * 4;
   if (smem > (size_t)220 * 1024) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  // CORRLA_B200_JACOBI_EXCHANGE=barrier selects the cluster-barrier exchange instead of st.async + mbarrier
+  static const int use_async = [] { const char* e = getenv("CORRLA_B200_JACOBI_EXCHANGE"); return (e != nullptr && e[0] == 'b') ? 0 : 1; }();
+  auto kern = use_async ? jacobi_cluster_kernel<true> : jacobi_cluster_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)C, 1, 1);
@@ -295,7 +366,7 @@ cudaError_t jacobi_svd_cluster_launch(const double* W, int ldw, int l, double* s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info);
+  return cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info);
 }
 
 }  // namespace corrla
