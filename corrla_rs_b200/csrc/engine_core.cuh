@@ -398,9 +398,16 @@ struct Core {
     ST_TRY(read_flags(fs, &robust, nullptr));                    // identical on every rank: G is the all-reduced Gram
     if (!robust) {
       // fast path: CholeskyQR2
+      // ... with the second Cholesky replaced by its first-order expansion: the probe bounds cond(G) by ~1e8, so after
+      // the first pass G2 = I + E with |E| <~ 1e-8 and X*(3/2 I - 1/2 G2) is orthonormal to (3/8)E^2 ~ 1e-16.  Tfold is
+      // then symmetric, not triangular: every consumer of Tfold multiplies with the general GEMM.
       ST_TRY(apply_tri(vx, T1, X, nullptr));
       ST_TRY(gram(vx, X, nullptr, gx));
-      ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, nullptr, true, nullptr));
+      {
+        cudaError_t e = lowdin_launch(G, ld, l, Tfold, L16, ld, st);
+        ++launches;
+        if (e != cudaSuccess) { set_last_error("lowdin launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+      }
       ++qr_calls;
       return CORRLA_OK;
     }

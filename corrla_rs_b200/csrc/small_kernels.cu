@@ -968,6 +968,24 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256)
+lowdin_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict__ T, int Lrows, int ldt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Lrows * ldt) return;
+  const int i = idx / ldt, j = idx - i * ldt;
+  double v = 0.0;
+  if (i < l && j < l) {
+    const double g = (i <= j) ? G[(int64_t)i * ldg + j] : G[(int64_t)j * ldg + i];
+    v = (i == j ? 1.5 : 0.0) - 0.5 * g;
+  }
+  T[idx] = v;
+}
+
+cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, cudaStream_t s) {
+  lowdin_kernel<<<(Lrows * ldt + 255) / 256, 256, 0, s>>>(G, ldg, l, T, Lrows, ldt);
+  return cudaGetLastError();
+}
+
 cudaError_t repack_launch(const double* src, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double* dst,
                           int64_t ldd, cudaStream_t s, double scale) {
   if (rows <= 0 || cols <= 0) return cudaSuccess;

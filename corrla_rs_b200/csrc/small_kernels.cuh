@@ -40,6 +40,11 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose = 1);
 
+// T = 3/2 I - 1/2 G on the leading l x l block (G: upper triangle valid, pitch ldg), zero elsewhere in Lrows x ldt.
+// For a Gram matrix G = I + E of nearly orthonormal columns X, X*T has orthogonality error (3/8) E^2: the symmetric
+// (Loewdin) orthogonalisation to first order, which replaces the second Cholesky of CholeskyQR2 when |E| <~ 1e-8.
+cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, cudaStream_t s);
+
 // Cluster variant (jacobi_cluster.cu): row slabs of X and V in the shared memory of 4 or 8 CTAs, partial dot products
 // exchanged through DSMEM.  cudaErrorNotSupported when it does not apply (l < 32, slabs too large, or
 // CORRLA_B200_JACOBI_CLUSTER=0); jacobi_svd_launch tries it first.

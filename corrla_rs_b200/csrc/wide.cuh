@@ -130,7 +130,8 @@ struct Wide {
         if (status != CORRLA_OK) break;
         const int refills = c.n_refill;
         status = c.qr_inplace(X[j], rows, distributed, rows_for_shift, Tq, from_a, complete);
-        if (status == CORRLA_OK) status = c.apply_tri(c.view_rows(X[j], rows), Tq, X[j], nullptr);
+        if (status == CORRLA_OK)      // Tq may be the symmetric first-order factor of the fast path: general product, in place
+          status = c.mm(c.view_rows(X[j], rows), true, Tq, X[j], c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 1);
         // columns refilled inside the panel QR are not orthogonal to the earlier panels yet: project and factor again
         if (c.n_refill == refills || j == 0) break;
       }
