@@ -79,7 +79,7 @@ __device__ __forceinline__ void chol_load(CholState& st, const double* __restric
   st.minratio = DBL_MAX;
 }
 
-__device__ __forceinline__ void chol_eliminate(CholState& st, int l, const double* d0, double (*rowbuf)[128],
+__device__ __forceinline__ void chol_eliminate(CholState& st, int l, const double* d0, const double* d0inv, double (*rowbuf)[128],
                                                double* tdiag, int* dead_s, bool shifted, double tol_dead, int ty,
                                                int tx) {
   for (int j = 0; j < l; ++j) {
@@ -95,7 +95,7 @@ __device__ __forceinline__ void chol_eliminate(CholState& st, int l, const doubl
     bool is_dead;
     if (shifted) is_dead = !(dj > 0.0) || !(piv > 0.0);
     else is_dead = !(dj > 0.0) || !(piv > tol_dead * dj);
-    const double ratio = (dj > 0.0 && piv > 0.0) ? piv / dj : 0.0;
+    const double ratio = (dj > 0.0 && piv > 0.0) ? piv * d0inv[j] : 0.0;    // reciprocals precomputed: no fp64 divide per step
     if (ratio < st.minratio) st.minratio = ratio;
     if (ty == 0 && tx == 0) dead_s[j] = is_dead ? 1 : 0;
     if (is_dead) {
@@ -144,7 +144,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
                 const int* cond_flag) {
   if (cond_flag != nullptr && *cond_flag == 0) return;
   extern __shared__ double sm[];
-  __shared__ double rowbuf[2][128], d0[128], tdiag[128];
+  __shared__ double rowbuf[2][128], d0[128], d0inv[128], tdiag[128];
   __shared__ int dead_s[128];
   __shared__ double trace_s;
   const int lp = l + 1;
@@ -153,7 +153,11 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
   const int tx = tid & 31, ty = tid >> 5;
   const double tol_dead = kTolDeadPerCol * l;
 
-  for (int j = tid; j < 128; j += nt) d0[j] = (j < l) ? G[(int64_t)j * ldg + j] : 0.0;
+  for (int j = tid; j < 128; j += nt) {
+    const double g = (j < l) ? G[(int64_t)j * ldg + j] : 0.0;
+    d0[j] = g;
+    d0inv[j] = g > 0.0 ? 1.0 / g : 0.0;
+  }
   __syncthreads();
   if (tid == 0) {
     double tr = 0.0;
@@ -163,7 +167,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
   CholState st;
   chol_load(st, G, ldg, l, 0.0, ty, tx);
   __syncthreads();
-  chol_eliminate(st, l, d0, rowbuf, tdiag, dead_s, false, tol_dead, ty, tx);
+  chol_eliminate(st, l, d0, d0inv, rowbuf, tdiag, dead_s, false, tol_dead, ty, tx);
   int shifted = 0;
   if (mode == kCholAuto) {
     if (st.minratio < kTauShift) {      // uniform: every thread tracked the same pivots
@@ -171,7 +175,7 @@ chol_inv_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict
       const double shift = 11.0 * (global_rows * l + (double)l * (l + 1)) * (0.5 * DBL_EPSILON) * trace_s;
       __syncthreads();
       chol_load(st, G, ldg, l, shift, ty, tx);
-      chol_eliminate(st, l, d0, rowbuf, tdiag, dead_s, true, tol_dead, ty, tx);
+      chol_eliminate(st, l, d0, d0inv, rowbuf, tdiag, dead_s, true, tol_dead, ty, tx);
       shifted = 1;
     }
     if (tid == 0 && flag3 != nullptr) *flag3 = shifted;
