@@ -404,10 +404,13 @@ struct Core {
       ST_TRY(apply_tri(vx, T1, X, nullptr));
       ST_TRY(gram(vx, X, nullptr, gx));
       {
-        cudaError_t e = lowdin_launch(G, ld, l, Tfold, L16, ld, st);
+        cudaError_t e = lowdin_launch(G, ld, l, Tfold, L16, ld, flags + 18, st);
         ++launches;
         if (e != cudaSuccess) { set_last_error("lowdin launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
       }
+      // ||E||_F above 2e-8 (possible near the probe threshold on very tall matrices): the real second Cholesky runs,
+      // behind the device flag -- an empty launch otherwise
+      ST_TRY(chol(kCholPlain, rows_for_shift, Tfold, flags + 18, true, nullptr));
       ++qr_calls;
       return CORRLA_OK;
     }

@@ -972,21 +972,36 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256)
-lowdin_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict__ T, int Lrows, int ldt) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Lrows * ldt) return;
-  const int i = idx / ldt, j = idx - i * ldt;
-  double v = 0.0;
-  if (i < l && j < l) {
-    const double g = (i <= j) ? G[(int64_t)i * ldg + j] : G[(int64_t)j * ldg + i];
-    v = (i == j ? 1.5 : 0.0) - 0.5 * g;
+// One CTA.  Also measures E = G - I: *redo = 1 when ||E||_F^2 > 4e-16, i.e. when the neglected (3/8)E^2 would show in
+// the orthogonality of X*T; the caller then lets the Cholesky kernel overwrite T (launched behind this flag).
+__global__ void __launch_bounds__(1024)
+lowdin_kernel(const double* __restrict__ G, int ldg, int l, double* __restrict__ T, int Lrows, int ldt, int* redo) {
+  __shared__ double red[32];
+  double e2 = 0.0;
+  for (int idx = threadIdx.x; idx < Lrows * ldt; idx += blockDim.x) {
+    const int i = idx / ldt, j = idx - i * ldt;
+    double v = 0.0;
+    if (i < l && j < l) {
+      const double g = (i <= j) ? G[(int64_t)i * ldg + j] : G[(int64_t)j * ldg + i];
+      const double e = g - (i == j ? 1.0 : 0.0);
+      e2 += e * e;
+      v = (i == j ? 1.0 : 0.0) - 0.5 * e;
+    }
+    T[idx] = v;
   }
-  T[idx] = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    if (redo != nullptr) *redo = (tot > 4e-16 || !(tot == tot)) ? 1 : 0;
+  }
 }
 
-cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, cudaStream_t s) {
-  lowdin_kernel<<<(Lrows * ldt + 255) / 256, 256, 0, s>>>(G, ldg, l, T, Lrows, ldt);
+cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, int* redo, cudaStream_t s) {
+  lowdin_kernel<<<1, 1024, 0, s>>>(G, ldg, l, T, Lrows, ldt, redo);
   return cudaGetLastError();
 }
 

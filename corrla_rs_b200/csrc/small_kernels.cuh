@@ -43,7 +43,8 @@ cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, do
 // T = 3/2 I - 1/2 G on the leading l x l block (G: upper triangle valid, pitch ldg), zero elsewhere in Lrows x ldt.
 // For a Gram matrix G = I + E of nearly orthonormal columns X, X*T has orthogonality error (3/8) E^2: the symmetric
 // (Loewdin) orthogonalisation to first order, which replaces the second Cholesky of CholeskyQR2 when |E| <~ 1e-8.
-cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, cudaStream_t s);
+// *redo (device int) = 1 when ||E||_F > 2e-8: the caller then runs the real Cholesky behind that flag.
+cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows, int ldt, int* redo, cudaStream_t s);
 
 // Cluster variant (jacobi_cluster.cu): row slabs of X and V in the shared memory of 4 or 8 CTAs, partial dot products
 // exchanged through DSMEM.  cudaErrorNotSupported when it does not apply (l < 32, slabs too large, or

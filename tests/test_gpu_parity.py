@@ -306,6 +306,21 @@ def test_thin_q_ill_conditioned(cb, kappa):
     assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-11 * np.linalg.norm(a)
 
 
+@pytest.mark.parametrize("kappa", [30.0, 1e3, 3e3, 8e3, 2e4])
+def test_thin_q_near_the_fast_path_threshold(cb, kappa):
+    """cond(Y) around the probe threshold (~1e4) on a tall matrix: the CholeskyQR fast path replaces the second Cholesky
+    by its first-order expansion only while the measured ||G2 - I||_F is below 2e-8; above it the real factorisation runs
+    behind a device flag.  Orthonormality must stay at machine precision on both sides of that switch."""
+    rng = np.random.default_rng(int(kappa))
+    m, l = 300_000, 96
+    u, _ = np.linalg.qr(rng.standard_normal((m, l)))
+    v, _ = np.linalg.qr(rng.standard_normal((l, l)))
+    a = (u * np.logspace(0, -np.log10(kappa), l)) @ v.T
+    q = cb.thin_q(a)
+    assert np.max(np.abs(q.T @ q - np.eye(l))) < 1e-13
+    assert np.linalg.norm(a - q @ (q.T @ a)) < 1e-12 * np.linalg.norm(a)
+
+
 def test_thin_q_rank_deficient_is_completed(cb):
     rng = np.random.default_rng(114)
     base = rng.standard_normal((3000, 10))
