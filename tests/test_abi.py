@@ -101,3 +101,37 @@ def test_host_alloc_roundtrip(built_lib):
     assert float(view.sum()) == 1.5 * 3 * (1 << 20)
     del arr, view
     gc.collect()
+
+
+def test_host_side_mirrors_without_gpu():
+    """The parts of the DMDc / POD / active-subspace mirrors that are host work by design (small dense algebra) against
+    the oracle's restatement -- no device needed."""
+    from corrla_rs_b200.rom import RbfInterp
+    from corrla_rs_b200.stats import FittedActiveSsRsvd
+    from oracle import ref_rom, ref_stats
+    rng = np.random.default_rng(21)
+    t = np.sort(rng.uniform(0.0, 5.0, 17)).reshape(-1, 1)
+    w = np.stack([np.sin(t[:, 0]), t[:, 0] ** 2, np.exp(-t[:, 0])], axis=1)
+    ours = RbfInterp(1, 0.0, 1, 1)
+    ours.fit(t, w)                                                     # all weight columns at once
+    for j in range(3):
+        ref = ref_rom.RbfInterpLin(1)
+        ref.fit(t, w[:, j])
+        tq = np.array([[1.234]])
+        assert abs(ours.predict(tq)[0, j] - ref.predict(tq)[0, 0]) < 1e-12
+        assert np.max(np.abs(ours.predict(t)[:, j] - w[:, j])) < 1e-8     # interpolates the nodes
+    x2 = rng.standard_normal((25, 2))
+    y2 = np.sin(x2[:, 0]) + x2[:, 1]
+    for kernel_type, param in ((2, 1.0), (3, 0.0), (0, 0.7)):          # multiquadric, cubic, Gaussian
+        f = RbfInterp(kernel_type, param, 2, 1)
+        f.fit(x2, y2)
+        assert np.max(np.abs(f.predict(x2).ravel() - y2)) < 1e-6
+    with pytest.raises(NotImplementedError):
+        RbfInterp(1, 0.0, 2, 2)
+    g = rng.standard_normal((5, 400))
+    ref = ref_stats.ActiveSsRsvd(None, 2).fit_gradients(g)
+    fit = FittedActiveSsRsvd(ref.components_, ref.singular_vals_, 2)
+    assert np.allclose(fit.var_diag_evd_sensi(), ref.var_diag_evd_sensi())
+    xs = rng.standard_normal((7, 5))
+    assert fit.transform(xs).shape == (7, 2) and fit.inv_transform(fit.transform(xs)).shape == (7, 5)
+    assert np.allclose(fit.components(), ref.components()) and np.allclose(fit.singular_vals(), ref.singular_vals())
