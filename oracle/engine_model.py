@@ -256,3 +256,44 @@ def engine_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: in
     u = y @ (tf @ vr[:, :k])
     v = qz @ ur[:, :k]
     return u, sig[:k].reshape(k, 1).copy(), v.T.copy()
+
+
+# --------------------------------------------------------------------------------------
+# row-sharded data flow of the consumers in csrc/rom.cu (for the gloo tests)
+# --------------------------------------------------------------------------------------
+def dmdc_sharded(x_local: np.ndarray, u: np.ndarray, n_modes: int, n_iter: int, omegas, rank: int, nranks: int,
+                 allreduce=_identity_allreduce, n_x_global: float | None = None):
+    """corrla_dmdc_f64 with a communicator: every rank holds a block of state rows, the control rows are stacked under the
+    LAST rank's block; the r x r cross products are all-reduced, u_til_2 travels as an all-reduce of a buffer that is zero
+    everywhere but on the last rank.  Returns (a_til replicated, b local rows, modes_scale local rows, s_til, u_hat local)."""
+    n_x, n_u = x_local.shape[0], u.shape[0]
+    nxg = float(n_x if n_x_global is None else n_x_global)
+    last = rank == nranks - 1
+    stack = np.vstack([x_local, u]) if last else x_local
+    xv, yv = stack[:, :-1], x_local[:, 1:]
+    r = n_modes
+    u_til, s_til, vt_til = engine_rsvd(xv, r, n_iter, 12, omegas[0], allreduce=allreduce, global_rows=nxg + n_u)
+    u_hat, _s, _vt = engine_rsvd(yv, r, n_iter, 12, omegas[1], allreduce=allreduce, global_rows=nxg)
+    s = s_til.ravel()
+    s_inv = np.where(np.abs(s) < 1e-20, 0.0, 1.0 / (s + 1e-20))
+    vs = vt_til.T * s_inv
+    u1 = u_til[:n_x]
+    p1 = yv @ vs
+    tmp = allreduce(u_hat.T @ p1)
+    c1 = allreduce(u1.T @ u_hat)
+    a_til = tmp @ c1
+    u2t = allreduce(u_til[n_x:].T.copy() if last else np.zeros((r, n_u)))        # broadcast from the last rank
+    b = (u_hat @ tmp) @ u2t
+    modes_scale = yv @ (vs @ c1)
+    return a_til, b, modes_scale, s_til, u_hat
+
+
+def pod_sharded(x_local_cols: np.ndarray, n_modes: int, omega, allreduce=_identity_allreduce,
+                n_points_global: float | None = None):
+    """corrla_pod_f64 with a communicator: every rank holds a block of POINTS (columns of x); the thin matrix of the
+    RSVD is x_local^T, its left vectors are the local modes; weights = sum over ranks of x_local * modes_local."""
+    thin = x_local_cols.T
+    u, s, _vt = engine_rsvd(thin, n_modes, 10, 10, omega, allreduce=allreduce,
+                            global_rows=float(thin.shape[0] if n_points_global is None else n_points_global))
+    weights = allreduce(x_local_cols @ u)
+    return u, weights, s

@@ -31,6 +31,10 @@ def test_row_sharded_algorithm_matches_oracle(tmp_path, world):
     assert res["sigma_rel"] < 1e-10 and res["sin_u"] < 1e-8 and res["sin_v"] < 1e-8
     assert res["orth"] < 1e-12
     assert res["same_uid"] and res["replicated_identical"]
+    # the consumers' sharded data flow (csrc/rom.cu with a communicator): DMDc with the control rows under the last
+    # rank's block, POD with the points split; against the single-process oracle
+    assert res["dmdc_b_err"] < 1e-8 and res["dmdc_eig_err"] < 1e-8 and res["dmdc_sigma_rel"] < 1e-10, res
+    assert res["pod_sin_modes"] < 1e-8 and res["pod_recon_err"] < 1e-8, res
 
 
 def test_bench_shard_partition_is_gpu_count_independent():
