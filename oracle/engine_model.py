@@ -297,3 +297,55 @@ def pod_sharded(x_local_cols: np.ndarray, n_modes: int, omega, allreduce=_identi
                             global_rows=float(thin.shape[0] if n_points_global is None else n_points_global))
     weights = allreduce(x_local_cols @ u)
     return u, weights, s
+
+
+# --------------------------------------------------------------------------------------
+# sketches wider than one 128-column panel (csrc/wide.cuh)
+# --------------------------------------------------------------------------------------
+def wide_plan(l: int):
+    """Panel geometry of Wide::plan: P panels of equal padded width w (multiple of 8, <= 128)."""
+    lc = (l + 7) // 8 * 8
+    p = (lc + 127) // 128
+    w = ((l + p - 1) // p + 7) // 8 * 8
+    return p, w
+
+
+def block_qr(x: np.ndarray, w: int, allreduce, global_rows: float, refill_a=None, complete=False):
+    """Wide::block_qr: block classical Gram-Schmidt with two projection sweeps against the finished panels, then the
+    adaptive CholeskyQR of the single-panel path (qr_fold) on the panel; Q is formed explicitly."""
+    q = np.array(x, dtype=np.float64, copy=True)
+    l = q.shape[1]
+    for j0 in range(0, l, w):
+        j1 = min(l, j0 + w)
+        for _rep in range(2):
+            for i0 in range(0, j0, w):
+                qi = q[:, i0:i0 + w]
+                q[:, j0:j1] -= qi @ allreduce(qi.T @ q[:, j0:j1])
+        xj, tf, _, _ = qr_fold(q[:, j0:j1].copy(), allreduce, global_rows, refill_a=refill_a, complete=complete)
+        q[:, j0:j1] = xj @ tf
+    return q
+
+
+def wide_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: int, omega: np.ndarray,
+              allreduce=_identity_allreduce, global_rows: float | None = None, schedule: int = 0):
+    """The panel path of the engine (l > 128) on one row shard of a thin matrix: same outputs as engine_rsvd."""
+    a = np.asarray(a_local, dtype=np.float64)
+    m, n = a.shape
+    l = min(n_rank + n_oversamples, n)
+    _p, w = wide_plan(l)
+    grows = float(m if global_rows is None else global_rows)
+    y = a @ omega
+    nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
+    for i in range(n_iter):
+        do_qr = schedule == 1 or i > 2
+        if do_qr:
+            y = block_qr(y, w, allreduce, grows, refill_a=a)
+        z = allreduce(a.T @ y)
+        y = a @ z if do_qr else (a @ z) * (1.0 / np.sqrt(nu2))
+        nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
+    q = block_qr(y, w, allreduce, grows, refill_a=a, complete=True)
+    zb = allreduce(a.T @ q)
+    qz = block_qr(zb, w, _identity_allreduce, float(n))
+    ur, sig, vr = jacobi_svd(qz.T @ zb)
+    k = n_rank
+    return q @ vr[:, :k], sig[:k].reshape(k, 1).copy(), (qz @ ur[:, :k]).T.copy()

@@ -235,3 +235,25 @@ def test_stats_oracle_passes_the_reference_tests():
     sens = fit.var_diag_evd_sensi()
     assert len(sens) == 3 and sens[1] > sens[0] and sens[1] > sens[2]
     assert np.max(np.abs(act.grad_est.grad_at([0.0, 1.0, 0.0]) - np.array([[0.2, 1.0, 0.0]]))) < 1e-1
+
+
+def test_engine_model_wide_panels_match_oracle():
+    """The column-panel algorithm the engine runs above 128 sketch columns (csrc/wide.cuh), as a numpy model:
+    panel geometry, block Gram-Schmidt + per-panel CholeskyQR, blockwise core -- against the oracle."""
+    from oracle import engine_model
+    assert engine_model.wide_plan(129) == (2, 72) and engine_model.wide_plan(160) == (2, 80)
+    assert engine_model.wide_plan(256) == (2, 128) and engine_model.wide_plan(270) == (3, 96)
+    for l in (129, 200, 257, 500, 1000, 2048):
+        p, w = engine_model.wide_plan(l)
+        assert w <= 128 and w % 8 == 0 and (p - 1) * w < l <= p * w
+    rng = np.random.default_rng(5)
+    m, n, k, q, pp = 900, 200, 150, 4, 10
+    u, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    a = (u * (10.0 * 0.985 ** np.arange(n))) @ v.T
+    omega = rng.standard_normal((n, k + pp))
+    u0, s0, vt0 = ref_rsvd.random_svd(a, k, q, pp, omega=omega)
+    u1, s1, vt1 = engine_model.wide_rsvd(a, k, q, pp, omega)
+    assert ref_rsvd.sigma_rel_err(s0, s1) < 1e-10
+    assert ref_rsvd.subspace_sine(u0, u1) < 1e-8 and ref_rsvd.subspace_sine(vt0.T, vt1.T) < 1e-8
+    assert np.max(np.abs(u1.T @ u1 - np.eye(k))) < 1e-12
