@@ -135,6 +135,23 @@ def main():
                           "weights_err": float(np.max(np.abs(w0 - xp @ mfull))),
                           "recon_err": float(np.max(np.abs(w0 @ mfull.T - ref.mode_weights @ ref.modes.T))),
                           "weights_replicated": float(max(np.max(np.abs(g[3] - w0)) for g in gathered))}
+    # covariance / correlation with the samples sharded over the ranks (means and Gram all-reduced)
+    from oracle import ref_stats
+    rng = np.random.default_rng(80)
+    xs = rng.standard_normal((7001, 24)) @ rng.standard_normal((24, 24)) + 30.0 * rng.standard_normal((1, 24))
+    per = (7001 + world - 1) // world
+    r0, r1 = rank * per, min(7001, (rank + 1) * per)
+    cov_l, mu_l, ev_l, vec_l = cb.cov(xs[r0:r1].copy(), "centered", evd=True, comm=comm, global_rows=7001)
+    cor_l = cb.pearson_corr(xs[r0:r1].copy(), comm=comm)          # global row count by all-reduce
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (np.asarray(cov_l), np.asarray(cor_l)))
+    if rank == 0:
+        c0 = ref_stats.mat_cov_centered(xs)
+        results["cov"] = {"cov_err": float(np.max(np.abs(cov_l - c0)) / np.max(np.abs(c0))),
+                          "cor_err": float(np.max(np.abs(cor_l - ref_stats.pearson_corr(xs)))),
+                          "mean_err": float(np.max(np.abs(mu_l.ravel() - xs.mean(axis=0)))),
+                          "eig_err": float(np.max(np.abs(ev_l.ravel() - np.linalg.eigvalsh(c0)[::-1])) / np.max(np.abs(c0))),
+                          "replicated": float(max(np.max(np.abs(g[0] - cov_l)) + np.max(np.abs(g[1] - cor_l)) for g in gathered))}
     # thin_q sharded
     rng = np.random.default_rng(5)
     a = rng.standard_normal((9000, 48))

@@ -52,6 +52,9 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
     pd_ = res["pod"]
     assert pd_["sin_modes"] < 1e-8 and pd_["orth"] < 1e-12 and pd_["weights_err"] < 1e-10 and pd_["recon_err"] < 1e-8, pd_
     assert pd_["weights_replicated"] == 0.0, pd_
+    cv = res["cov"]
+    assert cv["cov_err"] < 1e-11 and cv["cor_err"] < 1e-11 and cv["mean_err"] < 1e-11 and cv["eig_err"] < 1e-11, cv
+    assert cv["replicated"] == 0.0, cv
     st = res["streamed"]
     assert st["min_chunks"] >= 2 and st["sigma_rel"] < 1e-12 and st["u_diff"] < 1e-10 and st["vt_diff"] < 1e-10, st
     assert res["thin_q"]["orth"] < 1e-13 and res["thin_q"]["span"] < 1e-13
