@@ -225,6 +225,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
       CU_TRY(cudaMemcpy(&herr, o.comm->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
       if (herr != 0) { set_last_error("peer-memory exchange timed out: a rank never published its epoch"); return CORRLA_ERR_COMM; }
     }
+    if (!power_only && hflags[5] < 0) { set_last_error("the Jacobi kernel's cluster exchange timed out"); return CORRLA_ERR_CUDA; }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);     // each pass is wide_P launches when the sketch is cut into panels
     tm->qr_third_passes = c.n_robust; tm->qr_refills = c.n_refill; tm->jacobi_sweeps = hflags[4]; tm->live_columns = wide ? l : (hflags[1] ? hflags[1] : l);

@@ -23,7 +23,7 @@ constexpr int kCJThreads = 512;          // 64 groups of 8 lanes: every pair of 
 constexpr int kCJLanes = 8;
 constexpr int kCJMaxSweeps = 60;
 constexpr int kCJMaxCluster = 8;
-constexpr unsigned kCJSpinLimit = 1u << 26;   // bounded waits: a lost transaction becomes an error flag, not a hang
+constexpr unsigned kCJSpinLimit = 1u << 22;   // bounded waits: a lost transaction becomes an error flag, not a hang
 
 __device__ __forceinline__ uint32_t cj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cj_mapa(uint32_t addr, uint32_t rank) {
@@ -148,7 +148,8 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       const uint32_t bar = my_bar_a + (uint32_t)(par * 8);
       const unsigned phase = (par == 0 ? uses0 : uses1) & 1u;
       unsigned spins = 0;
-      while (!cj_mbar_try_wait(bar, phase)) { if (++spins > kCJSpinLimit) { failed = 1; break; } }
+      // after one timeout nothing is waited for any more: the kernel runs to its end (garbage out, info[1] = -1)
+      while (!failed && !cj_mbar_try_wait(bar, phase)) { if (++spins > kCJSpinLimit) failed = 1; }
       if (par == 0) ++uses0; else ++uses1;
       if (tid == 0) cj_mbar_expect(bar, next2_cols ? bytes_cols : bytes_pairs);
     } else {
