@@ -132,7 +132,11 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
         t1, _, _ = chol_inv(g, False, global_rows)
         x = x @ t1
         g = distributed_allreduce(x.T @ x)
-        tf, _, _ = chol_inv(g, False, global_rows)
+        e = g - np.eye(g.shape[0])
+        if np.sum(e * e) <= 4e-16:
+            tf = np.eye(g.shape[0]) - 0.5 * e          # first-order (Loewdin) factor instead of the second Cholesky
+        else:
+            tf, _, _ = chol_inv(g, False, global_rows)
         return x, tf, False, x.shape[1]
     lc = (x.shape[1] + 7) // 8 * 8
     sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), sketch_rng or np.random.default_rng(777)))
