@@ -22,7 +22,7 @@ from . import _ffi
 from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 
 __all__ = ["rsvd", "random_svd", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
-           "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings",
+           "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings", "release_buffers",
            "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights",
            "cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "active_ss", "active_ss_fit"]
 
@@ -56,6 +56,14 @@ class Context:
     def handle(self):
         return self._h
 
+    def release_buffers(self) -> int:
+        """Give the cached device buffers back to the driver (corrla_ctx_trim); returns the bytes released.  After a
+        host-path call on a large matrix the device copy of A, Y and the outputs otherwise stay allocated for the life
+        of the context, which starves e.g. torch's caching allocator in the same process."""
+        if getattr(self, "_h", None):
+            return int(_ffi.load().corrla_ctx_trim(self._h))
+        return 0
+
     def close(self):
         if getattr(self, "_h", None):
             _ffi.load().corrla_ctx_destroy(self._h)
@@ -70,6 +78,12 @@ class Context:
 
 _default_ctx: dict[int, Context] = {}
 _ctx_lock = threading.Lock()
+
+
+def release_buffers() -> int:
+    """Trim every hidden per-device default context (see Context.release_buffers)."""
+    with _ctx_lock:
+        return sum(c.release_buffers() for c in _default_ctx.values())
 
 
 def _context_for(device: int | None) -> Context:
@@ -235,12 +249,34 @@ def _ptr(x):
     return x.data_ptr() if _is_torch(x) else x.ctypes.data
 
 
+def _check_out(x, rows: int, cols: int, on_device: bool, name: str):
+    """A caller-provided output: float64, rows x cols, column-major and contiguous (the layout the C ABI writes),
+    living where the input lives.  Reusing outputs across calls keeps their pages faulted in (or pinned), which is
+    what makes the device->host copy of a multi-gigabyte U run at DMA speed."""
+    if _is_torch(x):
+        import torch
+        shape, strides = tuple(x.shape), tuple(x.stride())
+        ok = x.dtype == torch.float64 and x.is_cuda == on_device
+    elif isinstance(x, np.ndarray):
+        shape, strides = x.shape, tuple(st // 8 for st in x.strides)
+        ok = x.dtype == np.float64 and not on_device and x.flags.writeable
+    else:
+        raise TypeError(f"out[{name}] must be a numpy array or a torch tensor")
+    if len(shape) == 1 and cols == 1:
+        shape, strides = (shape[0], 1), (strides[0], shape[0])
+    colmajor = len(shape) == 2 and (strides[0] == 1 or shape[0] == 1) and (strides[1] == shape[0] or shape[1] == 1)
+    if not ok or tuple(shape) != (rows, cols) or not colmajor:
+        raise ValueError(f"out[{name}] must be a column-major float64 array of shape ({rows}, {cols}) "
+                         f"{'on the device' if on_device else 'on the host'}")
+    return x
+
+
 # --------------------------------------------------------------------------------------------
 # public API
 # --------------------------------------------------------------------------------------------
 def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, seed: int | None = None,
          schedule="reference", ctx: Context | None = None, comm: ShardComm | None = None,
-         global_rows: int | None = None, center: bool = False):
+         global_rows: int | None = None, center: bool = False, out=None):
     """Randomized SVD, drop-in for `corrla_rs.rsvd(a_mat, n_rank, n_iters, n_oversamples)`
     (src/lib_math_utils_py.rs:21-36 -> random_svd, src/lib_math_utils/random_svd.rs:63-110).
 
@@ -249,7 +285,9 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
     `seed` makes the on-device Philox generator reproducible (the reference is unseeded),
     `schedule="stabilised"` re-orthonormalises in every power iteration, `comm` runs row-sharded over
     several GPUs (a_mat is then this rank's rows of the thin matrix), `center=True` decomposes a_mat minus its
-    column means (center_mat_col, mat_utils.rs:482-502) without forming the centred copy when a_mat is tall."""
+    column means (center_mat_col, mat_utils.rs:482-502) without forming the centred copy when a_mat is tall,
+    `out=(u, s, vt)` writes into caller-owned column-major arrays (reused across calls: no fresh multi-gigabyte
+    allocation and no page faults in the device->host copy; pinned host arrays are copied by direct DMA)."""
     for name, v in (("n_rank", n_rank), ("n_iters", n_iters), ("n_oversamples", n_oversamples)):
         if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
             raise TypeError(f"{name} must be an int")
@@ -265,9 +303,15 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
                          schedule=schedule, comm=comm, global_rows=global_rows, stream=stream, device=device,
                          center=center)
     k = int(n_rank)
-    u = _colmajor_empty_like(a, nrows, max(k, 1))
-    vt = _colmajor_empty_like(a, max(k, 1), ncols)
-    s = _colmajor_empty_like(a, max(k, 1), 1)
+    if out is not None:
+        u, s, vt = out
+        _check_out(u, nrows, max(k, 1), a.on_device, "u")
+        _check_out(s, max(k, 1), 1, a.on_device, "s")
+        _check_out(vt, max(k, 1), ncols, a.on_device, "vt")
+    else:
+        u = _colmajor_empty_like(a, nrows, max(k, 1))
+        vt = _colmajor_empty_like(a, max(k, 1), ncols)
+        s = _colmajor_empty_like(a, max(k, 1), 1)
     t = Timings()
     st = lib.corrla_rsvd_f64(a.ptr, nrows, ncols, a.strides[0], a.strides[1], k, int(n_iters), int(n_oversamples),
                              C.byref(o), _ptr(u), _ptr(s), _ptr(vt), C.byref(t))

@@ -48,6 +48,8 @@ class Timings(C.Structure):
         ("pass_flops", C.c_double),
         ("p2p_exchanges", C.c_int),
         ("streamed_chunks", C.c_int),
+        ("jacobi_converged", C.c_int),
+        ("fused_small", C.c_int),
     ]
 
     def as_dict(self):
@@ -85,6 +87,7 @@ SYMBOLS = {
     "corrla_host_free": (None, [C.c_void_p, C.c_size_t]),
     "corrla_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "corrla_ctx_destroy": (None, [C.c_void_p]),
+    "corrla_ctx_trim": (C.c_size_t, [C.c_void_p]),
     "corrla_comm_unique_id": (C.c_int, [C.c_char_p]),
     "corrla_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "corrla_comm_destroy": (None, [C.c_void_p]),

@@ -153,6 +153,7 @@ int comm_init(const unsigned char id[128], int rank, int nranks, int device, cor
   if (r != ncclSuccess) { set_last_error("ncclCommInitRank: %s", a.GetErrorString(r)); return CORRLA_ERR_COMM; }
   corrla_comm* cc = new corrla_comm();
   cc->lib = a.lib; cc->nccl_comm = c; cc->rank = rank; cc->nranks = nranks; cc->device = device;
+  if (const char* e = getenv("CORRLA_B200_XCHG_TIMEOUT_CYCLES")) { const long long v = atoll(e); if (v > 0) cc->timeout_cycles = v; }
   setup_peer_memory(cc);      // best effort: on failure the communicator stays NCCL-only
   *out = cc;
   return CORRLA_OK;
@@ -200,5 +201,6 @@ bool corrla_comm::next_exchange(size_t count, corrla::PeerExchange* px) {
   px->block_counter = block_counter;
   px->err = err_flag;
   px->rank = rank; px->nranks = nranks; px->epoch = epoch;
+  px->timeout_cycles = timeout_cycles;
   return true;
 }

@@ -25,6 +25,7 @@ struct PeerExchange {
   int* err;                                            // local: set to 1 if a peer never showed up (timeout)
   int rank, nranks;
   unsigned long long epoch;
+  long long timeout_cycles;                            // bound of the acquire spin (clock64 ticks)
 };
 }  // namespace corrla
 
@@ -39,6 +40,7 @@ struct corrla_comm {
   unsigned int* block_counter = nullptr;
   int* err_flag = nullptr;
   unsigned long long epoch = 0;
+  long long timeout_cycles = 20000000000ll;            // ~10 s; CORRLA_B200_XCHG_TIMEOUT_CYCLES overrides (tests)
   // sum-all-reduce `count` doubles in place on `stream` with NCCL; returns 0 or a negative corrla_status
   int allreduce_f64(double* buf, size_t count, cudaStream_t stream);
   // next exchange descriptor (advances the epoch); false if the peer path is off or `count` does not fit

@@ -6,6 +6,31 @@
 
 namespace corrla_eng {
 
+// Every call ends here, with or without a timings struct: the device-side decision and failure flags come back through
+// pinned memory behind ONE stream synchronisation (the one host outputs need anyway before their copy), and a failure
+// reported by a kernel -- a peer that never published its epoch in the fused all-reduce, a lost DSMEM transaction in
+// the Jacobi cluster -- becomes a status code instead of silently wrong numbers.  The communicator's error flag is
+// cleared once reported, so the next call on it starts clean.
+static int finish_device(Scope& sc, Core& c, corrla_comm* comm, bool power_only, int* hflags /* 32 */) {
+  int* pin = sc.ctx->hflag + 16;                    // [16, 48): the run's flags, [48]: peer-exchange error
+  pin[32] = 0;
+  CU_TRY(cudaMemcpyAsync(pin, c.flags, 32 * sizeof(int), cudaMemcpyDeviceToHost, sc.st));
+  const bool p2p = comm != nullptr && comm->p2p && comm->err_flag != nullptr;
+  if (p2p) CU_TRY(cudaMemcpyAsync(pin + 32, comm->err_flag, sizeof(int), cudaMemcpyDeviceToHost, sc.st));
+  CU_TRY(cudaStreamSynchronize(sc.st));
+  memcpy(hflags, pin, 32 * sizeof(int));
+  if (p2p && pin[32] != 0) {
+    cudaMemsetAsync(comm->err_flag, 0, sizeof(int), sc.st);
+    set_last_error("peer-memory exchange timed out: a rank never published its epoch (results are invalid)");
+    return CORRLA_ERR_COMM;
+  }
+  if (!power_only && hflags[5] < 0) {
+    set_last_error("the Jacobi kernel's cluster exchange timed out (results are invalid)");
+    return CORRLA_ERR_CUDA;
+  }
+  return CORRLA_OK;
+}
+
 int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t cs, size_t n_rank, size_t n_iter,
               size_t n_oversamples, const corrla_rsvd_opts* opts_in, double* u, double* s, double* vt,
               corrla_timings* tm, bool power_only, double* q_out, bool u_optional, double* means_out) {
@@ -143,6 +168,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
 
   const bool out_dev = o.out_on_device != 0;
   double d2h_ms = 0.0;
+  int hflags[32] = {0};
   if (power_only) {
     // Q = Y * Tf, column-major m x l
     double* qd = out_dev ? q_out : static_cast<double*>(sc.ctx->get("Uout", (size_t)m * l * 8));
@@ -150,8 +176,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     if (wide) ST_TRY(wd.scatter_q(qd));
     else ST_TRY(c.mm(c.view_rows(c.Y, m), true, c.Tf, qd, 1, m, l));
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
+    ST_TRY(finish_device(sc, c, o.comm, true, hflags));
     if (!out_dev) {
-      CU_TRY(cudaStreamSynchronize(sc.st));
       pretouch.join();
       Timer t; CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, q_out, (size_t)m * l * 8, qd, (size_t)m * l * 8, (size_t)m * l * 8, 1)); d2h_ms = t.ms();
     }
@@ -195,8 +221,8 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     }
     if (out_dev) CU_TRY(cudaMemcpyAsync(s, sig_dev, (size_t)kk * 8, cudaMemcpyDeviceToDevice, sc.st));
     if (tm) { CU_TRY(cudaEventRecord(ev1, sc.st)); }
+    ST_TRY(finish_device(sc, c, o.comm, false, hflags));
     if (!out_dev) {
-      CU_TRY(cudaStreamSynchronize(sc.st));
       pretouch.join();
       Timer t;
       if (want_u) CU_TRY(copy_d2h_2d(sc.ctx->bounce, sc.st, u, (size_t)nrows * kk * 8, ud, (size_t)nrows * kk * 8, (size_t)nrows * kk * 8, 1));
@@ -206,9 +232,6 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     }
   }
   if (tm) {
-    int hflags[16];
-    CU_TRY(cudaMemcpyAsync(hflags, c.flags, sizeof(hflags), cudaMemcpyDeviceToHost, sc.st));
-    CU_TRY(cudaStreamSynchronize(sc.st));
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
     double pass_ms = 0.0;
@@ -220,18 +243,11 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
     tm->pass_launches = c.n_pass_events; tm->pass_ms = pass_ms; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l / (double)wide_P;
     tm->p2p_exchanges = c.p2p_exchanges;
     tm->streamed_chunks = n_chunks;
-    if (o.comm != nullptr && o.comm->p2p) {
-      int herr = 0;
-      CU_TRY(cudaMemcpy(&herr, o.comm->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-      if (herr != 0) { set_last_error("peer-memory exchange timed out: a rank never published its epoch"); return CORRLA_ERR_COMM; }
-    }
-    if (!power_only && hflags[5] < 0) { set_last_error("the Jacobi kernel's cluster exchange timed out"); return CORRLA_ERR_CUDA; }
     tm->device_ms = ms; tm->d2h_ms = d2h_ms; tm->gpu_launches = c.launches;
     tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);     // each pass is wide_P launches when the sketch is cut into panels
     tm->qr_third_passes = c.n_robust; tm->qr_refills = c.n_refill; tm->jacobi_sweeps = hflags[4]; tm->live_columns = wide ? l : (hflags[1] ? hflags[1] : l);
+    tm->jacobi_converged = power_only ? 1 : (hflags[5] > 0 ? 1 : 0);
     tm->total_ms = total.ms();
-  } else if (out_dev) {
-    // nothing to wait for: results are ordered on the caller's stream
   }
   return CORRLA_OK;
 }
@@ -399,6 +415,16 @@ int corrla_ctx_create(int device, corrla_ctx** out) {
   try { return ctx_create(device, out); } catch (...) { return CORRLA_ERR_ALLOC; }
 }
 void corrla_ctx_destroy(corrla_ctx* ctx) { delete ctx; }
+size_t corrla_ctx_trim(corrla_ctx* ctx) {
+  if (ctx == nullptr) return 0;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ctx->device);
+  const size_t freed = ctx->trim();
+  if (prev >= 0) cudaSetDevice(prev);
+  return freed;
+}
 
 int corrla_comm_unique_id(unsigned char id[128]) { return id ? comm_unique_id(id) : CORRLA_ERR_INVALID; }
 int corrla_comm_init(const unsigned char id[128], int rank, int nranks, int device, corrla_comm** out) {

@@ -33,7 +33,7 @@ struct corrla_ctx {
   std::map<std::string, Buf> pool;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   BounceBuffers bounce;
-  int* hflag = nullptr;              // pinned: device-side decisions read back by the host (two ints)
+  int* hflag = nullptr;              // pinned, 64 ints: [0,2) decisions read back inside a QR, [16,49) end-of-call flags
   std::vector<cudaEvent_t> events;   // reusable timing events
   cudaEvent_t event(size_t i) {
     while (events.size() <= i) {
@@ -54,6 +54,18 @@ struct corrla_ctx {
     if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     b.p = p; b.bytes = want;
     return p;
+  }
+  // Give the cached device buffers (and the pinned staging memory) back to the driver.  cudaFree waits for the device,
+  // so buffers still referenced by queued work are safe.  The next call re-allocates what it needs.
+  size_t trim() {
+    size_t freed = 0;
+    for (auto& kv : pool) if (kv.second.p) { cudaFree(kv.second.p); freed += kv.second.bytes; kv.second.p = nullptr; kv.second.bytes = 0; }
+    pool.clear();
+    if (pinned) { cudaFreeHost(pinned); freed += pinned_bytes; pinned = nullptr; pinned_bytes = 0; }
+    freed += 2 * bounce.bytes;
+    bounce.release();
+    cudaGetLastError();
+    return freed;
   }
   void* get_pinned(size_t bytes) {
     if (pinned_bytes >= bytes) return pinned;
@@ -119,7 +131,7 @@ inline int ctx_create(int device, corrla_ctx** out) {
   if (cudaGetDeviceProperties(&p, device) == cudaSuccess) c->num_sms = p.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&c->hflag), 64) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&c->hflag), 256) != cudaSuccess) {
     set_last_error("cudaStreamCreate / cudaMallocHost failed");
     delete c;
     return CORRLA_ERR_CUDA;

@@ -1,6 +1,7 @@
 #include "hostcopy.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -64,8 +65,14 @@ cudaError_t BounceBuffers::ensure(size_t want) {
   }
   bytes = want;
   in_flight[0] = in_flight[1] = false;
-  const unsigned hc = std::thread::hardware_concurrency();
-  threads = (int)std::max(1u, std::min(16u, hc ? hc : 4u));
+  // the staging copies share the host cores with the other ranks of the node: up to 16 threads, but no more than this
+  // process's share (torchrun exports LOCAL_WORLD_SIZE; CORRLA_B200_COPY_THREADS overrides)
+  unsigned hc = std::thread::hardware_concurrency();
+  if (hc == 0) hc = 4;
+  unsigned share = hc;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int lw = atoi(e); if (lw > 1) share = std::max(1u, hc / (unsigned)lw); }
+  threads = (int)std::max(1u, std::min(16u, share));
+  if (const char* e = getenv("CORRLA_B200_COPY_THREADS")) { const int v = atoi(e); if (v > 0) threads = std::min(v, 64); }
   return cudaSuccess;
 }
 

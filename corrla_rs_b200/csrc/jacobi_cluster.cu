@@ -60,8 +60,9 @@ template <bool kAsync>
 __global__ void __launch_bounds__(kCJThreads)
 jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                       double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, int transpose,
-                      int* info) {
+                      int* info, unsigned spin_limit) {
   cg::cluster_group cluster = cg::this_cluster();
+  __shared__ int fail_s;                   // any thread of this CTA gave up waiting for a peer's partial sums
   const int C = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) double smc[];
@@ -91,6 +92,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   const uint32_t bytes_cols = (uint32_t)(C * l * 8), bytes_pairs = (uint32_t)(C * h * 8);
   unsigned uses0 = 0, uses1 = 0;              // completed uses of the two mbarriers (phase parity)
   int failed = 0;
+  if (tid == 0) fail_s = 0;
   if (kAsync && tid == 0) {
     cj_mbar_init(my_bar_a, 1);
     cj_mbar_init(my_bar_a + 8, 1);
@@ -148,8 +150,9 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       const uint32_t bar = my_bar_a + (uint32_t)(par * 8);
       const unsigned phase = (par == 0 ? uses0 : uses1) & 1u;
       unsigned spins = 0;
+      if (spin_limit == 0) { failed = 1; fail_s = 1; }       // test hook: every wait "times out" at once
       // after one timeout nothing is waited for any more: the kernel runs to its end (garbage out, info[1] = -1)
-      while (!failed && !cj_mbar_try_wait(bar, phase)) { if (++spins > kCJSpinLimit) failed = 1; }
+      while (!failed && !cj_mbar_try_wait(bar, phase)) { if (++spins > spin_limit) { failed = 1; fail_s = 1; } }
       if (par == 0) ++uses0; else ++uses1;
       if (tid == 0) cj_mbar_expect(bar, next2_cols ? bytes_cols : bytes_pairs);
     } else {
@@ -280,7 +283,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
     out_ux[(int64_t)i * ldo + r] = sj > 0.0 ? Xs[(size_t)j * lr + il] / sj : 0.0;
     out_va[(int64_t)i * ldo + r] = Vs[(size_t)j * lr + il];
   }
-  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = failed ? -1 : converged; }
+  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = converged; }
   // exactly zero singular values leave zero columns in Ux: rank 0 completes them to an orthonormal basis (unit
   // vectors, two Gram-Schmidt passes), like the single-CTA kernel
   __syncthreads();
@@ -333,7 +336,10 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
     }
   }
   // nobody may exit while a peer can still write into its shared memory (the last pushes precede the last barrier)
+  __threadfence();
   cluster.sync();
+  // a timeout in ANY thread of ANY CTA of the cluster is reported (rank 0 wrote info[1] before the barrier above)
+  if (tid == 0 && fail_s != 0 && info != nullptr) atomicMin(info + 1, -1);
 }
 
 }  // namespace
@@ -367,7 +373,9 @@ cudaError_t jacobi_svd_cluster_launch(const double* W, int ldw, int l, double* s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info);
+  // CORRLA_B200_TEST_JACOBI_SPIN_LIMIT: test hook -- a tiny limit forces the bounded-wait timeout path
+  static const unsigned spin_limit = [] { const char* e = getenv("CORRLA_B200_TEST_JACOBI_SPIN_LIMIT"); return e == nullptr ? kCJSpinLimit : (unsigned)strtoul(e, nullptr, 10); }();
+  return cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info, spin_limit);
 }
 
 }  // namespace corrla

@@ -417,6 +417,7 @@ int cov_impl(const double* x, int64_t nrows, int64_t ncols, int64_t rs, int64_t 
   CU_TRY(cudaGetLastError());
 
   double *sig = nullptr, *Ur = nullptr;
+  int* jinfo = nullptr;
   if (evals != nullptr) {
     // symmetric positive semi-definite: the SVD is the eigendecomposition, already sorted in descending order
     sig = rb.zeros("cov_sig", (size_t)L16);
@@ -427,6 +428,7 @@ int cov_impl(const double* x, int64_t nrows, int64_t ncols, int64_t rs, int64_t 
     if (!sig || !Ur || !Vr || !js || !info) { set_last_error("device allocation failed (eigendecomposition)"); return CORRLA_ERR_ALLOC; }
     e = jacobi_svd_launch(S, ld, d, sig, Vr, Ur, L16, ld, js, info, st);
     if (e != cudaSuccess) { set_last_error("jacobi launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    jinfo = info;
   }
   if (out_dev) {
     if (means && kind != CORRLA_COV_GRAM) CU_TRY(cudaMemcpyAsync(means, mu, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
@@ -448,6 +450,11 @@ int cov_impl(const double* x, int64_t nrows, int64_t ncols, int64_t rs, int64_t 
     CU_TRY(cudaMemcpyAsync(out, out_dev_buf, (size_t)d * d * 8, cudaMemcpyDeviceToHost, st));
     if (means && kind != CORRLA_COV_GRAM) CU_TRY(cudaMemcpyAsync(means, mu, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+  }
+  if (jinfo != nullptr) {
+    int hj[2] = {0, 0};
+    CU_TRY(cudaMemcpy(hj, jinfo, sizeof(hj), cudaMemcpyDeviceToHost));
+    if (hj[1] < 0) { set_last_error("the Jacobi kernel's cluster exchange timed out (results are invalid)"); return CORRLA_ERR_CUDA; }
   }
   return CORRLA_OK;
 }
@@ -530,6 +537,7 @@ int active_ss_impl(const double* x, int64_t n, int64_t nfeat, int64_t x_rs, int6
   }
   CU_TRY(cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
+  if (hinfo[1] < 0) { set_last_error("the Jacobi kernel's cluster exchange timed out (results are invalid)"); return CORRLA_ERR_CUDA; }
   if (!out_dev && grad_mat != nullptr) ST_TRY(copy_out(ctx, st, grad_mat, g_cm, (size_t)n * d));
   if (n_deficient) *n_deficient = hinfo[2];
   return CORRLA_OK;

@@ -348,15 +348,46 @@ __device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
   return v;
 }
 
+// A rank that has seen a timeout publishes its later epochs with the poison bit set: every peer that reads such a flag
+// raises its own error flag (and stops waiting), so one lost rank makes the call fail on ALL ranks instead of leaving
+// some of them with a silently wrong sum.
+constexpr unsigned long long kEpochPoison = 1ull << 62;
+__device__ __forceinline__ unsigned long long publish_word(const PeerExchange& px) {
+  return px.epoch | ((*reinterpret_cast<volatile int*>(px.err) != 0) ? kEpochPoison : 0ull);
+}
+// wait (bounded) until rank `src` has published this epoch
+__device__ __forceinline__ void wait_for_peer(const PeerExchange& px, int src) {
+  const unsigned long long* f = px.my_flags + src;
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned long long v = ld_acquire_sys_u64(f);
+    if (v & kEpochPoison) { *px.err = 1; break; }
+    if (v >= px.epoch) break;
+    if (clock64() - t0 > px.timeout_cycles) { *px.err = 1; break; }   // default ~10 s: the peer never arrived
+    __nanosleep(64);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_exchange_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside, int64_t ld,
                        double* __restrict__ out, size_t x_count, size_t x_extra, const PeerExchange px,
                        const int* cond_flag) {
-  if (cond_flag != nullptr && *cond_flag == 0) return;
+  // A conditionally skipped exchange (every rank sees the same flag: it derives from all-reduced data) still takes part
+  // in the epoch protocol: block 0 publishes this epoch and waits for the peers', so that the half of the symmetric
+  // region used two epochs apart is never overwritten while a slower peer is still summing it.  No data moves.
+  const bool skip = (cond_flag != nullptr && *cond_flag == 0);
+  if (skip && blockIdx.x != 0) return;
   __shared__ int s_last;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   double* mine = px.mine;
+  if (skip) {
+    if (threadIdx.x < px.nranks) {
+      st_release_sys_u64(px.peer_flags[threadIdx.x] + px.rank, publish_word(px));
+      wait_for_peer(px, threadIdx.x);
+    }
+    return;
+  }
 
   // ---- phase 0: the whole ld-pitched block is (re)written, pads included, so nothing stale is ever summed
   {
@@ -393,19 +424,12 @@ reduce_exchange_kernel(const double* __restrict__ ws, int splits, int tilesM, in
   }
   __syncthreads();
   if (s_last) {
-    if (threadIdx.x < px.nranks) st_release_sys_u64(px.peer_flags[threadIdx.x] + px.rank, px.epoch);
+    if (threadIdx.x < px.nranks) st_release_sys_u64(px.peer_flags[threadIdx.x] + px.rank, publish_word(px));
     if (threadIdx.x == 0) *px.block_counter = 0u;               // ready for the next launch (stream ordered)
   }
 
   // ---- acquire: wait (bounded) for every rank's flag
-  if (threadIdx.x < px.nranks) {
-    const unsigned long long* f = px.my_flags + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(f) < px.epoch) {
-      if (clock64() - t0 > 20000000000ll) { *px.err = 1; break; }   // ~10 s: a peer never arrived
-      __nanosleep(64);
-    }
-  }
+  if (threadIdx.x < px.nranks) wait_for_peer(px, threadIdx.x);
   __syncthreads();
 
   // ---- phase 1
@@ -553,6 +577,17 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
   *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM * 8;   // 8 consumer warps per work item
 }
 
+// The blocks of reduce_exchange_kernel wait for the flag their own LAST block publishes, so all of them must be
+// resident at once: a cooperative launch guarantees that (or fails) even when other streams hold SMs.
+static cudaError_t launch_reduce_exchange(int blocks, cudaStream_t stream, const double* ws, int splits, int tilesM, int Lc,
+                                          int64_t Mside, int64_t ld, double* out, size_t x_count, size_t x_extra,
+                                          const PeerExchange& px, const int* cond_flag) {
+  void* args[] = {(void*)&ws, (void*)&splits, (void*)&tilesM, (void*)&Lc, (void*)&Mside, (void*)&ld, (void*)&out,
+                  (void*)&x_count, (void*)&x_extra, (void*)&px, (void*)&cond_flag};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(reduce_exchange_kernel), dim3((unsigned)blocks), dim3(256),
+                                     args, 0, stream);
+}
+
 cudaError_t sum_array_launch(const double* partials, int64_t n, double* slot, cudaStream_t stream) {
   sumsq_finalize_kernel<<<1, 1024, 0, stream>>>(partials, n, slot, nullptr);
   return cudaGetLastError();
@@ -566,7 +601,8 @@ cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, i
     if ((ld & 1) || x_count < (size_t)(Mside * ld) || (x_count & 1)) return cudaErrorInvalidValue;
     const int64_t work = std::max<int64_t>(Mside * (Lc / 2), (int64_t)(x_count / 2));
     const int blocks = (int)std::min<int64_t>((work + 255) / 256, num_sms);
-    reduce_exchange_kernel<<<blocks, 256, 0, stream>>>(ws, splits, tilesM, Lc, Mside, ld, out, x_count, 0, *px, cond_flag);
+    const cudaError_t ce = launch_reduce_exchange(blocks, stream, ws, splits, tilesM, Lc, Mside, ld, out, x_count, 0, *px, cond_flag);
+    if (ce != cudaSuccess) return ce;
   } else {
     const int64_t total = Mside * (Lc / 2);
     const int blocks = (int)((total + 255) / 256);
@@ -642,10 +678,10 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
     const int Lc = a.nblk * 8;
     const int64_t work = std::max<int64_t>(a.Mside * (Lc / 2), (int64_t)(c.x_count / 2));
     const int blocks = (int)std::min<int64_t>((work + 255) / 256, w.num_sms);     // all co-resident: blocks spin
-    reduce_exchange_kernel<<<blocks, 256, 0, stream>>>(a.splits > 1 ? w.ws : nullptr, a.splits, a.tilesM, Lc, a.Mside,
-                                                       c.out_rs, c.out, c.x_count, c.x_extra, *c.px, a.cond_flag);
+    const cudaError_t ce = launch_reduce_exchange(blocks, stream, a.splits > 1 ? w.ws : nullptr, a.splits, a.tilesM, Lc,
+                                                  a.Mside, c.out_rs, c.out, c.x_count, c.x_extra, *c.px, a.cond_flag);
     if (launches) ++*launches;
-    return cudaGetLastError();
+    return ce != cudaSuccess ? ce : cudaGetLastError();
   }
   if (a.splits > 1) {
     const int Lc = a.nblk * 8;

@@ -87,6 +87,9 @@ typedef struct corrla_timings {
   double pass_flops;       /* algorithmic flops of one such launch on this GPU: 2 * local_rows * ncols * l */
   int p2p_exchanges;       /* cross-rank sums done inside the reduction kernel over NVLink peer memory (0 => NCCL only) */
   int streamed_chunks;     /* host input: row chunks whose first product(s) ran behind the host->device copy (0 = copied first) */
+  int jacobi_converged;    /* 1: the Jacobi SVD of the l x l core met its tolerance; 0: it stopped at the sweep limit (a
+                              warning -- the factors are still orthogonal to working accuracy, sigma to ~1e-10) */
+  int fused_small;         /* 1: the whole call ran as ONE kernel with the matrix resident in shared memory (tiny inputs) */
 } corrla_timings;
 
 CORRLA_API void corrla_rsvd_opts_default(corrla_rsvd_opts* opts);
@@ -204,9 +207,13 @@ CORRLA_API int corrla_thin_q_f64(const double* a, int64_t nrows, int64_t ncols, 
 CORRLA_API void* corrla_host_alloc(size_t bytes);
 CORRLA_API void corrla_host_free(void* p, size_t bytes);
 
-/* contexts */
+/* contexts.  A context keeps its device buffers between calls (grow-only): after one host-path call on a large
+ * matrix the device copy of A, Y and the outputs stay allocated.  corrla_ctx_trim gives them back (returns the bytes
+ * released); the next call allocates again.  Failures reported by a kernel (peer-exchange or cluster-exchange
+ * timeouts) are returned by the call that hit them whether or not a timings struct was passed. */
 CORRLA_API int corrla_ctx_create(int device, corrla_ctx** out);
 CORRLA_API void corrla_ctx_destroy(corrla_ctx* ctx);
+CORRLA_API size_t corrla_ctx_trim(corrla_ctx* ctx);
 
 /* communicator (NCCL, loaded with dlopen("libnccl.so.2")); id is the 128-byte ncclUniqueId from rank 0 */
 CORRLA_API int corrla_comm_unique_id(unsigned char id[128]);

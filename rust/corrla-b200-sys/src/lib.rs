@@ -53,6 +53,8 @@ pub struct corrla_timings {
     pub pass_flops: f64,
     pub p2p_exchanges: c_int,
     pub streamed_chunks: c_int,
+    pub jacobi_converged: c_int,
+    pub fused_small: c_int,
 }
 
 extern "C" {
@@ -91,6 +93,7 @@ extern "C" {
     pub fn corrla_host_free(p: *mut c_void, bytes: usize);
     pub fn corrla_ctx_create(device: c_int, out: *mut *mut corrla_ctx) -> c_int;
     pub fn corrla_ctx_destroy(ctx: *mut corrla_ctx);
+    pub fn corrla_ctx_trim(ctx: *mut corrla_ctx) -> usize;
     pub fn corrla_comm_unique_id(id: *mut u8) -> c_int;
     pub fn corrla_comm_init(id: *const u8, rank: c_int, nranks: c_int, device: c_int, out: *mut *mut corrla_comm) -> c_int;
     pub fn corrla_comm_destroy(comm: *mut corrla_comm);

@@ -58,3 +58,24 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
     st = res["streamed"]
     assert st["min_chunks"] >= 2 and st["sigma_rel"] < 1e-12 and st["u_diff"] < 1e-10 and st["vt_diff"] < 1e-10, st
     assert res["thin_q"]["orth"] < 1e-13 and res["thin_q"]["span"] < 1e-13
+    rb = res["robust_stage"]
+    assert rb["robust_qr_stages"] >= 1, rb                       # the sketch-preconditioned stage really ran, sharded
+    assert rb["sigma_lead_rel"] < 1e-9 and rb["orth_u"] < 1e-12 and rb["orth_v"] < 1e-12, rb
+    assert rb["repeat_u_diff"] == 0.0 and rb["repeat_s_diff"] == 0.0, rb     # bit-reproducible call after call
+
+
+def test_peer_exchange_timeout_fails_on_every_rank(tmp_path):
+    """One rank is given a 1-cycle exchange timeout and its peer arrives late: the call must fail with CORRLA_ERR_COMM
+    on BOTH ranks (the poisoned epoch tells the late rank), with timings == NULL; a fresh communicator then works."""
+    if gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           str(ROOT / "tests" / "_nccl_timeout_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    res = json.loads((tmp_path / "timeout.json").read_text())
+    assert res["p2p"] is True
+    assert res["status"] == [-6, -6], res                        # CORRLA_ERR_COMM on both ranks
+    assert res["after_sigma_rel"] < 1e-10 and res["after_status"] == [0, 0], res
