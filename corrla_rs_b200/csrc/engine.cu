@@ -2,6 +2,7 @@
 // (random_svd.rs:15-110) as a sequence of skinny DMMA GEMMs, CholeskyQR and a Jacobi SVD, all on one
 // CUDA stream, with NCCL all-reduces of the small replicated factors when the rows are sharded.
 #include "engine_core.cuh"
+#include "fused_small.cuh"
 #include "wide.cuh"
 
 namespace corrla_eng {
@@ -29,6 +30,106 @@ static int finish_device(Scope& sc, Core& c, corrla_comm* comm, bool power_only,
     return CORRLA_ERR_CUDA;
   }
   return CORRLA_OK;
+}
+
+// Tiny problems: the whole call as ONE kernel with the matrix in shared memory (fused_small.cu).  Returns true when the
+// call was served (its status is in *status); false when the path does not apply or the kernel asked for the general one
+// (an exactly zero singular value among the first k: no direction to normalise).
+static bool try_fused_small(Scope& sc, const corrla_rsvd_opts& o, const double* a, int64_t m, int64_t n, int64_t trs, int64_t tcs,
+                            bool fat, int l, size_t k, size_t n_iter, int64_t nrows, int64_t ncols, double* u, double* s,
+                            double* vt, corrla_timings* tm, bool power_only, double* q_out, Timer& total, int* status) {
+  const char* env_off = getenv("CORRLA_B200_NO_FUSED_SMALL");      // read per call: tests compare the two paths in one process
+  const bool disabled = env_off != nullptr && env_off[0] == '1';
+  if (disabled || o.comm != nullptr || o.center != 0 || l > kFusedMaxL || m > 4096) return false;
+  const int kk = power_only ? l : (int)k;
+  if (fused_small_smem_bytes((int)m, (int)n, l, kk) == 0) return false;
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  auto fail = [&](int code) { *status = code; return true; };
+  auto cu_fail = [&](cudaError_t e, const char* what) {
+    set_last_error("%s failed: %s", what, cudaGetErrorString(e)); cudaGetLastError(); *status = CORRLA_ERR_CUDA; return true;
+  };
+  const bool in_dev = o.a_on_device != 0, out_dev = o.out_on_device != 0;
+  FusedSmallArgs fa{};
+  fa.m = (int)m; fa.n = (int)n; fa.l = l; fa.k = kk; fa.n_iter = (int)n_iter; fa.schedule = o.schedule; fa.power_only = power_only ? 1 : 0;
+  fa.seed = o.seed;
+  // staging: [A m*n | Omega n*l] in, [U m*k | V n*k | S k | Q m*l] out
+  const size_t in_elems = (in_dev ? 0 : (size_t)m * n) + ((o.omega != nullptr && !o.omega_on_device) ? (size_t)n * l : 0);
+  const size_t out_elems = out_dev ? 0 : (power_only ? (size_t)m * l : (size_t)(m + n + 1) * kk);
+  double* dstage = static_cast<double*>(ctx->get("fs_stage", (in_elems + out_elems + 8) * 8));
+  int* info = reinterpret_cast<int*>(ctx->get("fs_info", 64));
+  double* hstage = (in_elems + out_elems) ? static_cast<double*>(ctx->get_pinned((in_elems + out_elems + 8) * 8)) : nullptr;
+  if (!dstage || !info || ((in_elems + out_elems) && !hstage)) { set_last_error("allocation failed (fused small path)"); return fail(CORRLA_ERR_ALLOC); }
+  Timer th2d;
+  size_t off = 0;
+  if (in_dev) { fa.a = a; fa.a_rs = trs; fa.a_cs = tcs; }
+  else {
+    for (int64_t i = 0; i < m; ++i)
+      for (int64_t j = 0; j < n; ++j) hstage[off + i * n + j] = a[i * trs + j * tcs];
+    fa.a = dstage + off; fa.a_rs = n; fa.a_cs = 1;
+    off += (size_t)m * n;
+  }
+  if (o.omega != nullptr) {
+    if (o.omega_on_device) { fa.omega = o.omega; fa.om_rs = o.omega_rs; fa.om_cs = o.omega_cs; }
+    else {
+      for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < l; ++j) hstage[off + i * l + j] = o.omega[i * o.omega_rs + j * o.omega_cs];
+      fa.omega = dstage + off; fa.om_rs = l; fa.om_cs = 1;
+      off += (size_t)n * l;
+    }
+  }
+  if (off > 0) {
+    cudaError_t e = cudaMemcpyAsync(dstage, hstage, off * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cu_fail(e, "cudaMemcpyAsync (fused small input)");
+  }
+  const double h2d_ms = th2d.ms();
+  // outputs (:96-109): thin-U is m x k, thin-V is n x k; a fat input swaps their roles
+  double* out_base = dstage + in_elems;
+  double *sd = nullptr, *qd = nullptr;
+  if (power_only) { qd = out_dev ? q_out : out_base; fa.qout = qd; }
+  else {
+    double* udst = out_dev ? u : (u != nullptr ? out_base : nullptr);               // nrows x k column-major
+    double* vdst = out_dev ? vt : out_base + (size_t)nrows * kk;                    // k x ncols column-major
+    sd = out_dev ? s : out_base + (size_t)(nrows + ncols) * kk;
+    if (!fat) { fa.u = udst; fa.u_rs = 1; fa.u_cs = m; fa.v = vdst; fa.v_rs = kk; fa.v_cs = 1; }
+    else      { fa.u = vdst; fa.u_rs = kk; fa.u_cs = 1; fa.v = udst; fa.v_rs = 1; fa.v_cs = n; }
+    fa.s = sd;
+  }
+  fa.info = info;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (tm) { ev0 = ctx->event(0); ev1 = ctx->event(1); if (ev0 && ev1) cudaEventRecord(ev0, st); }
+  cudaError_t e = fused_small_launch(fa, st);
+  if (e != cudaSuccess) return cu_fail(e, "fused small kernel launch");
+  if (tm && ev0 && ev1) cudaEventRecord(ev1, st);
+  int* pin = ctx->hflag + 16;
+  e = cudaMemcpyAsync(pin, info, 4 * sizeof(int), cudaMemcpyDeviceToHost, st);
+  Timer td2h;
+  if (e == cudaSuccess && out_elems > 0) e = cudaMemcpyAsync(hstage + in_elems, out_base, out_elems * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cu_fail(e, "fused small kernel");
+  if (pin[2] != 0) return false;                               // general path (it owns the orthonormal completion)
+  if (!out_dev) {
+    const double* h = hstage + in_elems;
+    if (power_only) memcpy(q_out, h, (size_t)m * l * 8);
+    else {
+      if (u != nullptr) memcpy(u, h, (size_t)nrows * kk * 8);
+      memcpy(vt, h + (size_t)nrows * kk, (size_t)ncols * kk * 8);
+      memcpy(s, h + (size_t)(nrows + ncols) * kk, (size_t)kk * 8);
+    }
+  }
+  (void)qd;
+  if (tm) {
+    float ms = 0.f;
+    if (ev0 && ev1 && cudaEventElapsedTime(&ms, ev0, ev1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    tm->h2d_ms = h2d_ms; tm->device_ms = ms; tm->d2h_ms = out_dev ? 0.0 : td2h.ms(); tm->gpu_launches = 1;
+    tm->passes_over_a = 2 + 2 * (int)n_iter - (power_only ? 1 : 0);
+    tm->jacobi_sweeps = pin[0]; tm->jacobi_converged = power_only ? 1 : pin[1]; tm->live_columns = l;
+    tm->pass_launches = 0; tm->pass_ms = 0.0; tm->pass_flops = 2.0 * (double)m * (double)n * (double)l;
+    tm->fused_small = 1;
+    tm->total_ms = total.ms();
+  }
+  *status = CORRLA_OK;
+  return true;
 }
 
 int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t cs, size_t n_rank, size_t n_iter,
@@ -61,6 +162,11 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
 
   Scope sc;
   ST_TRY(open_scope(&o, &sc));
+  {
+    int fs_status = CORRLA_OK;
+    if (try_fused_small(sc, o, a, m, n, trs, tcs, fat, l, k, n_iter, nrows, ncols, u, s, vt, tm, power_only, q_out, total, &fs_status))
+      return fs_status;
+  }
   Core c;
   c.ctx = sc.ctx; c.st = sc.st; c.comm = o.comm;
   c.refill_seed = o.seed ^ 0x9e3779b97f4a7c15ull;

@@ -79,6 +79,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(recv + (size_t)2 * C * l);   // [2] mbarriers (kAsync)
   int* rnk = reinterpret_cast<int*>(bars + 2);
   int* anyflag = rnk + l;
+  int* bigflag = anyflag + 1;               // some pair of this sweep was further than kJacobiNearCos from orthogonal
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int LP = kCJLanes;
   const int grp = tid / LP, sub = tid % LP, ngrp = nt / LP;
@@ -92,7 +93,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   const uint32_t bytes_cols = (uint32_t)(C * l * 8), bytes_pairs = (uint32_t)(C * h * 8);
   unsigned uses0 = 0, uses1 = 0;              // completed uses of the two mbarriers (phase parity)
   int failed = 0;
-  if (tid == 0) fail_s = 0;
+  if (tid == 0) fail_s = (spin_limit == 0) ? 1 : 0;      // spin_limit == 0: test hook, the failure path from the start
   if (kAsync && tid == 0) {
     cj_mbar_init(my_bar_a, 1);
     cj_mbar_init(my_bar_a + 8, 1);
@@ -150,11 +151,11 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       const uint32_t bar = my_bar_a + (uint32_t)(par * 8);
       const unsigned phase = (par == 0 ? uses0 : uses1) & 1u;
       unsigned spins = 0;
-      if (spin_limit == 0) { failed = 1; fail_s = 1; }       // test hook: every wait "times out" at once
-      // after one timeout nothing is waited for any more: the kernel runs to its end (garbage out, info[1] = -1)
+      // after a timeout the CTA leaves the iteration at its next barrier (fail_s is read CTA-uniformly there), stops
+      // pushing and re-arming, and meets its peers -- who time out in turn -- at the final cluster barrier: info[1] = -1
       while (!failed && !cj_mbar_try_wait(bar, phase)) { if (++spins > spin_limit) { failed = 1; fail_s = 1; } }
       if (par == 0) ++uses0; else ++uses1;
-      if (tid == 0) cj_mbar_expect(bar, next2_cols ? bytes_cols : bytes_pairs);
+      if (tid == 0 && !failed) cj_mbar_expect(bar, next2_cols ? bytes_cols : bytes_pairs);
     } else {
       cluster.sync();
     }
@@ -175,13 +176,14 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       for (int src = 0; src < C; ++src) a += recv[((size_t)par * C + src) * l + j];
       nrm[j] = take_sqrt ? sqrt(a) : a;
     }
-    if (tid == 0) *anyflag = 0;
+    if (tid == 0) { *anyflag = 0; *bigflag = 0; }
     __syncthreads();
     par ^= 1;
   };
 
   for (; sweeps < kCJMaxSweeps; ++sweeps) {
     column_sums(false);                                   // exact norms once per sweep
+    if (fail_s) break;                                    // CTA-uniform: read behind the barrier that ends column_sums
     for (int r = 0; r < N1; ++r) {
       for (int pi = grp; pi < h; pi += ngrp) {
         int p, q;
@@ -229,11 +231,13 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
             cs_sn = make_double2(cs, sn);
             nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c;
             *anyflag = 1;
+            if (c * c > kJacobiNearCos2 * a * b) *bigflag = 1;
           }
         }
         rot[pi] = cs_sn;
       }
       __syncthreads();
+      if (fail_s) break;                                  // CTA-uniform (set only between the previous barrier and this one)
       for (int pi = grp; pi < h; pi += ngrp) {
         const double2 cs_sn = rot[pi];
         const double cs = cs_sn.x, sn = cs_sn.y;
@@ -258,13 +262,23 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
       __syncthreads();
       par ^= 1;
     }
-    const int any = *anyflag;                             // identical on every CTA: same sums, same decisions
-    if (!any) { converged = 1; ++sweeps; break; }
+    if (fail_s) break;
+    // Quadratic convergence: when every rotation of a sweep was by less than kJacobiNearCos, what is left afterwards is
+    // of the order of its square, below the tolerance -- no further sweep is needed just to confirm it.
+    const int any = *anyflag, big = *bigflag;             // identical on every CTA: same sums, same decisions
+    if (!any || !big) { converged = 1; ++sweeps; break; }
   }
 
   // singular values (column norms over all rows), descending ranks, outputs for my rows
-  column_sums(true);
-  for (int j = tid; j < l; j += nt) {
+  if (!fail_s) column_sums(true);
+  // Agree on the outcome across the cluster: a CTA that gave up stops pushing, so its peers time out in turn, but the
+  // barriers below must be taken by everybody or by nobody.  After this barrier every CTA reads every fail flag.
+  __syncthreads();
+  cluster.sync();
+  int anyfail = 0;
+  for (int r = 0; r < C; ++r) anyfail |= *cluster.map_shared_rank(&fail_s, r);
+  const bool dead = anyfail != 0;                         // cluster-uniform: nothing is written, info[1] = -1
+  for (int j = tid; j < l && !dead; j += nt) {
     const double sj = nrm[j];
     int r = 0;
     for (int i = 0; i < l; ++i) r += (nrm[i] > sj || (nrm[i] == sj && i < j)) ? 1 : 0;
@@ -274,7 +288,7 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   __syncthreads();
   double* out_ux = transpose ? Vr_out : Ur_out;
   double* out_va = transpose ? Ur_out : Vr_out;
-  for (int idx = tid; idx < l * lr; idx += nt) {
+  for (int idx = tid; idx < l * lr && !dead; idx += nt) {
     const int j = idx / lr, il = idx - j * lr;
     const int i = r0 + il;
     if (i >= r1) continue;
@@ -283,13 +297,14 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
     out_ux[(int64_t)i * ldo + r] = sj > 0.0 ? Xs[(size_t)j * lr + il] / sj : 0.0;
     out_va[(int64_t)i * ldo + r] = Vs[(size_t)j * lr + il];
   }
-  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = converged; }
+  if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = dead ? -1 : converged; }
   // exactly zero singular values leave zero columns in Ux: rank 0 completes them to an orthonormal basis (unit
   // vectors, two Gram-Schmidt passes), like the single-CTA kernel
   __syncthreads();
   int nz = 0;
   for (int j = 0; j < l; ++j) nz += (nrm[j] > 0.0) ? 1 : 0;          // replicated data: uniform everywhere
-  if (nz < l) {
+  // (after a failed exchange the replicated data may differ between CTAs: `dead` is what keeps this branch uniform)
+  if (nz < l && !dead) {
     __threadfence();
     cluster.sync();                                                   // all slabs of Ux are in global memory
     if (rank == 0) {
@@ -338,8 +353,6 @@ jacobi_cluster_kernel(const double* __restrict__ Win, int ldw, int l, double* __
   // nobody may exit while a peer can still write into its shared memory (the last pushes precede the last barrier)
   __threadfence();
   cluster.sync();
-  // a timeout in ANY thread of ANY CTA of the cluster is reported (rank 0 wrote info[1] before the barrier above)
-  if (tid == 0 && fail_s != 0 && info != nullptr) atomicMin(info + 1, -1);
 }
 
 }  // namespace

@@ -203,6 +203,75 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
   }
 }
 
+// reduce_outer, narrow sketch (8x1 warp layout) and a short output side: see GemmArgs::kgroups.  Warp w works on box
+// w % a_boxes and takes the k4-steps S = 4*chunk + s with S % kgroups == w / a_boxes.  Every group's partial tile
+// (16*a_boxes rows) goes to the split-K workspace as if it were one more split.
+template <int JW, bool FULL>
+__device__ __forceinline__ void consumer_loop_mc_kgroups(const GemmArgs& p, unsigned char* smem, unsigned char* smemB,
+                                                         uint32_t sBar, int warp, int lane, int jn) {
+  const int g = lane >> 2, t = lane & 3;
+  const int kg = p.kgroups, bv = p.a_boxes;
+  const int box = warp % bv, kgrp = warp / bv;
+  int a_xo[2][4];
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    const int mc = colperm(g, par);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int kr = 4 * s + t;
+      a_xo[par][s] = kr * 128 + ((((mc >> 1) ^ (kr & 7))) << 4) + ((mc & 1) << 3);
+    }
+  }
+  const int a_base = box * 2048;
+  const int b_off = t * p.ldb * 8 + g * 8;
+  const int b_step = 4 * p.ldb * 8;
+  const int W = p.tilesM * p.splits;
+  const int Lc = p.nblk * 8;
+  uint32_t stage = 0, phase = 0;
+  double acc[2][JW][2];
+  for (int w = blockIdx.x; w < W; w += gridDim.x) {
+    const int split = w / p.tilesM;
+    const int64_t c0 = (int64_t)split * p.chunks_per_split;
+    const int64_t c1 = min(c0 + p.chunks_per_split, p.chunks_total);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int64_t c = c0; c < c1; ++c) {
+      mbar_wait(sBar + 8 * stage, phase);
+      const unsigned char* a = smem + stage * kAStageBytes + a_base;
+      const unsigned char* b = smemB + stage * p.b_stage_bytes + b_off;
+      const int sbase = (int)((c & 1) << 2);              // kgroups <= 8: only the parity of the chunk matters
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (((sbase + s) & (kg - 1)) == kgrp) {
+          const double a0 = *reinterpret_cast<const double*>(a + a_xo[0][s]);
+          const double a1 = *reinterpret_cast<const double*>(a + a_xo[1][s]);
+#pragma unroll
+          for (int j = 0; j < JW; ++j)
+            if (FULL || j < jn) {
+              const double bf = *reinterpret_cast<const double*>(b + s * b_step + j * 64);
+              dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, bf);
+              dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, bf);
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sBar + 8 * (8 + stage));
+      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+    }
+    double* wsp = p.ws + ((int64_t)w * kg + kgrp) * (16 * bv) * Lc;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int tr = 16 * box + colperm(g, i);
+#pragma unroll
+      for (int j = 0; j < JW; ++j)
+        if (FULL || j < jn)
+          *reinterpret_cast<double2*>(wsp + (int64_t)tr * Lc + 8 * j + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
 template <bool KC, int WM, int WN, int MI, int JW, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
@@ -241,7 +310,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
     tma_prefetch_desc(&tmA);
     const int W = p.tilesM * p.splits;
     uint32_t stage = 0, phase = 0;
-    const uint32_t tx = kAStageBytes + p.b_stage_bytes;
+    const uint32_t tx = (KC ? kAStageBytes : (uint32_t)p.a_boxes * 2048u) + p.b_stage_bytes;
     for (int w = blockIdx.x; w < W; w += gridDim.x) {
       const int split = w / p.tilesM, tile = w - split * p.tilesM;
       const int64_t c0 = (int64_t)split * p.chunks_per_split;
@@ -257,7 +326,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
           tma_load_2d(dstA, &tmA, k0, m0, full);
         } else {
 #pragma unroll
-          for (int b = 0; b < 8; ++b) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
+          for (int b = 0; b < 8; ++b)
+            if (b < p.a_boxes) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
         }
         bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -269,13 +339,18 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
   // ------------------------------ DMMA consumer warpgroups ------------------------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
   const int jn = min(JW, (p.nblk - (warp / WM) + WN - 1) / WN);   // valid n-block slots of this warp (nb = wn + WN*j)
+  if (!KC && MODE == 0 && WN == 1 && p.kgroups > 1) {
+    if (jn == JW) consumer_loop_mc_kgroups<JW, true>(p, smem, smemB, sBar, warp, lane, jn);
+    else consumer_loop_mc_kgroups<JW, false>(p, smem, smemB, sBar, warp, lane, jn);
+    return;
+  }
   if (jn == JW) consumer_loop<KC, WM, WN, MI, JW, true, MODE>(p, smem, smemB, sBar, red, warp, lane, jn);
   else consumer_loop<KC, WM, WN, MI, JW, false, MODE>(p, smem, smemB, sBar, red, warp, lane, jn);
 }
 
 // out(r, c) = alpha * sum_s ws[s][tile(r)][r % 128][c]; one thread per column pair.
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside,
+splitk_reduce_kernel(const double* __restrict__ ws, int splits, int64_t split_stride, int Lc, int64_t Mside,
                      double* __restrict__ out, int64_t out_rs, int64_t out_cs, int ncols_out,
                      const double* alpha_sumsq, const double* col_bias, double* sumsq_partials, const int* cond_flag,
                      int accumulate) {
@@ -290,9 +365,7 @@ splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int 
   if (idx < total) {
     const int64_t r = idx / half;
     const int col = (int)(idx - r * half) * 2;
-    const int64_t tile = r / kTileM, rt = r - tile * kTileM;
-    const int64_t split_stride = (int64_t)tilesM * kTileM * Lc;
-    const double* src = ws + (tile * kTileM + rt) * Lc + col;
+    const double* src = ws + r * Lc + col;                 // (tile*128 + row in tile) * Lc == r * Lc
     double s0 = 0.0, s1 = 0.0;
     for (int s = 0; s < splits; ++s) {
       const double2 v = *reinterpret_cast<const double2*>(src + s * split_stride);
@@ -317,6 +390,61 @@ splitk_reduce_kernel(const double* __restrict__ ws, int splits, int tilesM, int 
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+      sumsq_partials[blockIdx.x] = tot;
+    }
+  }
+}
+
+// The same reduction for MANY splits and a small output (a 64 x 24 product of a million-row contraction leaves ~600
+// partial tiles): one warp per output column pair, lane s adds splits s, s + 32, ... and a fixed butterfly adds the
+// lanes -- still one summation order, so still bit-reproducible, but ~20 dependent loads deep instead of ~600.
+__global__ void __launch_bounds__(256)
+splitk_reduce_warp_kernel(const double* __restrict__ ws, int splits, int64_t split_stride, int Lc, int64_t Mside,
+                          double* __restrict__ out, int64_t out_rs, int64_t out_cs, int ncols_out,
+                          const double* alpha_sumsq, const double* col_bias, double* sumsq_partials, const int* cond_flag,
+                          int accumulate) {
+  if (cond_flag != nullptr && *cond_flag == 0) return;
+  __shared__ double red[8];
+  const int half = Lc >> 1;
+  const int64_t total = Mside * half;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t idx = (int64_t)blockIdx.x * 8 + wib;
+  double alpha = 1.0;
+  if (alpha_sumsq != nullptr) alpha = rsqrt(*alpha_sumsq);
+  double ss = 0.0;
+  if (idx < total) {
+    const int64_t r = idx / half;
+    const int col = (int)(idx - r * half) * 2;
+    const double* src = ws + r * Lc + col;
+    double s0 = 0.0, s1 = 0.0;
+    for (int s = lane; s < splits; s += 32) {
+      const double2 v = *reinterpret_cast<const double2*>(src + s * split_stride);
+      s0 += v.x; s1 += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      if (col_bias != nullptr) { s0 -= col_bias[col]; s1 -= col_bias[col + 1]; }
+      s0 *= alpha; s1 *= alpha;
+      double* o = out + r * out_rs + (int64_t)col * out_cs;
+      if (accumulate) {
+        if (col < ncols_out) s0 += o[0];
+        if (col + 1 < ncols_out) s1 += o[out_cs];
+      }
+      ss = s0 * s0 + s1 * s1;
+      if (col < ncols_out) o[0] = s0;
+      if (col + 1 < ncols_out) o[out_cs] = s1;
+    }
+  }
+  if (sumsq_partials != nullptr) {
+    if (lane == 0) red[wib] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < 8; ++i) tot += red[i];
       sumsq_partials[blockIdx.x] = tot;
     }
   }
@@ -369,7 +497,7 @@ __device__ __forceinline__ void wait_for_peer(const PeerExchange& px, int src) {
 }
 
 __global__ void __launch_bounds__(256)
-reduce_exchange_kernel(const double* __restrict__ ws, int splits, int tilesM, int Lc, int64_t Mside, int64_t ld,
+reduce_exchange_kernel(const double* __restrict__ ws, int splits, int64_t split_stride, int Lc, int64_t Mside, int64_t ld,
                        double* __restrict__ out, size_t x_count, size_t x_extra, const PeerExchange px,
                        const int* cond_flag) {
   // A conditionally skipped exchange (every rank sees the same flag: it derives from all-reduced data) still takes part
@@ -393,7 +521,6 @@ reduce_exchange_kernel(const double* __restrict__ ws, int splits, int tilesM, in
   {
     const int64_t ld2 = ld >> 1;
     const int64_t body_pairs = (int64_t)((x_count - x_extra) >> 1);
-    const int64_t split_stride = (int64_t)tilesM * kTileM * Lc;
     for (int64_t idx = tid; idx < body_pairs; idx += nthreads) {
       const int64_t r = idx / ld2;
       const int col = (int)(idx - r * ld2) * 2;
@@ -575,14 +702,20 @@ void gemm_plan(int64_t Mside, int64_t K, int nblk, int num_sms, int force_splits
   *ws_bytes = best_s > 1 ? (size_t)tilesM * best_s * tile_bytes : 0;
   const int64_t reduce_blocks = (Mside * (Lc / 2) + 255) / 256;
   *n_partials = best_s > 1 ? (size_t)reduce_blocks : (size_t)tilesM * 8;   // 8 consumer warps per work item
+  if (Mside <= 64 && nblk <= 7) {
+    // a reduce_outer product this short runs in k-groups (GemmArgs::kgroups): it always goes through the workspace,
+    // and its reduction uses one warp per output pair
+    *ws_bytes = std::max(*ws_bytes, (size_t)best_s * tile_bytes);
+    *n_partials = std::max(*n_partials, (size_t)((Mside * (Lc / 2) + 7) / 8));
+  }
 }
 
 // The blocks of reduce_exchange_kernel wait for the flag their own LAST block publishes, so all of them must be
 // resident at once: a cooperative launch guarantees that (or fails) even when other streams hold SMs.
-static cudaError_t launch_reduce_exchange(int blocks, cudaStream_t stream, const double* ws, int splits, int tilesM, int Lc,
-                                          int64_t Mside, int64_t ld, double* out, size_t x_count, size_t x_extra,
+static cudaError_t launch_reduce_exchange(int blocks, cudaStream_t stream, const double* ws, int splits, int64_t split_stride,
+                                          int Lc, int64_t Mside, int64_t ld, double* out, size_t x_count, size_t x_extra,
                                           const PeerExchange& px, const int* cond_flag) {
-  void* args[] = {(void*)&ws, (void*)&splits, (void*)&tilesM, (void*)&Lc, (void*)&Mside, (void*)&ld, (void*)&out,
+  void* args[] = {(void*)&ws, (void*)&splits, (void*)&split_stride, (void*)&Lc, (void*)&Mside, (void*)&ld, (void*)&out,
                   (void*)&x_count, (void*)&x_extra, (void*)&px, (void*)&cond_flag};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(reduce_exchange_kernel), dim3((unsigned)blocks), dim3(256),
                                      args, 0, stream);
@@ -601,13 +734,14 @@ cudaError_t reduce_partials_launch(const double* ws, int splits, int rows_pad, i
     if ((ld & 1) || x_count < (size_t)(Mside * ld) || (x_count & 1)) return cudaErrorInvalidValue;
     const int64_t work = std::max<int64_t>(Mside * (Lc / 2), (int64_t)(x_count / 2));
     const int blocks = (int)std::min<int64_t>((work + 255) / 256, num_sms);
-    const cudaError_t ce = launch_reduce_exchange(blocks, stream, ws, splits, tilesM, Lc, Mside, ld, out, x_count, 0, *px, cond_flag);
+    const cudaError_t ce = launch_reduce_exchange(blocks, stream, ws, splits, (int64_t)tilesM * kTileM * Lc, Lc, Mside, ld, out,
+                                                  x_count, 0, *px, cond_flag);
     if (ce != cudaSuccess) return ce;
   } else {
     const int64_t total = Mside * (Lc / 2);
     const int blocks = (int)((total + 255) / 256);
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, tilesM, Lc, Mside, out, ld, 1, Lc, nullptr, nullptr,
-                                                     nullptr, cond_flag, 0);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, (int64_t)tilesM * kTileM * Lc, Lc, Mside, out, ld, 1, Lc,
+                                                     nullptr, nullptr, nullptr, cond_flag, 0);
   }
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -631,10 +765,23 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   gemm_plan(a.Mside, a.K, a.nblk, w.num_sms, c.force_splits, &a.tilesM, &a.splits, &a.chunks_per_split, &ws_bytes,
             &n_partials);
   a.chunks_total = std::max<int64_t>(1, (a.K + kChunkK - 1) / kChunkK);
+  // short output side of a reduce_outer product with the narrow warp layout: k-groups (GemmArgs::kgroups)
+  a.kgroups = 1; a.a_boxes = 8;
+  if (!kc && a.nblk <= 7 && a.tilesM == 1) {
+    a.a_boxes = (int)std::min<int64_t>(8, (a.Mside + 15) / 16);
+    if (a.Mside <= 64) {
+      a.a_boxes = a.Mside <= 16 ? 1 : (a.Mside <= 32 ? 2 : 4);
+      a.kgroups = 8 / a.a_boxes;
+      ws_bytes = (size_t)a.splits * kTileM * a.nblk * 8 * sizeof(double);      // splits * kgroups * (16 * a_boxes) rows
+      n_partials = (size_t)((a.Mside * (a.nblk * 4) + 7) / 8);                 // blocks of the warp-parallel reduction
+    }
+  }
+  const int splits_eff = a.splits * a.kgroups;                                 // partial tiles per output tile
+  const int64_t split_stride = (a.kgroups > 1) ? (int64_t)16 * a.a_boxes * a.nblk * 8 : (int64_t)a.tilesM * kTileM * a.nblk * 8;
   if (ws_bytes > w.ws_bytes) return cudaErrorMemoryAllocation;
   if (c.sumsq_slot != nullptr && n_partials > w.n_partials) return cudaErrorMemoryAllocation;
   a.ws = w.ws;
-  a.sumsq_partials = (c.sumsq_slot != nullptr && a.splits == 1) ? w.sumsq_partials : nullptr;
+  a.sumsq_partials = (c.sumsq_slot != nullptr && splits_eff == 1) ? w.sumsq_partials : nullptr;
 
   const bool fused_x = (c.px != nullptr);
   if (fused_x) {
@@ -642,7 +789,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
         c.x_count < (size_t)(a.Mside * c.out_rs) + c.x_extra || ((c.x_count - c.x_extra) & 1) || (c.out_rs & 1) ||
         c.ncols_out != c.nblk * 8)
       return cudaErrorInvalidValue;
-    if (a.splits == 1) a.out = c.px->mine;        // the GEMM epilogue writes my half of the symmetric region directly
+    if (splits_eff == 1) a.out = c.px->mine;      // the GEMM epilogue writes my half of the symmetric region directly
   }
   a.b_stage_bytes = (uint32_t)(kChunkK * c.ldb * 8);
   const size_t per_stage = kAStageBytes + a.b_stage_bytes;
@@ -678,18 +825,27 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
     const int Lc = a.nblk * 8;
     const int64_t work = std::max<int64_t>(a.Mside * (Lc / 2), (int64_t)(c.x_count / 2));
     const int blocks = (int)std::min<int64_t>((work + 255) / 256, w.num_sms);     // all co-resident: blocks spin
-    const cudaError_t ce = launch_reduce_exchange(blocks, stream, a.splits > 1 ? w.ws : nullptr, a.splits, a.tilesM, Lc,
+    const cudaError_t ce = launch_reduce_exchange(blocks, stream, splits_eff > 1 ? w.ws : nullptr, splits_eff, split_stride, Lc,
                                                   a.Mside, c.out_rs, c.out, c.x_count, c.x_extra, *c.px, a.cond_flag);
     if (launches) ++*launches;
     return ce != cudaSuccess ? ce : cudaGetLastError();
   }
-  if (a.splits > 1) {
+  if (splits_eff > 1) {
     const int Lc = a.nblk * 8;
     const int64_t total = a.Mside * (Lc / 2);
-    const int blocks = (int)((total + 255) / 256);
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(w.ws, a.splits, a.tilesM, Lc, a.Mside, a.out, a.out_rs, a.out_cs,
-                                                     a.ncols_out, a.alpha_sumsq, a.col_bias,
-                                                     c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag, a.accumulate);
+    int blocks;
+    if (splits_eff >= 64 && total <= 65536) {
+      blocks = (int)((total + 7) / 8);                                          // one warp per output pair
+      splitk_reduce_warp_kernel<<<blocks, 256, 0, stream>>>(w.ws, splits_eff, split_stride, Lc, a.Mside, a.out, a.out_rs,
+                                                            a.out_cs, a.ncols_out, a.alpha_sumsq, a.col_bias,
+                                                            c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag,
+                                                            a.accumulate);
+    } else {
+      blocks = (int)((total + 255) / 256);
+      splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(w.ws, splits_eff, split_stride, Lc, a.Mside, a.out, a.out_rs, a.out_cs,
+                                                       a.ncols_out, a.alpha_sumsq, a.col_bias,
+                                                       c.sumsq_slot ? w.sumsq_partials : nullptr, a.cond_flag, a.accumulate);
+    }
     if (launches) ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -47,6 +47,11 @@ struct GemmArgs {
   // when non-null and *cond_flag == 0 the kernel does nothing
   const int* cond_flag;
   int stages; uint32_t b_stage_bytes;
+  // reduce_outer with a SHORT output side (Mside <= 64, narrow sketches): only `a_boxes` of the eight 16-column TMA
+  // boxes of a stage hold rows of the output; the 8 consumer warps then form kgroups = 8 / a_boxes groups that share
+  // the boxes and split the k4-steps between them (each group writes its own partial tile, summed by the split-K
+  // reduction), so no DMMA is spent on zero padding and all four FP64 pipes of the SM stay busy.  1 / 8 otherwise.
+  int kgroups, a_boxes;
 };
 
 // Host-side description of one product; see gemm_launch().

@@ -1,4 +1,5 @@
 #include "small_kernels.cuh"
+#include "philox.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -8,41 +9,20 @@ namespace corrla {
 
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) + Box-Muller
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-
 __global__ void __launch_bounds__(256)
 philox_normal_kernel(double* __restrict__ out, int64_t rows, int cols, int64_t ld, uint64_t seed) {
   const int64_t total = rows * cols;
   const int64_t npairs = (total + 1) >> 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += stride) {
-    uint32_t c[4] = {(uint32_t)(p & 0xffffffffu), (uint32_t)((uint64_t)p >> 32), 0u, 0u};
-    philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
-    const uint64_t x = ((uint64_t)c[0] | ((uint64_t)c[1] << 32)) >> 11;
-    const uint64_t y = ((uint64_t)c[2] | ((uint64_t)c[3] << 32)) >> 11;
-    const double u1 = ((double)x + 1.0) * 0x1.0p-53;   // (0, 1]
-    const double u2 = (double)y * 0x1.0p-53;           // [0, 1)
-    const double r = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
+    double z0, z1;
+    philox_normal_pair(p, seed, &z0, &z1);
     const int64_t e0 = 2 * p, e1 = e0 + 1;
     const int64_t i0 = e0 / cols;
-    out[i0 * ld + (e0 - i0 * cols)] = r * cs;
+    out[i0 * ld + (e0 - i0 * cols)] = z0;
     if (e1 < total) {
       const int64_t i1 = e1 / cols;
-      out[i1 * ld + (e1 - i1 * cols)] = r * sn;
+      out[i1 * ld + (e1 - i1 * cols)] = z1;
     }
   }
 }
@@ -270,6 +250,7 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
   }
   int* rnk = reinterpret_cast<int*>(nrm + l);
   int* anyflag = rnk + l;
+  int* bigflag = anyflag + 1;
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int LP = kJacobiLanes;
   const int grp = tid / LP, sub = tid % LP, ngrp = nt / LP;
@@ -320,7 +301,7 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
       for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
       if (sub == 0) nrm[j] = a;
     }
-    if (tid == 0) *anyflag = 0;
+    if (tid == 0) { *anyflag = 0; *bigflag = 0; }
     __syncthreads();
     for (int r = 0; r < N1; ++r) {
       for (int pi = grp; pi < h; pi += ngrp) {
@@ -362,14 +343,14 @@ jacobi_svd_kernel(const double* __restrict__ Win, int ldw, int l, double* __rest
             vp[i] = make_double2(cs * vx.x - sn * vy.x, cs * vx.y - sn * vy.y);
             vq[i] = make_double2(sn * vx.x + cs * vy.x, sn * vx.y + cs * vy.y);
           }
-          if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; *anyflag = 1; }
+          if (sub == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; *anyflag = 1; if (c * c > kJacobiNearCos2 * a * b) *bigflag = 1; }
         }
       }
       __syncthreads();
     }
-    const int any = *anyflag;
+    const int any = *anyflag, big = *bigflag;
     __syncthreads();
-    if (!any) { converged = 1; ++sweeps; break; }
+    if (!any || !big) { converged = 1; ++sweeps; break; }   // see kJacobiNearCos2
   }
 
   // singular values, ranks (descending), outputs

@@ -33,6 +33,10 @@ cudaError_t chol_inv_launch(const double* G, int ldg, int l, double* T, int Lrow
 cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const int* deadmask, uint64_t seed,
                                uint64_t stream_id, const int* cond_flag, cudaStream_t s);
 
+// Columns whose cosine is below this in EVERY pair of a sweep are orthogonal to ~cos^2 <= 1e-15 after that sweep (the
+// cyclic Jacobi method converges quadratically), so the sweep that would only confirm convergence is not run.
+constexpr double kJacobiNearCos2 = 9e-16;      // (3e-8)^2
+
 // One-sided (Hestenes) Jacobi SVD of the l x l matrix W (row-major, pitch ldw): W = Ur * diag(sigma) * Vr^T,
 // sigma sorted descending.  Ur, Vr are written as Lrows x ldo row-major, zero padded (ready to be a GEMM B
 // operand).  scratch: 2*l*(l|1) doubles of global memory, used when the matrices do not fit in shared memory.

@@ -115,6 +115,15 @@ int main(int argc, char** argv) {
   fails += check(129, 1030, 1030, 18, true, 2, w);
   fails += check(17, 5, 6, 5, true, 0, w);
   fails += check(17, 5, 6, 5, false, 0, w);
+  // short output side of a reduce_outer product with a narrow sketch: the k-group path (1, 2 and 4 boxes), few and many
+  // splits (serial and warp-parallel reduction), ragged K
+  fails += check(100000, 64, 64, 18, false, 0, w);
+  fails += check(100003, 24, 24, 18, false, 0, w);
+  fails += check(50000, 12, 12, 10, false, 0, w);
+  fails += check(3000, 40, 40, 30, false, 3, w);
+  fails += check(77, 64, 64, 18, false, 0, w);
+  fails += check(5000, 16, 16, 50, false, 0, w);
+  fails += check(70000, 100, 100, 18, false, 0, w);
   printf("correctness failures: %d\n", fails);
   if (argc > 1) {
     speed(1 << 20, 1024, 110, true, w, "Y=A*X row-major (K2)");
@@ -127,6 +136,8 @@ int main(int argc, char** argv) {
     speed(1 << 20, 112, 110, true, w, "apply Y*T");
     speed(1 << 20, 64, 18, true, w, "C5 Y=A*X");
     speed(1 << 20, 64, 18, false, w, "C5 Z=A^T*Y");
+    speed(1 << 20, 24, 18, false, w, "C5 Gram Y^T*Y");
+    speed(1 << 20, 24, 18, true, w, "C5 apply Y*T");
   }
   return fails ? 1 : 0;
 }
