@@ -12,6 +12,7 @@
 #include "fused_small.cuh"
 
 #include <cfloat>
+#include <cstdio>
 
 #include "philox.cuh"
 #include "ptx.cuh"
@@ -46,7 +47,7 @@ __host__ __device__ inline FsLayout fs_layout(int m, int n, int l, int k) {
   L.oV = o; o += (size_t)L.l8 * L.lp;
   L.oM1 = o; o += (size_t)L.l8 * L.pl;
   L.oM2 = o; o += (size_t)L.l8 * L.pl;
-  L.oTau = o; o += (size_t)L.l8;
+  L.oTau = o; o += 2 * (size_t)L.l8;      // hv0 | hden of the Householder reflectors
   L.oNrm = o; o += (size_t)L.l8;
   L.oSig = o; o += (size_t)L.l8;
   L.oRed = o; o += 64;
@@ -107,33 +108,39 @@ __device__ __forceinline__ double fs_warp_sum(double v) {
   return v;
 }
 
-// Householder reflector of column j of Y (rows j..rows-1), LAPACK dlarfg, by ONE warp: v (v[j] = 1 implied) is left
-// below the diagonal, beta = R[j][j] on it, tau[j] in shared memory (0 => H = I).
-__device__ __forceinline__ void fs_make_reflector(double* x, int j, int rows, double* tau, int lane) {
+// Householder reflectors, kept UNSCALED so that no square root and no division sits on the critical path of a column
+// step (an FP64 sqrt or divide is a ~500-cycle dependent chain here, and a step has nothing to hide it behind):
+//   x = column j below row j,  alpha = x[j],  s = alpha^2 + |x[j+1:]|^2,  nrm = sqrt(s) = s * rsqrt(s),
+//   beta = -sign(alpha) nrm = R[j][j],   v = x - beta e_j  (v[j] = alpha - beta kept in hv0[j], v[j+1:] = x[j+1:] in place),
+//   H = I - v v^T / (nrm (nrm + |alpha|))      since v^T v = 2 nrm (nrm + |alpha|).
+// make_reflector leaves beta on the diagonal, v0 in hv0[j] and the DENOMINATOR nrm (nrm + |alpha|) in hden[j] (0 => H = I);
+// whoever applies the reflector takes the reciprocal itself, which overlaps with its own dot-product reduction.
+__device__ __forceinline__ void fs_make_reflector(double* x, int j, int rows, double* hv0, double* hden, int lane) {
   double sig = 0.0;
   for (int r = j + 1 + lane; r < rows; r += 32) sig += x[r] * x[r];
   sig = fs_warp_sum(sig);
   const double alpha = x[j];
-  double tj = 0.0;
+  double v0 = 0.0, den = 0.0;
   __syncwarp();
   if (sig > 0.0) {
-    const double nrm = sqrt(alpha * alpha + sig);
+    const double s2 = fma(alpha, alpha, sig);
+    const double nrm = s2 * rsqrt(s2);
     const double beta = (alpha >= 0.0) ? -nrm : nrm;
-    tj = (beta - alpha) / beta;
-    const double scal = 1.0 / (alpha - beta);
-    for (int r = j + 1 + lane; r < rows; r += 32) x[r] *= scal;
+    v0 = alpha - beta;
+    den = nrm * (nrm + fabs(alpha));
     if (lane == 0) x[j] = beta;
   }
-  if (lane == 0) tau[j] = tj;
+  if (lane == 0) { hv0[j] = v0; hden[j] = den; }
 }
 
-// x <- H_j x for one column x (one warp); v = column j of the factored matrix
-__device__ __forceinline__ void fs_apply_reflector(const double* v, double tj, double* x, int j, int rows, int lane) {
-  double dot = (lane == 0) ? x[j] : 0.0;
+// x <- H_j x for one column x (one warp); v = column j of the factored matrix (rows > j), v0 / den as above
+__device__ __forceinline__ void fs_apply_reflector(const double* v, double v0, double den, double* x, int j, int rows, int lane) {
+  const double tau = 1.0 / den;                        // independent of the reduction below: the two chains overlap
+  double dot = (lane == 0) ? v0 * x[j] : 0.0;
   for (int r = j + 1 + lane; r < rows; r += 32) dot += v[r] * x[r];
   dot = fs_warp_sum(dot);
-  const double w = tj * dot;
-  if (lane == 0) x[j] -= w;
+  const double w = tau * dot;
+  if (lane == 0) x[j] -= w * v0;
   for (int r = j + 1 + lane; r < rows; r += 32) x[r] -= w * v[r];
   __syncwarp();
 }
@@ -141,17 +148,17 @@ __device__ __forceinline__ void fs_apply_reflector(const double* v, double tj, d
 // In-place Householder QR of the rows x l column-major matrix F (pitch p): reflectors below the diagonal, R on and above
 // it.  Column c belongs to warp c % 16; the owner of column j+1 builds the next reflector right after updating that
 // column, so a step costs one CTA barrier.  Replaces faer's qr() at random_svd.rs:38 / :57 for this path.
-__device__ void fs_house_factor(double* F, int p, int rows, int l, double* tau, int warp, int lane) {
-  if (warp == 0) fs_make_reflector(F, 0, rows, tau, lane);
+__device__ void fs_house_factor(double* F, int p, int rows, int l, double* hv0, double* hden, int warp, int lane) {
+  if (warp == 0) fs_make_reflector(F, 0, rows, hv0, hden, lane);
   __syncthreads();
   for (int j = 0; j < l; ++j) {
-    const double tj = tau[j];
+    const double v0 = hv0[j], den = hden[j];
     const double* v = F + j * p;
     int c = j + 1 + ((warp - (j + 1)) % kFsWarps + kFsWarps) % kFsWarps;      // first column > j owned by this warp
     for (; c < l; c += kFsWarps) {
       double* x = F + c * p;
-      if (tj != 0.0) fs_apply_reflector(v, tj, x, j, rows, lane);
-      if (c == j + 1) fs_make_reflector(x, j + 1, rows, tau, lane);
+      if (den != 0.0) fs_apply_reflector(v, v0, den, x, j, rows, lane);
+      if (c == j + 1) fs_make_reflector(x, j + 1, rows, hv0, hden, lane);
     }
     __syncthreads();
   }
@@ -159,53 +166,51 @@ __device__ void fs_house_factor(double* F, int p, int rows, int l, double* tau, 
 
 // Explicit thin Q (rows x l, column-major into Qb, pitch p) from the factored matrix: column c is H_0 ... H_c e_c.
 // Columns are independent: no barrier until the end.  (compute_thin_q, random_svd.rs:38 / :57)
-__device__ void fs_house_form_q(const double* F, int p, int rows, int l, const double* tau, double* Qb, int warp, int lane) {
+__device__ void fs_house_form_q(const double* F, int p, int rows, int l, const double* hv0, const double* hden, double* Qb,
+                                int warp, int lane) {
   for (int c = warp; c < l; c += kFsWarps) {
     double* qc = Qb + c * p;
     for (int r = lane; r < rows; r += 32) qc[r] = (r == c) ? 1.0 : 0.0;
     __syncwarp();
     for (int j = c; j >= 0; --j) {
-      const double tj = tau[j];
-      if (tj != 0.0) fs_apply_reflector(F + j * p, tj, qc, j, rows, lane);
+      const double den = hden[j];
+      if (den != 0.0) fs_apply_reflector(F + j * p, hv0[j], den, qc, j, rows, lane);
     }
   }
   __syncthreads();
 }
 
-// One-sided Jacobi SVD of the l x l matrix held as columns X[j*lp + i] (l <= 32), by ONE warp: two lanes per column pair
-// (each owns half of the rows), round-robin tournament, no barrier beyond __syncwarp.  V accumulates the rotations.
-// Stands in for faer's svd() at random_svd.rs:89 on the QR-preconditioned core.
-__device__ void fs_jacobi_warp(double* X, double* V, int lp, int l, double* nrm, int lane, int* sweeps_out, int* conv_out) {
+// One-sided Jacobi SVD of the l x l matrix held as columns X[j*lp + i] (l <= 32) by the whole CTA: one WARP per column
+// pair of the round-robin tournament (at most 16 pairs), lane i owns row i of both columns, so a round is four shared
+// loads, one butterfly, the rotation parameters (the two dependent rsqrt are what a round costs) and four stores, then
+// one CTA barrier.  V accumulates the rotations.  Stands in for faer's svd() at random_svd.rs:89 on the
+// QR-preconditioned core.  flags: two ints of shared memory.
+__device__ void fs_jacobi_cta(double* X, double* V, int lp, int l, double* nrm, int* flags, int warp, int lane,
+                              int* sweeps_out, int* conv_out) {
   const int h = (l + 1) >> 1, N1 = 2 * h - 1;
-  const int pi = lane >> 1, half = lane & 1;
-  const int rsplit = (l + 1) >> 1;
-  const int r0 = half ? rsplit : 0, r1 = half ? l : rsplit;
   const double tol2 = (double)l * DBL_EPSILON * DBL_EPSILON;
+  const bool row = lane < l;
   int sweeps = 0, converged = 0;
   for (; sweeps < kFsMaxSweeps; ++sweeps) {
-    for (int j = lane; j < l; j += 32) {
-      double a = 0.0;
-      for (int i = 0; i < l; ++i) { const double x = X[j * lp + i]; a += x * x; }
-      nrm[j] = a;
+    for (int j = warp; j < l; j += kFsWarps) {            // exact squared norms once per sweep
+      const double x = row ? X[j * lp + lane] : 0.0;
+      const double a = fs_warp_sum(x * x);
+      if (lane == 0) nrm[j] = a;
     }
-    __syncwarp();
-    int any = 0, big = 0;
+    if (warp == 0 && lane == 0) { flags[0] = 0; flags[1] = 0; }
+    __syncthreads();
     for (int r = 0; r < N1; ++r) {
       int p = 0, q = l;
-      if (pi < h) {
-        if (pi == 0) { p = N1; q = r; }
-        else { p = r + pi; if (p >= N1) p -= N1; q = r - pi; if (q < 0) q += N1; }
+      if (warp < h) {
+        if (warp == 0) { p = N1; q = r; }
+        else { p = r + warp; if (p >= N1) p -= N1; q = r - warp; if (q < 0) q += N1; }
         if (p > q) { const int tmp = p; p = q; q = tmp; }
       }
-      const bool valid = (pi < h) && (q < l);
-      double c = 0.0;
-      if (valid) {
-        const double* xp = X + p * lp;
-        const double* xq = X + q * lp;
-        for (int i = r0; i < r1; ++i) c += xp[i] * xq[i];
-      }
-      c += __shfl_xor_sync(0xffffffffu, c, 1);          // both lanes of the pair now hold the same bits
-      if (valid) {
+      if (warp < h && q < l) {                            // warp-uniform
+        double* xp = X + p * lp + lane;
+        double* xq = X + q * lp + lane;
+        const double x = row ? *xp : 0.0, y = row ? *xq : 0.0;
+        const double c = fs_warp_sum(x * y);              // identical bits in every lane
         const double a = nrm[p], b = nrm[q];
         if (c * c > tol2 * a * b) {
           // division-free rotation (see jacobi_svd_kernel): cos(2 theta) = |d| r, r = 1/sqrt(d^2 + 4c^2)
@@ -216,25 +221,26 @@ __device__ void fs_jacobi_warp(double* X, double* V, int lp, int l, double* nrm,
           const double cr = fabs(c) * rr;
           const double cs = uu * icu;
           const double sn = copysign(cr * icu, d * c);
-          const double t = copysign(cr * icu * icu, d * c);
-          double* xp = X + p * lp;
-          double* xq = X + q * lp;
-          double* vp = V + p * lp;
-          double* vq = V + q * lp;
-          for (int i = r0; i < r1; ++i) {
-            const double x = xp[i], y = xq[i];
-            xp[i] = cs * x - sn * y; xq[i] = sn * x + cs * y;
-            const double vx = vp[i], vy = vq[i];
-            vp[i] = cs * vx - sn * vy; vq[i] = sn * vx + cs * vy;
+          if (row) {
+            double* vp = V + p * lp + lane;
+            double* vq = V + q * lp + lane;
+            const double vx = *vp, vy = *vq;
+            *xp = cs * x - sn * y; *xq = sn * x + cs * y;
+            *vp = cs * vx - sn * vy; *vq = sn * vx + cs * vy;
           }
-          if (half == 0) { nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c; }
-          any = 1;
-          if (c * c > kJacobiNearCos2 * a * b) big = 1;
+          if (lane == 0) {
+            const double t = copysign(cr * icu * icu, d * c);
+            nrm[p] = fmax(a - t * c, 0.0); nrm[q] = b + t * c;
+            flags[0] = 1;
+            if (c * c > kJacobiNearCos2 * a * b) flags[1] = 1;
+          }
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (!__any_sync(0xffffffffu, any) || !__any_sync(0xffffffffu, big)) { converged = 1; ++sweeps; break; }   // kJacobiNearCos2
+    const int any = flags[0], big = flags[1];
+    __syncthreads();                                      // everybody has read the flags before the next sweep clears them
+    if (!any || !big) { converged = 1; ++sweeps; break; }   // kJacobiNearCos2: no sweep just to confirm convergence
   }
   *sweeps_out = sweeps;
   *conv_out = converged;
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(kFsThreads, 1)
 fused_small_rsvd_kernel(const FusedSmallArgs p) {
   extern __shared__ __align__(16) double fsm[];
   __shared__ int s_perm[kFusedMaxL];
-  __shared__ int s_info[4];
+  __shared__ int s_info[8];
   const int m = p.m, n = p.n, l = p.l, k = p.k;
   const FsLayout L = fs_layout(m, n, l, k);
   double* sA = fsm + L.oA;
@@ -256,12 +262,17 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
   double* sV = fsm + L.oV;
   double* sM1 = fsm + L.oM1;
   double* sM2 = fsm + L.oM2;
-  double* tau = fsm + L.oTau;
+  double* hv0 = fsm + L.oTau;
+  double* hden = hv0 + L.l8;
   double* nrm = fsm + L.oNrm;
   double* sig = fsm + L.oSig;
   double* red = fsm + L.oRed;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbl = L.l8 / 8;
+  // phase clocks (thread 0, debug only): 0 stage-in, 1 A*Z, 2 A^T*Y, 3 thin Q, 4 normalise, 5 QR of B^T, 6 Jacobi, 7 outputs
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+  auto tick = [&](int ph) { if (p.debug && tid == 0) { const long long now = clock64(); tph[ph] += now - tlast; tlast = now; } };
 
   // ---- stage A (any strides) and Omega; everything else starts as zeros (the pads must stay zero)
   for (size_t idx = tid; idx < L.total - L.oY; idx += kFsThreads) fsm[L.oY + idx] = 0.0;
@@ -287,19 +298,23 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     }
   }
   __syncthreads();
+  tick(0);
 
   auto mm_AZ = [&](const double* Zin, double* Yout) {          // Y = A * Z            random_svd.rs:31, :47-51
     fs_gemm(nbl, sA, L.pa, 1, Zin, 1, L.pn, Yout, 1, L.pm, L.m8 / 8, L.n8 / 4, L.m8, L.l8, 1.0, warp, lane);
     __syncthreads();
+    tick(1);
   };
   auto mm_AtY = [&](const double* Yin, double* Zout) {         // Z = A^T * Y          :42-46, :80
     fs_gemm(nbl, sA, 1, L.pa, Yin, 1, L.pm, Zout, 1, L.pn, L.n8 / 8, L.m8 / 4, L.n8, L.l8, 1.0, warp, lane);
     __syncthreads();
+    tick(2);
   };
   auto thin_q = [&](double*& F, double*& Other, int pitch, int rows) {    // F <- thin Q of F (buffers swap)
-    fs_house_factor(F, pitch, rows, l, tau, warp, lane);
-    fs_house_form_q(F, pitch, rows, l, tau, Other, warp, lane);
+    fs_house_factor(F, pitch, rows, l, hv0, hden, warp, lane);
+    fs_house_form_q(F, pitch, rows, l, hv0, hden, Other, warp, lane);
     double* tmp = F; F = Other; Other = tmp;
+    tick(3);
   };
 
   mm_AZ(sZ, sY);
@@ -322,6 +337,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     const double sc = red[32];
     for (int idx = tid; idx < l * L.pm; idx += kFsThreads) sY[idx] *= sc;
     __syncthreads();
+    tick(4);
   }
   thin_q(sY, sY2, L.pm, m);                                    // :57   sY = Q
 
@@ -336,16 +352,17 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
 
   mm_AtY(sY, sZ);                                              // :80   sZ = B^T (n x l)
   // SVD of B (:89): B^T = Qz R (Householder), one-sided Jacobi on R^T, then U = Q * Vr, V = Qz * Ur
-  fs_house_factor(sZ, L.pn, n, l, tau, warp, lane);
+  fs_house_factor(sZ, L.pn, n, l, hv0, hden, warp, lane);
   for (int idx = tid; idx < l * l; idx += kFsThreads) {
     const int j = idx / l, i = idx - j * l;                    // X column j = row j of R:  X[j][i] = R[j][i], i >= j
     sX[j * L.lp + i] = (i >= j) ? sZ[i * L.pn + j] : 0.0;
     sV[j * L.lp + i] = (i == j) ? 1.0 : 0.0;
   }
-  fs_house_form_q(sZ, L.pn, n, l, tau, sZ2, warp, lane);       // sZ2 = Qz   (ends with a barrier)
+  fs_house_form_q(sZ, L.pn, n, l, hv0, hden, sZ2, warp, lane);       // sZ2 = Qz   (ends with a barrier)
+  tick(5);
+  int sweeps, conv;
+  fs_jacobi_cta(sX, sV, L.lp, l, nrm, s_info + 4, warp, lane, &sweeps, &conv);
   if (warp == 0) {
-    int sweeps, conv;
-    fs_jacobi_warp(sX, sV, L.lp, l, nrm, lane, &sweeps, &conv);
     // singular values, descending order
     for (int j = lane; j < l; j += 32) {
       double a = 0.0;
@@ -366,6 +383,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     if (lane == 0) { s_info[0] = sweeps; s_info[1] = conv; s_info[2] = bad ? 1 : 0; }
   }
   __syncthreads();
+  tick(6);
   // R^T * Vacc = Ux * Sigma:  R = Vacc Sigma Ux^T  =>  Ur = Vacc, Vr = Ux;  M1 = Vr[:, :k] (for U), M2 = Ur[:, :k] (for V)
   for (int idx = tid; idx < k * l; idx += kFsThreads) {
     const int c = idx / l, i = idx - c * l;
@@ -382,6 +400,11 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     fs_gemm(nbk, sZ2, 1, L.pn, sM2, 1, L.pl, p.v, p.v_rs, p.v_cs, L.n8 / 8, L.l8 / 4, n, k, 1.0, warp, lane);
   for (int c = tid; c < k; c += kFsThreads) p.s[c] = sig[c];
   if (tid == 0) { p.info[0] = s_info[0]; p.info[1] = s_info[1]; p.info[2] = s_info[2]; }
+  tick(7);
+  if (p.debug && tid == 0)
+    printf("fused_small m=%d n=%d l=%d q=%d cycles: stage-in %lld | A*Z %lld | A^T*Y %lld | thin-Q %lld | normalise %lld | QR(B^T) %lld | "
+           "Jacobi %lld (%d sweeps) | outputs %lld\n", m, n, l, p.n_iter, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6],
+           s_info[0], tph[7]);
 }
 
 }  // namespace

@@ -1,7 +1,9 @@
 #include "gradients.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace corrla {
 
@@ -15,6 +17,8 @@ constexpr int kCT = 128;          // candidates per tile: 4 per lane
 constexpr int kDC = 32;           // features per staged chunk
 constexpr int kKnnThreads = 256;
 constexpr int kQPitch = kQT + 1, kCPitch = kCT + 1;   // odd pitches: the transposing stores are conflict free
+constexpr int kKnnSlots = 5;      // list entries per lane in the insertion routine: lists of up to 160 entries
+constexpr int kKnnMargin = 16;    // extra shortlist entries of the GEMM-form search (see knn_gemm_kernel)
 
 // Warp-collective insertion of the lanes flagged in `mask` (lowest lane first = increasing candidate index) into the
 // sorted list (ld, li) of length k; returns the new k-th best distance.  Equal distances keep the lower index first.
@@ -30,16 +34,16 @@ __device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dis
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       const int pos = cnt;
-      double td[4]; int ti[4];
+      double td[kKnnSlots]; int ti[kKnnSlots];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kKnnSlots; ++j) {
         const int p = lane + 32 * j;
         td[j] = 0.0; ti[j] = 0;
         if (p > pos && p < k) { td[j] = ld[p - 1]; ti[j] = li[p - 1]; }
       }
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kKnnSlots; ++j) {
         const int p = lane + 32 * j;
         if (p > pos && p < k) { ld[p] = td[j]; li[p] = ti[j]; }
         else if (p == pos && p < k) { ld[p] = dv; li[p] = iv; }
@@ -54,7 +58,8 @@ __device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dis
 }
 
 __global__ void __launch_bounds__(kKnnThreads)
-knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, int* __restrict__ idx_out) {
+knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, int* __restrict__ idx_out,
+           const int* __restrict__ qlist, const int* __restrict__ qcount) {
   extern __shared__ __align__(16) double smk[];
   double* Qs = smk;                                   // [kDC][kQPitch]  query chunk, feature-major
   double* Cs = Qs + kDC * kQPitch;                    // [kDC][kCPitch]  candidate chunk, feature-major
@@ -62,6 +67,14 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
   int* Li = reinterpret_cast<int*>(Ld + (size_t)kQT * k);   // [kQT][k]  their indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q0 = (int64_t)blockIdx.x * kQT;
+  // with a query list (the queries the GEMM-form search could not certify) block b takes entries 64b .. 64b + 63 of it
+  const int64_t nq = (qlist != nullptr) ? (int64_t)*qcount : n;
+  if (q0 >= nq) return;
+  auto qrow = [&](int ql) -> int64_t {
+    const int64_t e = q0 + ql;
+    if (e >= nq) return n;                                 // past the end: behaves like a row beyond the matrix
+    return (qlist != nullptr) ? (int64_t)qlist[e] : e;
+  };
   for (int i = tid; i < kQT * k; i += kKnnThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
 
   for (int64_t c0 = 0; c0 < n; c0 += kCT) {
@@ -74,7 +87,7 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
       __syncthreads();
       for (int i = tid; i < kDC * kQT; i += kKnnThreads) {
         const int q = i / kDC, dd = i - q * kDC;
-        const int64_t row = q0 + q;
+        const int64_t row = qrow(q);
         Qs[dd * kQPitch + q] = (row < n && d0 + dd < d) ? X[row * ldx + d0 + dd] : 0.0;
       }
       for (int i = tid; i < kDC * kCT; i += kKnnThreads) {
@@ -101,7 +114,7 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int ql = 8 * warp + a;
-      if (q0 + ql < n) {                                              // uniform in the warp
+      if (q0 + ql < nq) {                                             // uniform in the warp
         double* ld = Ld + (size_t)ql * k;
         int* li = Li + (size_t)ql * k;
         double thr = ld[k - 1];
@@ -118,9 +131,216 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
   __syncwarp();
   for (int a = 0; a < 8; ++a) {
     const int ql = 8 * warp + a;
-    const int64_t row = q0 + ql;
+    const int64_t row = qrow(ql);
     if (row >= n) break;
     for (int p = lane; p < k; p += 32) idx_out[row * k + p] = Li[(size_t)ql * k + p];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// GEMM-form nearest-neighbour search on the FP64 tensor pipe
+// ------------------------------------------------------------------------------------------------
+// |q - c|^2 = |q|^2 + |c|^2 - 2 q.c : the N^2 d inner products are a GEMM, done with DMMA.8x8x4 at one FMA per feature
+// pair where the exact kernel above spends a subtraction and an FMA on the plain FP64 pipe.  Those distances carry a
+// rounding error of order d eps (|q|^2 + |c|^2), so this pass only builds a SHORTLIST of k + kKnnMargin candidates per
+// query; knn_rerank_kernel then recomputes the exact sum (a-b)^2 of the shortlist in feature order (the kd-tree's
+// squared_euclidean), sorts it with the exact tie rule, and certifies the result: every candidate left out has an
+// approximate distance >= the shortlist's last one, hence an exact distance >= that - delta; if the exact k-th distance
+// is below that bound the k neighbours are provably the exact ones.  Queries that cannot be certified (more than
+// kKnnMargin near-ties at the k-th distance: duplicated or lattice data) are redone by the exact kernel.
+// A CTA owns 64 queries (tile resident in shared memory) and streams all candidates in tiles of CT rows, one
+// cp.async.bulk per tile (a tile of the packed sample matrix is contiguous) through a 2-stage mbarrier pipeline fed by a
+// producer warp.  8 consumer warps (4 x 2): warp tile 16 queries x CT/2 candidates.  Both operands are row-major with
+// the engine pitch ld == 4 (mod 8), which makes the DMMA fragment loads bank-conflict free.
+constexpr int kGQ = 64;
+constexpr int kGThreads = 9 * 32;
+
+template <int CT>
+__global__ void __launch_bounds__(kGThreads, 1)
+knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, int64_t n, int d8, int64_t ldx, int kp,
+                int* __restrict__ short_idx, double* __restrict__ short_thr) {
+  constexpr int JW = CT / 16;                         // n-blocks of 8 candidates per warp
+  constexpr int DP = CT + 8;                          // pitch of the distance tile: 16-byte stores of a quarter warp spread
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int ld = (int)ldx;
+  double* Qs = reinterpret_cast<double*>(smraw);                       // [64][ld]
+  double* Cs = Qs + (size_t)kGQ * ld;                                  // [2][CT][ld]
+  double* Cn = Cs + (size_t)2 * CT * ld;                               // [2][CT]   squared norms of the tile
+  double* Qn = Cn + 2 * CT;                                            // [64]
+  double* Dt = Qn + kGQ;                                               // [64][DP]  distances of the current tile
+  double* Ld = Dt + (size_t)kGQ * DP;                                  // [64][kp]
+  int* Li = reinterpret_cast<int*>(Ld + (size_t)kGQ * kp);             // [64][kp]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Li + (size_t)kGQ * kp + ((kGQ * kp) & 1));   // full[2], empty[2]
+  const uint32_t sBar = smem_u32(bars);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q0 = (int64_t)blockIdx.x * kGQ;
+  const int64_t tiles = (n + CT - 1) / CT;
+
+  if (tid == 0) {
+    mbar_init(sBar, 1); mbar_init(sBar + 8, 1);
+    mbar_init(sBar + 16, 8); mbar_init(sBar + 24, 8);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < kGQ * ld; i += kGThreads) {
+    const int q = i / ld, c = i - q * ld;
+    Qs[i] = (q0 + q < n) ? X[(q0 + q) * ldx + c] : 0.0;
+  }
+  for (int i = tid; i < kGQ; i += kGThreads) Qn[i] = (q0 + i < n) ? nrm2[q0 + i] : 0.0;
+  for (int i = tid; i < kGQ * kp; i += kGThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ------------------------------ producer: one bulk copy per candidate tile (+ its norms) ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t t = 0; t < tiles; ++t) {
+        mbar_wait(sBar + 16 + 8 * stage, phase ^ 1u);
+        const int64_t c0 = t * CT;
+        const int rows = (int)min((int64_t)CT, n - c0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
+        const uint32_t nbytes = (uint32_t)((rows + 1) & ~1) * 8u;        // 16-byte granules (the norm array is padded)
+        mbar_arrive_expect_tx(sBar + 8 * stage, bytes + nbytes);
+        bulk_load(smem_u32(Cs + (size_t)stage * CT * ld), X + c0 * ldx, bytes, sBar + 8 * stage);
+        bulk_load(smem_u32(Cn + stage * CT), nrm2 + c0, nbytes, sBar + 8 * stage);
+        if (++stage == 2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------ consumers ------------------------------
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int ksteps = d8 >> 2;
+    const double* ap0 = Qs + (size_t)(16 * wm + g) * ld + t4;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t t = 0; t < tiles; ++t) {
+      const int64_t c0 = t * CT;
+      mbar_wait(sBar + 8 * stage, phase);
+      const double* cs = Cs + (size_t)stage * CT * ld;
+      const double* bp0 = cs + (size_t)((CT / 2) * wn + g) * ld + t4;
+      double acc[2][JW][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 2
+      for (int s = 0; s < ksteps; ++s) {
+        const double a0 = ap0[4 * s], a1 = ap0[4 * s + 8 * ld];
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+          const double bf = bp0[4 * s + 8 * j * ld];
+          dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, bf);
+          dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, bf);
+        }
+      }
+      const double* cn = Cn + stage * CT + (CT / 2) * wn;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ql = 16 * wm + 8 * i + g;
+        const double qn = Qn[ql];
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+          const int cl = 8 * j + 2 * t4;
+          const double d0 = fma(-2.0, acc[i][j][0], qn + cn[cl]);
+          const double d1 = fma(-2.0, acc[i][j][1], qn + cn[cl + 1]);
+          *reinterpret_cast<double2*>(Dt + (size_t)ql * DP + (CT / 2) * wn + cl) = make_double2(d0, d1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sBar + 16 + 8 * stage);             // the candidate tile is free again
+      if (++stage == 2) { stage = 0; phase ^= 1u; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the distance tile is complete (consumer warps only)
+      // selection: warp w owns queries 8w .. 8w + 7; candidates in increasing index order, ties keep the lower index
+#pragma unroll 1
+      for (int a = 0; a < 8; ++a) {
+        const int ql = 8 * warp + a;
+        if (q0 + ql < n) {
+          double* ldq = Ld + (size_t)ql * kp;
+          int* liq = Li + (size_t)ql * kp;
+          double thr = ldq[kp - 1];
+#pragma unroll
+          for (int b = 0; b < CT / 32; ++b) {
+            const int64_t cg = c0 + lane + 32 * b;
+            const double dist = (cg < n) ? Dt[(size_t)ql * DP + lane + 32 * b] : DBL_MAX;
+            const unsigned mask = __ballot_sync(0xffffffffu, dist < thr);
+            if (mask) thr = knn_insert(ldq, liq, kp, dist, (int)cg, thr, mask, lane);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // everybody is done with the distance tile
+    }
+    for (int a = 0; a < 8; ++a) {
+      const int ql = 8 * warp + a;
+      const int64_t row = q0 + ql;
+      if (row >= n) break;
+      for (int p = lane; p < kp; p += 32) short_idx[row * kp + p] = Li[(size_t)ql * kp + p];
+      if (lane == 0) short_thr[row] = Ld[(size_t)ql * kp + kp - 1];
+    }
+  }
+}
+
+// squared norms of the rows (the same d-term sums the distance identity needs) and their maximum
+__global__ void __launch_bounds__(256)
+knn_norms_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, double* __restrict__ nrm2, int64_t n_pad,
+                 unsigned long long* __restrict__ max_bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0.0;
+  if (i < n) {
+    const double* x = X + i * ldx;
+    for (int c = 0; c < d; ++c) a = fma(x[c], x[c], a);
+  }
+  if (i < n_pad) nrm2[i] = a;
+  // non-negative doubles order like their bit patterns
+  double m = a;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// One warp per query: exact distances of its shortlist (sum of (a-b)^2 in feature order, like the exact kernel and the
+// kd-tree), the k nearest in (distance, index) order, and the certificate described above.
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, int64_t n, int d, int64_t ldx, int k, int kp,
+                  const int* __restrict__ short_idx, const double* __restrict__ short_thr,
+                  const unsigned long long* __restrict__ max_bits, int* __restrict__ idx_out, int* __restrict__ qlist,
+                  int* __restrict__ qcount) {
+  __shared__ double sd[8][160];
+  __shared__ int si[8][160];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 8 + w;
+  if (q >= n) return;
+  const double* xq = X + q * ldx;
+  for (int p = lane; p < kp; p += 32) {
+    const int c = short_idx[q * kp + p];
+    double a = DBL_MAX;
+    if (c >= 0) {
+      const double* xc = X + (int64_t)c * ldx;
+      a = 0.0;
+      for (int f = 0; f < d; ++f) { const double t = xq[f] - xc[f]; a = fma(t, t, a); }
+    }
+    sd[w][p] = a;
+    si[w][p] = c >= 0 ? c : 0x7fffffff;
+  }
+  __syncwarp();
+  double dk = DBL_MAX;
+  for (int p = lane; p < kp; p += 32) {
+    const double a = sd[w][p];
+    const int c = si[w][p];
+    int r = 0;
+    for (int o = 0; o < kp; ++o) r += (sd[w][o] < a || (sd[w][o] == a && si[w][o] < c)) ? 1 : 0;
+    if (r < k) idx_out[q * k + r] = c;
+    if (r == k - 1) dk = a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dk = fmin(dk, __shfl_xor_sync(0xffffffffu, dk, o));
+  if (lane == 0) {
+    // |approximate - exact| <= (2d + 8) eps (|q|^2 + |c|^2) for every pair; a candidate outside the shortlist has an
+    // approximate distance >= thr.  With fewer than kp samples the shortlist is the whole set: nothing was left out.
+    const double nmax = __longlong_as_double((long long)*max_bits);
+    const double delta = (2.0 * d + 8.0) * DBL_EPSILON * (nrm2[q] + nmax);
+    const double thr = short_thr[q];
+    const bool certified = (n <= kp) || (dk < thr - 2.0 * delta);
+    if (!certified) qlist[atomicAdd(qcount, 1)] = (int)q;
   }
 }
 
@@ -234,14 +454,77 @@ poly_grad_kernel(const double* __restrict__ X, const double* __restrict__ y, int
 
 }  // namespace
 
-cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, cudaStream_t s) {
-  if (n <= 0 || d <= 0 || k <= 0 || k > kKnnMaxK || k > n) return cudaErrorInvalidValue;
+static cudaError_t knn_exact_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, const int* qlist,
+                                    const int* qcount, int64_t n_queries, cudaStream_t s) {
   const size_t smem = ((size_t)kDC * kQPitch + (size_t)kDC * kCPitch + (size_t)kQT * k) * 8 + (size_t)kQT * k * 4;
   cudaError_t e = cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
-  const int64_t blocks = (n + kQT - 1) / kQT;
-  knn_kernel<<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx);
+  const int64_t blocks = (n_queries + kQT - 1) / kQT;
+  if (blocks <= 0) return cudaSuccess;
+  knn_kernel<<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount);
   return cudaGetLastError();
+}
+
+static size_t knn_gemm_smem(int ct, int ld, int kp) {
+  size_t doubles = (size_t)kGQ * ld + (size_t)2 * ct * ld + 2 * (size_t)ct + kGQ + (size_t)kGQ * (ct + 8) + (size_t)kGQ * kp;
+  size_t bytes = doubles * 8 + ((size_t)kGQ * kp + 1) / 2 * 2 * 4 + 4 * 8;
+  return bytes;
+}
+
+size_t knn_scratch_bytes(int64_t n, int k) {
+  const int kp = k + kKnnMargin;
+  const size_t n_pad = (size_t)((n + 63) / 64 * 64 + 64);
+  // norms | shortlist thresholds | shortlist indices | query list | counters
+  return (n_pad + (size_t)n) * 8 + ((size_t)n * kp + (size_t)n) * 4 + 64 + 256;
+}
+
+cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, void* scratch, size_t scratch_bytes,
+                       int* n_exact_fallback, cudaStream_t s) {
+  if (n <= 0 || d <= 0 || k <= 0 || k > kKnnMaxK || k > n) return cudaErrorInvalidValue;
+  if (n_exact_fallback) *n_exact_fallback = -1;                           // -1: the exact kernel did everything
+  const char* env = getenv("CORRLA_B200_KNN_EXACT");
+  const int kp = k + kKnnMargin;
+  const int d8 = (d + 7) / 8 * 8;
+  int ct = 64;
+  if (knn_gemm_smem(ct, (int)ldx, kp) > 225 * 1024) ct = 32;
+  const bool gemm_ok = (env == nullptr || env[0] != '1') && scratch != nullptr && scratch_bytes >= knn_scratch_bytes(n, k) &&
+                       (ldx % 8) == 4 && ldx >= d8 && ldx <= 260 && n >= 2048 && n < ((int64_t)1 << 31) &&
+                       knn_gemm_smem(ct, (int)ldx, kp) <= 225 * 1024;
+  if (!gemm_ok) return knn_exact_launch(X, n, d, ldx, k, idx, nullptr, nullptr, n, s);
+
+  const size_t n_pad = (size_t)((n + 63) / 64 * 64 + 64);
+  unsigned char* base = static_cast<unsigned char*>(scratch);
+  double* nrm2 = reinterpret_cast<double*>(base);
+  double* thr = nrm2 + n_pad;
+  int* sidx = reinterpret_cast<int*>(thr + n);
+  int* qlist = sidx + (size_t)n * kp;
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(qlist + n) + 63) & ~(uintptr_t)63);
+  cudaError_t e = cudaMemsetAsync(counters, 0, 64, s);
+  if (e != cudaSuccess) return e;
+  knn_norms_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(X, n, d, ldx, nrm2, (int64_t)n_pad, counters);
+  const size_t smem = knn_gemm_smem(ct, (int)ldx, kp);
+  const unsigned blocks = (unsigned)((n + kGQ - 1) / kGQ);
+  if (ct == 64) {
+    e = cudaFuncSetAttribute(knn_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e != cudaSuccess) return e;
+    knn_gemm_kernel<64><<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
+  } else {
+    e = cudaFuncSetAttribute(knn_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e != cudaSuccess) return e;
+    knn_gemm_kernel<32><<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
+  }
+  int* qcount = reinterpret_cast<int*>(counters + 1);
+  knn_rerank_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, nrm2, n, d, ldx, k, kp, sidx, thr, counters, idx, qlist, qcount);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // queries without a certificate go through the exact kernel (normally none)
+  int hcount = 0;
+  e = cudaMemcpyAsync(&hcount, qcount, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return e;
+  if (n_exact_fallback) *n_exact_fallback = hcount;
+  if (hcount > 0) return knn_exact_launch(X, n, d, ldx, k, idx, qlist, qcount, hcount, s);
+  return cudaSuccess;
 }
 
 int poly_grad_num_coef(int d, int order) { return order == 2 ? d + d * (d + 1) / 2 : d; }

@@ -204,8 +204,8 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
 }
 
 // reduce_outer, narrow sketch (8x1 warp layout) and a short output side: see GemmArgs::kgroups.  Warp w works on box
-// w % a_boxes and takes the k4-steps S = 4*chunk + s with S % kgroups == w / a_boxes.  Every group's partial tile
-// (16*a_boxes rows) goes to the split-K workspace as if it were one more split.
+// column w % a_boxes of sub-chunk w / a_boxes of every stage.  Every group's partial tile (16*a_boxes rows) goes to the
+// split-K workspace as if it were one more split.
 template <int JW, bool FULL>
 __device__ __forceinline__ void consumer_loop_mc_kgroups(const GemmArgs& p, unsigned char* smem, unsigned char* smemB,
                                                          uint32_t sBar, int warp, int lane, int jn) {
@@ -222,8 +222,8 @@ __device__ __forceinline__ void consumer_loop_mc_kgroups(const GemmArgs& p, unsi
       a_xo[par][s] = kr * 128 + ((((mc >> 1) ^ (kr & 7))) << 4) + ((mc & 1) << 3);
     }
   }
-  const int a_base = box * 2048;
-  const int b_off = t * p.ldb * 8 + g * 8;
+  const int a_base = (kgrp * bv + box) * 2048;
+  const int b_off = (16 * kgrp + t) * p.ldb * 8 + g * 8;
   const int b_step = 4 * p.ldb * 8;
   const int W = p.tilesM * p.splits;
   const int Lc = p.nblk * 8;
@@ -239,12 +239,12 @@ __device__ __forceinline__ void consumer_loop_mc_kgroups(const GemmArgs& p, unsi
       for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     for (int64_t c = c0; c < c1; ++c) {
       mbar_wait(sBar + 8 * stage, phase);
-      const unsigned char* a = smem + stage * kAStageBytes + a_base;
-      const unsigned char* b = smemB + stage * p.b_stage_bytes + b_off;
-      const int sbase = (int)((c & 1) << 2);              // kgroups <= 8: only the parity of the chunk matters
+      // my sub-chunk may lie beyond the end of the reduction axis in the last stage: its rows of B were not loaded
+      if ((c * kg + kgrp) * kChunkK < p.k16) {
+        const unsigned char* a = smem + stage * kAStageBytes + a_base;
+        const unsigned char* b = smemB + stage * p.b_stage_bytes + b_off;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (((sbase + s) & (kg - 1)) == kgrp) {
+        for (int s = 0; s < 4; ++s) {
           const double a0 = *reinterpret_cast<const double*>(a + a_xo[0][s]);
           const double a1 = *reinterpret_cast<const double*>(a + a_xo[1][s]);
 #pragma unroll
@@ -310,7 +310,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
     tma_prefetch_desc(&tmA);
     const int W = p.tilesM * p.splits;
     uint32_t stage = 0, phase = 0;
-    const uint32_t tx = (KC ? kAStageBytes : (uint32_t)p.a_boxes * 2048u) + p.b_stage_bytes;
+    const uint32_t tx = (KC ? kAStageBytes : (uint32_t)(p.kgroups * p.a_boxes) * 2048u) + p.b_stage_bytes;
     for (int w = blockIdx.x; w < W; w += gridDim.x) {
       const int split = w / p.tilesM, tile = w - split * p.tilesM;
       const int64_t c0 = (int64_t)split * p.chunks_per_split;
@@ -319,17 +319,28 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const GemmArgs p) {
       for (int64_t c = c0; c < c1; ++c) {
         mbar_wait(sBar + 8 * (8 + stage), phase ^ 1u);
         const uint32_t full = sBar + 8 * stage;
-        mbar_arrive_expect_tx(full, tx);
-        const int k0 = (int)(c * kChunkK);
+        const int k0 = (int)(c * kChunkK * p.kgroups);
         const uint32_t dstA = sA + stage * kAStageBytes;
         if (KC) {
+          mbar_arrive_expect_tx(full, tx);
           tma_load_2d(dstA, &tmA, k0, m0, full);
-        } else {
+          bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
+        } else if (p.kgroups == 1) {
+          mbar_arrive_expect_tx(full, tx);
 #pragma unroll
           for (int b = 0; b < 8; ++b)
             if (b < p.a_boxes) tma_load_2d(dstA + b * 2048, &tmA, m0 + 16 * b, k0, full);
+          bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
+        } else {
+          // kgroups sub-chunks of 16 reduction rows: boxes [sub-chunk][box column]; only the rows of B that exist
+          const int64_t rows_b = min((int64_t)kChunkK * p.kgroups, p.k16 - (int64_t)k0);
+          const uint32_t b_bytes = (uint32_t)(rows_b * p.ldb * 8);
+          mbar_arrive_expect_tx(full, (uint32_t)(p.kgroups * p.a_boxes) * 2048u + b_bytes);
+          for (int kb = 0; kb < p.kgroups; ++kb)
+            for (int cb = 0; cb < p.a_boxes; ++cb)
+              tma_load_2d(dstA + (kb * p.a_boxes + cb) * 2048, &tmA, m0 + 16 * cb, k0 + kChunkK * kb, full);
+          bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, b_bytes, full);
         }
-        bulk_load(sB + stage * p.b_stage_bytes, p.B + (int64_t)k0 * p.ldb, p.b_stage_bytes, full);
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -765,6 +776,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
   gemm_plan(a.Mside, a.K, a.nblk, w.num_sms, c.force_splits, &a.tilesM, &a.splits, &a.chunks_per_split, &ws_bytes,
             &n_partials);
   a.chunks_total = std::max<int64_t>(1, (a.K + kChunkK - 1) / kChunkK);
+  a.k16 = (a.K + kChunkK - 1) / kChunkK * kChunkK;
   // short output side of a reduce_outer product with the narrow warp layout: k-groups (GemmArgs::kgroups)
   a.kgroups = 1; a.a_boxes = 8;
   if (!kc && a.nblk <= 7 && a.tilesM == 1) {
@@ -772,6 +784,11 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
     if (a.Mside <= 64) {
       a.a_boxes = a.Mside <= 16 ? 1 : (a.Mside <= 32 ? 2 : 4);
       a.kgroups = 8 / a.a_boxes;
+      // a stage now spans kgroups sub-chunks: re-cut the reduction axis into stages, keep the planned number of splits
+      a.chunks_total = std::max<int64_t>(1, (a.K + (int64_t)kChunkK * a.kgroups - 1) / ((int64_t)kChunkK * a.kgroups));
+      a.splits = (int)std::min<int64_t>(a.splits, a.chunks_total);
+      a.chunks_per_split = (a.chunks_total + a.splits - 1) / a.splits;
+      a.splits = (int)((a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split);
       ws_bytes = (size_t)a.splits * kTileM * a.nblk * 8 * sizeof(double);      // splits * kgroups * (16 * a_boxes) rows
       n_partials = (size_t)((a.Mside * (a.nblk * 4) + 7) / 8);                 // blocks of the warp-parallel reduction
     }
@@ -791,7 +808,7 @@ cudaError_t gemm_launch(const GemmCall& c, const GemmWorkspace& w, cudaStream_t 
       return cudaErrorInvalidValue;
     if (splits_eff == 1) a.out = c.px->mine;      // the GEMM epilogue writes my half of the symmetric region directly
   }
-  a.b_stage_bytes = (uint32_t)(kChunkK * c.ldb * 8);
+  a.b_stage_bytes = (uint32_t)(kChunkK * a.kgroups * c.ldb * 8);
   const size_t per_stage = kAStageBytes + a.b_stage_bytes;
   const size_t fixed = 1024 + 16 * 8 + 16 * 8;  // alignment slack + barriers + reduction scratch
   a.stages = (int)std::min<size_t>(8, (kMaxDynSmem - fixed) / per_stage);

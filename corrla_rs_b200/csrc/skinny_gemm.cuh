@@ -48,10 +48,13 @@ struct GemmArgs {
   const int* cond_flag;
   int stages; uint32_t b_stage_bytes;
   // reduce_outer with a SHORT output side (Mside <= 64, narrow sketches): only `a_boxes` of the eight 16-column TMA
-  // boxes of a stage hold rows of the output; the 8 consumer warps then form kgroups = 8 / a_boxes groups that share
-  // the boxes and split the k4-steps between them (each group writes its own partial tile, summed by the split-K
-  // reduction), so no DMMA is spent on zero padding and all four FP64 pipes of the SM stay busy.  1 / 8 otherwise.
+  // boxes of a stage would hold rows of the output.  The other box slots then carry MORE of the reduction axis: a
+  // stage is kgroups = 8 / a_boxes sub-chunks of 16 reduction rows (a_boxes boxes each, same 16 KB), the 8 consumer
+  // warps form kgroups groups, group g contracts sub-chunk g of every stage, and each group writes its own partial
+  // tile (summed by the split-K reduction).  No DMMA is spent on zero padding, all four FP64 pipes of the SM stay
+  // busy, and the per-stage barrier traffic is amortised over kgroups times more data.  kgroups = 1, a_boxes = 8 otherwise.
   int kgroups, a_boxes;
+  int64_t k16;             // reduction length rounded up to 16 (rows of B that exist)
 };
 
 // Host-side description of one product; see gemm_launch().

@@ -403,6 +403,23 @@ def test_plain_c_caller_of_the_abi(tmp_path):
     assert "C ABI example OK" in r.stdout
 
 
+def test_c_replay_of_the_rust_wrapper_call_sequences(tmp_path):
+    """tools/c_abi_replay.c makes the calls rust/corrla-b200/src/lib.rs makes (default opts, NULL timings, NULL optional
+    outputs, faer column-major strides): the Rust crate cannot be compiled in this image, its call shapes can be run."""
+    import shutil
+    import subprocess
+    root = Path(__file__).resolve().parents[1]
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    exe = tmp_path / "c_abi_replay"
+    libdir = root / "corrla_rs_b200" / "lib"
+    subprocess.run(["gcc", "-O2", f"-I{root / 'include'}", "-o", str(exe), str(root / "tools" / "c_abi_replay.c"),
+                    f"-L{libdir}", "-lcorrla_b200", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "C ABI replay OK" in r.stdout
+
+
 # ------------------------------------------------------------------ degenerate shapes and parameters
 @pytest.mark.parametrize("shape,kqp", [((1, 1), (1, 2, 0)), ((2, 1), (1, 0, 0)), ((7, 3), (3, 1, 5)), ((3, 7), (2, 2, 1)),
                                         ((40, 40), (40, 3, 0)), ((500, 17), (1, 0, 0)), ((129, 128), (118, 2, 10)),

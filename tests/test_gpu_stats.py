@@ -165,3 +165,27 @@ def test_active_ss_asserts_ties_and_limits(cb):
     fit, g = cb.active_ss_fit(xs, ys, 1, 64, 1, return_gradients=True)
     assert np.max(np.abs(g - np.array([[1.0], [-2.0], [0.5], [3.0]]))) < 1e-11
     assert abs(np.diag(fit.singular_vals_)[0] - 14.25) < 1e-9 and np.max(np.abs(np.diag(fit.singular_vals_)[1:])) < 1e-12
+
+
+def test_knn_gemm_form_gives_the_exact_neighbour_lists(cb):
+    """The tensor-pipe nearest-neighbour search (shortlist by |q|^2 + |c|^2 - 2 q.c, exact re-rank, certificate) must
+    return the SAME neighbour lists as the exact sum-of-(a-b)^2 kernel: the gradient matrices (one local fit per sample
+    through exactly those neighbours) are compared bit for bit -- on continuous data, on data with a large common offset
+    (cancellation in the distance identity), and on lattice data full of exact ties (certificates fail: exact fallback)."""
+    import os
+    rng = np.random.default_rng(31)
+    cases = {
+        "gauss_d64": (rng.standard_normal((6000, 64)), 72),
+        "offset_d7": (1e3 + rng.standard_normal((4100, 7)), 12),
+        "lattice_d3": (rng.integers(0, 6, size=(3000, 3)).astype(np.float64), 10),
+        "wide_d100_k104": (rng.standard_normal((2500, 100)), 104),     # 32-candidate tiles
+    }
+    for name, (x, k) in cases.items():
+        y = np.sin(x[:, 0]) + x[:, 1] * x[:, 2] + 0.1 * x.sum(axis=1)
+        _, g_fast = cb.active_ss_fit(x, y, 1, k, 2, return_gradients=True)
+        os.environ["CORRLA_B200_KNN_EXACT"] = "1"
+        try:
+            _, g_exact = cb.active_ss_fit(x, y, 1, k, 2, return_gradients=True)
+        finally:
+            os.environ.pop("CORRLA_B200_KNN_EXACT", None)
+        assert np.array_equal(np.asarray(g_fast), np.asarray(g_exact)), name
