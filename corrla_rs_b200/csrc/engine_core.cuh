@@ -106,6 +106,13 @@ namespace corrla_eng {
 
 inline int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
 
+// l columns as P panels of equal padded width w (a multiple of 8, <= 128); only the last panel has padding columns
+inline void panel_plan(int l, int* P, int* w) {
+  const int lc = (l + 7) / 8 * 8;
+  *P = (lc + 127) / 128;
+  *w = ((l + *P - 1) / *P + 7) / 8 * 8;
+}
+
 inline int ensure_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

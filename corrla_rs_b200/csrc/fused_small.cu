@@ -28,7 +28,7 @@ constexpr int kFsMaxSweeps = 60;
 
 struct FsLayout {
   int m8, n8, l8, k8, pa, pm, pn, pl, lp;
-  size_t oA, oY, oY2, oZ, oZ2, oX, oV, oM1, oM2, oTau, oNrm, oSig, oRed, total;
+  size_t oA, oY, oY2, oZ, oZ2, oX, oV, oM1, oM2, oG, oT1, oT2, oTau, oNrm, oSig, oRed, total;
 };
 
 __host__ __device__ inline int fs_up8(int x) { return (x + 7) & ~7; }
@@ -47,6 +47,9 @@ __host__ __device__ inline FsLayout fs_layout(int m, int n, int l, int k) {
   L.oV = o; o += (size_t)L.l8 * L.lp;
   L.oM1 = o; o += (size_t)L.l8 * L.pl;
   L.oM2 = o; o += (size_t)L.l8 * L.pl;
+  L.oG = o; o += (size_t)L.l8 * L.pl;       // Gram matrix / Cholesky factor of the CholeskyQR2 path
+  L.oT1 = o; o += (size_t)L.l8 * L.pl;      // L^-1 (its transpose is R^-1)
+  L.oT2 = o; o += (size_t)L.l8 * L.pl;      // second-pass factor 3/2 I - 1/2 G2
   L.oTau = o; o += 2 * (size_t)L.l8;      // hv0 | hden of the Householder reflectors
   L.oNrm = o; o += (size_t)L.l8;
   L.oSig = o; o += (size_t)L.l8;
@@ -180,6 +183,109 @@ __device__ void fs_house_form_q(const double* F, int p, int rows, int l, const d
   __syncthreads();
 }
 
+
+// ---- CholeskyQR2 for the well-conditioned case (what the multi-kernel engine does on its fast path) -----------------
+// A Householder QR of a 100 x 18 matrix is 18 dependent column steps of ~2000 cycles each on one SM; CholeskyQR2 moves
+// the m-sized work into four small DMMA products and leaves one 18-step chain on an l x l matrix.
+
+// G = F^T F (F: rows8 x l8 column-major, pitch p; G: l8 x l8 row-major, pitch pl): one warp per 8 x 8 block of G
+__device__ void fs_gram(const double* F, int p, int rows8, int l8, const double* F2, double* G, int pl, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int nb = l8 >> 3, units = nb * nb, ks = rows8 >> 2;
+  for (int u = warp; u < units; u += kFsWarps) {
+    const int mb = u / nb, jb = u - mb * nb;
+    const double* ap = F + (8 * mb + g) * p + t;            // a(i, kk) = F [i*p + kk]
+    const double* bp = F2 + (8 * jb + g) * p + t;           // b(kk, j) = F2[j*p + kk]
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;          // two accumulator pairs: half the dependent DMMA chain
+    int s = 0;
+    for (; s + 1 < ks; s += 2) {
+      dmma_m8n8k4(c0, c1, ap[4 * s], bp[4 * s]);
+      dmma_m8n8k4(e0, e1, ap[4 * s + 4], bp[4 * s + 4]);
+    }
+    if (s < ks) dmma_m8n8k4(c0, c1, ap[4 * s], bp[4 * s]);
+    double* o = G + (8 * mb + g) * pl + 8 * jb + 2 * t;
+    o[0] = c0 + e0; o[1] = c1 + e1;
+  }
+}
+
+// Warp 0: Cholesky G = R^T R in place (upper triangle, rows of R) and W = L^-1 (L = R^T) in Wm, so that R^-1 = W^T
+// needs no separate triangular inversion.  Left-looking: lane k forms entry (j, k) of row j of R (k >= j) and of W (k <= j)
+// as a dot product over the finished rows m < j -- the inner loop only loads (R[m][j] is one broadcast word shared by
+// both sums), so nothing serialises behind shared-memory stores; one rsqrt per row is the dependent chain.
+// Returns false (warp-uniform) as soon as a pivot falls under 1e-8 of its original diagonal entry: cond(F) beyond ~1e4
+// or a rank-deficient F -- the Householder path takes over, nothing has been modified in F.
+__device__ bool fs_chol_inv_warp(double* G, double* Wm, int pl, int l, int lane) {
+  const bool col = lane < l;
+  const double d0 = col ? G[lane * pl + lane] : 1.0;
+  for (int j = 0; j < l; ++j) {
+    double sg = (col && lane >= j) ? G[j * pl + lane] : 0.0;
+    double sw = (lane == j) ? 1.0 : 0.0;
+    const bool up = col && lane >= j, lo = lane <= j;
+    for (int m = 0; m < j; ++m) {
+      const double rmj = G[m * pl + j];
+      const double rmk = up ? G[m * pl + lane] : 0.0;
+      const double wmk = (lo && lane <= m) ? Wm[m * pl + lane] : 0.0;
+      sg = fma(-rmj, rmk, sg);
+      sw = fma(-rmj, wmk, sw);
+    }
+    const double piv = __shfl_sync(0xffffffffu, sg, j);
+    const double dj = __shfl_sync(0xffffffffu, d0, j);
+    if (!(dj > 0.0) || !(piv > 1e-8 * dj)) return false;
+    const double inv = rsqrt(piv);
+    if (up) G[j * pl + lane] = sg * inv;
+    if (lo) Wm[j * pl + lane] = sw * inv;
+    __syncwarp();
+  }
+  return true;
+}
+
+// F (rows x l, column-major, pitch p) <- orthonormal basis of its span by CholeskyQR2 with the first-order second pass
+// (T2 = 3/2 I - 1/2 G2, exact to (3/8)|G2 - I|^2).  Returns 0: done, the basis is in F.  1: not applicable, F untouched.
+// 2: the second pass found |G2 - I| too large: `Other` holds F * R^-1 (same span, condition number ~1) for Householder.
+__device__ int fs_cholqr2(double* F, double* Other, int p, int rows8, int l, int l8, double* sG, double* sT1, double* sT2,
+                          int pl, double* red, int* sflag, int warp, int lane) {
+  const int tid = warp * 32 + lane;
+  const int nbl = l8 >> 3;
+  fs_gram(F, p, rows8, l8, F, sG, pl, warp, lane);
+  for (int idx = tid; idx < l8 * pl; idx += kFsThreads) sT1[idx] = 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    const bool ok = fs_chol_inv_warp(sG, sT1, pl, l, lane);
+    if (lane == 0) *sflag = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (*sflag == 0) return 1;
+  // Other = F * R^-1:   b(kk, j) = R^-1[kk][j] = W[j][kk] = sT1[j*pl + kk]
+  fs_gemm(nbl, F, 1, p, sT1, 1, pl, Other, 1, p, rows8 >> 3, l8 >> 2, rows8, l8, 1.0, warp, lane);
+  __syncthreads();
+  fs_gram(Other, p, rows8, l8, Other, sG, pl, warp, lane);
+  __syncthreads();
+  double e2 = 0.0;
+  for (int idx = tid; idx < l8 * pl; idx += kFsThreads) {
+    const int i = idx / pl, j = idx - i * pl;
+    double v = 0.0;
+    if (i < l && j < l) {
+      const double e = sG[idx] - (i == j ? 1.0 : 0.0);
+      e2 += e * e;
+      v = (i == j ? 1.0 : 0.0) - 0.5 * e;
+    }
+    sT2[idx] = v;
+  }
+  e2 = fs_warp_sum(e2);
+  if (lane == 0) red[warp] = e2;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < kFsWarps; ++w) tot += red[w];
+    *sflag = (tot <= 4e-16) ? 1 : 0;                       // NaN compares false: Householder
+  }
+  __syncthreads();
+  if (*sflag == 0) return 2;
+  fs_gemm(nbl, Other, 1, p, sT2, pl, 1, F, 1, p, rows8 >> 3, l8 >> 2, rows8, l8, 1.0, warp, lane);
+  __syncthreads();
+  return 0;
+}
+
 // One-sided Jacobi SVD of the l x l matrix held as columns X[j*lp + i] (l <= 32) by the whole CTA: one WARP per column
 // pair of the round-robin tournament (at most 16 pairs), lane i owns row i of both columns, so a round is four shared
 // loads, one butterfly, the rotation parameters (the two dependent rsqrt are what a round costs) and four stores, then
@@ -262,6 +368,9 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
   double* sV = fsm + L.oV;
   double* sM1 = fsm + L.oM1;
   double* sM2 = fsm + L.oM2;
+  double* sG = fsm + L.oG;
+  double* sT1 = fsm + L.oT1;
+  double* sT2 = fsm + L.oT2;
   double* hv0 = fsm + L.oTau;
   double* hden = hv0 + L.l8;
   double* nrm = fsm + L.oNrm;
@@ -310,16 +419,21 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     __syncthreads();
     tick(2);
   };
-  auto thin_q = [&](double*& F, double*& Other, int pitch, int rows) {    // F <- thin Q of F (buffers swap)
-    fs_house_factor(F, pitch, rows, l, hv0, hden, warp, lane);
-    fs_house_form_q(F, pitch, rows, l, hv0, hden, Other, warp, lane);
-    double* tmp = F; F = Other; Other = tmp;
+  // F <- thin Q of F: CholeskyQR2 when its Cholesky probe passes, else Householder (the buffers may swap)
+  auto thin_q = [&](double*& F, double*& Other, int pitch, int rows, int rows8) {
+    const int st = p.no_chol ? 1 : fs_cholqr2(F, Other, pitch, rows8, l, L.l8, sG, sT1, sT2, L.pl, red, s_info + 6, warp, lane);
+    if (st != 0) {
+      if (st == 2) { double* tmp = F; F = Other; Other = tmp; }
+      fs_house_factor(F, pitch, rows, l, hv0, hden, warp, lane);
+      fs_house_form_q(F, pitch, rows, l, hv0, hden, Other, warp, lane);
+      double* tmp = F; F = Other; Other = tmp;
+    }
     tick(3);
   };
 
   mm_AZ(sZ, sY);
   for (int it = 0; it < p.n_iter; ++it) {                      // :35
-    if (p.schedule == 1 || it > 2) thin_q(sY, sY2, L.pm, m);   // :37-39
+    if (p.schedule == 1 || it > 2) thin_q(sY, sY2, L.pm, m, L.m8);   // :37-39
     mm_AtY(sY, sZ);
     mm_AZ(sZ, sY);
     // Y <- Y / ||Y||_F                                         :53-55
@@ -339,7 +453,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     __syncthreads();
     tick(4);
   }
-  thin_q(sY, sY2, L.pm, m);                                    // :57   sY = Q
+  thin_q(sY, sY2, L.pm, m, L.m8);                              // :57   sY = Q
 
   if (p.power_only) {
     for (int idx = tid; idx < m * l; idx += kFsThreads) {
@@ -351,14 +465,39 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
   }
 
   mm_AtY(sY, sZ);                                              // :80   sZ = B^T (n x l)
-  // SVD of B (:89): B^T = Qz R (Householder), one-sided Jacobi on R^T, then U = Q * Vr, V = Qz * Ur
-  fs_house_factor(sZ, L.pn, n, l, hv0, hden, warp, lane);
-  for (int idx = tid; idx < l * l; idx += kFsThreads) {
-    const int j = idx / l, i = idx - j * l;                    // X column j = row j of R:  X[j][i] = R[j][i], i >= j
-    sX[j * L.lp + i] = (i >= j) ? sZ[i * L.pn + j] : 0.0;
-    sV[j * L.lp + i] = (i == j) ? 1.0 : 0.0;
+  // SVD of B (:89): B^T = Qz W with Qz the thin Q of B^T and W = Qz^T B^T (l x l, a small product: no R bookkeeping,
+  // whichever QR produced Qz), one-sided Jacobi on W^T, then U = Q * Vr, V = Qz * Ur
+  for (int idx = tid; idx < L.l8 * L.pn; idx += kFsThreads) sY2[idx] = sZ[idx];     // keep B^T (sY2 is free: sY holds Q)
+  __syncthreads();
+  thin_q(sZ, sZ2, L.pn, n, L.n8);                              // sZ = Qz
+  {
+    double* Qz = sZ;
+    // W[i][j] = sum_kk Qz[kk][i] * Bt[kk][j]  ->  X column i, row j  (X = W^T as columns: X[i*lp + j] = W[i][j])
+    const int g = lane >> 2, t = lane & 3;
+    const int nb = L.l8 >> 3, ks = L.n8 >> 2;
+    for (int u = warp; u < nb * nb; u += kFsWarps) {
+      const int mb = u / nb, jb = u - mb * nb;
+      const double* ap = Qz + (8 * mb + g) * L.pn + t;
+      const double* bp = sY2 + (8 * jb + g) * L.pn + t;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      int s2 = 0;
+      for (; s2 + 1 < ks; s2 += 2) {
+        dmma_m8n8k4(c0, c1, ap[4 * s2], bp[4 * s2]);
+        dmma_m8n8k4(e0, e1, ap[4 * s2 + 4], bp[4 * s2 + 4]);
+      }
+      if (s2 < ks) dmma_m8n8k4(c0, c1, ap[4 * s2], bp[4 * s2]);
+      const int i = 8 * mb + g, j = 8 * jb + 2 * t;
+      if (i < l) {
+        if (j < l) sX[i * L.lp + j] = c0 + e0;
+        if (j + 1 < l) sX[i * L.lp + j + 1] = c1 + e1;
+      }
+    }
+    for (int idx = tid; idx < l * l; idx += kFsThreads) {
+      const int j = idx / l, i = idx - j * l;
+      sV[j * L.lp + i] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
   }
-  fs_house_form_q(sZ, L.pn, n, l, hv0, hden, sZ2, warp, lane);       // sZ2 = Qz   (ends with a barrier)
   tick(5);
   int sweeps, conv;
   fs_jacobi_cta(sX, sV, L.lp, l, nrm, s_info + 4, warp, lane, &sweeps, &conv);
@@ -397,7 +536,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
   if (p.u != nullptr)                                          // :92   U = Q * Ub[:, :k]
     fs_gemm(nbk, sY, 1, L.pm, sM1, 1, L.pl, p.u, p.u_rs, p.u_cs, L.m8 / 8, L.l8 / 4, m, k, 1.0, warp, lane);
   if (p.v != nullptr)
-    fs_gemm(nbk, sZ2, 1, L.pn, sM2, 1, L.pl, p.v, p.v_rs, p.v_cs, L.n8 / 8, L.l8 / 4, n, k, 1.0, warp, lane);
+    fs_gemm(nbk, sZ, 1, L.pn, sM2, 1, L.pl, p.v, p.v_rs, p.v_cs, L.n8 / 8, L.l8 / 4, n, k, 1.0, warp, lane);
   for (int c = tid; c < k; c += kFsThreads) p.s[c] = sig[c];
   if (tid == 0) { p.info[0] = s_info[0]; p.info[1] = s_info[1]; p.info[2] = s_info[2]; }
   tick(7);

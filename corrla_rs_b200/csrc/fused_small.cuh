@@ -25,6 +25,7 @@ struct FusedSmallArgs {
   double* v; int64_t v_rs, v_cs;          // thin-V  n x k
   double* s;                              // k singular values
   double* qout;                           // power_only: Q, m x l column-major
+  int no_chol;                            // 1: Householder QR only (CORRLA_B200_FUSED_NO_CHOL=1; tests compare the two)
   int debug;                              // 1: thread 0 prints a clock64 phase breakdown (CORRLA_B200_FUSED_PROFILE=1)
   int* info;                              // [0] Jacobi sweeps, [1] converged, [2] 1 => result unusable, take the general path
 };

@@ -149,44 +149,40 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
 // approximate distance >= the shortlist's last one, hence an exact distance >= that - delta; if the exact k-th distance
 // is below that bound the k neighbours are provably the exact ones.  Queries that cannot be certified (more than
 // kKnnMargin near-ties at the k-th distance: duplicated or lattice data) are redone by the exact kernel.
-// A CTA owns 64 queries (tile resident in shared memory) and streams all candidates in tiles of CT rows, one
-// cp.async.bulk per tile (a tile of the packed sample matrix is contiguous) through a 2-stage mbarrier pipeline fed by a
-// producer warp.  8 consumer warps (4 x 2): warp tile 16 queries x CT/2 candidates.  Both operands are row-major with
-// the engine pitch ld == 4 (mod 8), which makes the DMMA fragment loads bank-conflict free.
+// A CTA owns 64 queries and streams all candidates in tiles of CT rows, one cp.async.bulk per tile (a tile of the packed
+// sample matrix is contiguous) through a 3-stage mbarrier pipeline fed by a producer warp.  The 8 consumer warps are
+// AUTONOMOUS: warp w owns queries 8w .. 8w+7 from the DMMA to the selection lists -- its A fragments (the 8 query rows)
+// stay in registers for the whole kernel, its 8 x CT distances go through a private slab of shared memory (the C
+// fragment layout is transposed into "lane = candidate" for the ballot-based selection), and nothing but the candidate
+// stages is shared, so there is no CTA barrier: a warp busy inserting only delays the others once the pipeline is full.
+// The candidate tile is row-major with the engine pitch ld == 4 (mod 8): bank-conflict-free DMMA B-fragment loads.
 constexpr int kGQ = 64;
 constexpr int kGThreads = 9 * 32;
+constexpr int kGStages = 3;
 
-template <int CT>
+template <int CT, int KS>
 __global__ void __launch_bounds__(kGThreads, 1)
 knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, int64_t n, int d8, int64_t ldx, int kp,
                 int* __restrict__ short_idx, double* __restrict__ short_thr) {
-  constexpr int JW = CT / 16;                         // n-blocks of 8 candidates per warp
-  constexpr int DP = CT + 8;                          // pitch of the distance tile: 16-byte stores of a quarter warp spread
+  constexpr int JW = CT / 8;                          // n-blocks of 8 candidates: every warp covers the whole tile
+  constexpr int DP = CT + 8;                          // pitch of a distance slab: the 16-byte stores of a quarter warp spread
   extern __shared__ __align__(16) unsigned char smraw[];
   const int ld = (int)ldx;
-  double* Qs = reinterpret_cast<double*>(smraw);                       // [64][ld]
-  double* Cs = Qs + (size_t)kGQ * ld;                                  // [2][CT][ld]
-  double* Cn = Cs + (size_t)2 * CT * ld;                               // [2][CT]   squared norms of the tile
-  double* Qn = Cn + 2 * CT;                                            // [64]
-  double* Dt = Qn + kGQ;                                               // [64][DP]  distances of the current tile
+  double* Cs = reinterpret_cast<double*>(smraw);                       // [stages][CT][ld]
+  double* Cn = Cs + (size_t)kGStages * CT * ld;                        // [stages][CT]   squared norms of the tile
+  double* Dt = Cn + kGStages * CT;                                     // [8 warps][8][DP]
   double* Ld = Dt + (size_t)kGQ * DP;                                  // [64][kp]
   int* Li = reinterpret_cast<int*>(Ld + (size_t)kGQ * kp);             // [64][kp]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Li + (size_t)kGQ * kp + ((kGQ * kp) & 1));   // full[2], empty[2]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Li + (size_t)kGQ * kp + ((kGQ * kp) & 1));   // full[3], empty[3]
   const uint32_t sBar = smem_u32(bars);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q0 = (int64_t)blockIdx.x * kGQ;
   const int64_t tiles = (n + CT - 1) / CT;
 
   if (tid == 0) {
-    mbar_init(sBar, 1); mbar_init(sBar + 8, 1);
-    mbar_init(sBar + 16, 8); mbar_init(sBar + 24, 8);
+    for (int s = 0; s < kGStages; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 8 * (kGStages + s), 8); }
     mbar_fence_init();
   }
-  for (int i = tid; i < kGQ * ld; i += kGThreads) {
-    const int q = i / ld, c = i - q * ld;
-    Qs[i] = (q0 + q < n) ? X[(q0 + q) * ldx + c] : 0.0;
-  }
-  for (int i = tid; i < kGQ; i += kGThreads) Qn[i] = (q0 + i < n) ? nrm2[q0 + i] : 0.0;
   for (int i = tid; i < kGQ * kp; i += kGThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
   __syncthreads();
 
@@ -195,7 +191,7 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t t = 0; t < tiles; ++t) {
-        mbar_wait(sBar + 16 + 8 * stage, phase ^ 1u);
+        mbar_wait(sBar + 8 * (kGStages + stage), phase ^ 1u);
         const int64_t c0 = t * CT;
         const int rows = (int)min((int64_t)CT, n - c0);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
@@ -203,79 +199,79 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
         mbar_arrive_expect_tx(sBar + 8 * stage, bytes + nbytes);
         bulk_load(smem_u32(Cs + (size_t)stage * CT * ld), X + c0 * ldx, bytes, sBar + 8 * stage);
         bulk_load(smem_u32(Cn + stage * CT), nrm2 + c0, nbytes, sBar + 8 * stage);
-        if (++stage == 2) { stage = 0; phase ^= 1u; }
+        if (++stage == kGStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
-    // ------------------------------ consumers ------------------------------
-    const int g = lane >> 2, t4 = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;
-    const int ksteps = d8 >> 2;
-    const double* ap0 = Qs + (size_t)(16 * wm + g) * ld + t4;
-    uint32_t stage = 0, phase = 0;
-    for (int64_t t = 0; t < tiles; ++t) {
-      const int64_t c0 = t * CT;
-      mbar_wait(sBar + 8 * stage, phase);
-      const double* cs = Cs + (size_t)stage * CT * ld;
-      const double* bp0 = cs + (size_t)((CT / 2) * wn + g) * ld + t4;
-      double acc[2][JW][2];
+    return;
+  }
+  // ------------------------------ consumers ------------------------------
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ksteps = d8 >> 2;
+  const int64_t myrow = q0 + 8 * warp + g;                               // the query of this lane's fragment row
+  double aq[KS];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+  for (int s = 0; s < KS; ++s) aq[s] = (s < ksteps && myrow < n) ? X[myrow * ldx + 4 * s + t4] : 0.0;
+  const double qn = (myrow < n) ? nrm2[myrow] : 0.0;
+  double* Dw = Dt + (size_t)warp * 8 * DP;
+  const double* thr_p = Ld + (size_t)(8 * warp + g) * kp + kp - 1;
+  uint32_t stage = 0, phase = 0;
+  for (int64_t t = 0; t < tiles; ++t) {
+    const int64_t c0 = t * CT;
+    mbar_wait(sBar + 8 * stage, phase);
+    const double* bp0 = Cs + (size_t)stage * CT * ld + (size_t)g * ld + t4;   // candidate 8j + g, feature 4s + t4
+    double acc[JW][2];
 #pragma unroll
-        for (int j = 0; j < JW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-#pragma unroll 2
-      for (int s = 0; s < ksteps; ++s) {
-        const double a0 = ap0[4 * s], a1 = ap0[4 * s + 8 * ld];
+    for (int j = 0; j < JW; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
 #pragma unroll
-        for (int j = 0; j < JW; ++j) {
-          const double bf = bp0[4 * s + 8 * j * ld];
-          dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, bf);
-          dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, bf);
-        }
+    for (int s = 0; s < KS; ++s) {
+      if (s < ksteps) {
+#pragma unroll
+        for (int j = 0; j < JW; ++j) dmma_m8n8k4(acc[j][0], acc[j][1], aq[s], bp0[4 * s + 8 * j * ld]);
       }
-      const double* cn = Cn + stage * CT + (CT / 2) * wn;
+    }
+    const double* cn = Cn + stage * CT;
+    const double thr = *thr_p;
+    bool hit = false;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int ql = 16 * wm + 8 * i + g;
-        const double qn = Qn[ql];
-#pragma unroll
-        for (int j = 0; j < JW; ++j) {
-          const int cl = 8 * j + 2 * t4;
-          const double d0 = fma(-2.0, acc[i][j][0], qn + cn[cl]);
-          const double d1 = fma(-2.0, acc[i][j][1], qn + cn[cl + 1]);
-          *reinterpret_cast<double2*>(Dt + (size_t)ql * DP + (CT / 2) * wn + cl) = make_double2(d0, d1);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sBar + 16 + 8 * stage);             // the candidate tile is free again
-      if (++stage == 2) { stage = 0; phase ^= 1u; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the distance tile is complete (consumer warps only)
-      // selection: warp w owns queries 8w .. 8w + 7; candidates in increasing index order, ties keep the lower index
+    for (int j = 0; j < JW; ++j) {
+      const int cl = 8 * j + 2 * t4;
+      const double d0 = fma(-2.0, acc[j][0], qn + cn[cl]);
+      const double d1 = fma(-2.0, acc[j][1], qn + cn[cl + 1]);
+      *reinterpret_cast<double2*>(Dw + g * DP + cl) = make_double2(d0, d1);
+      hit |= (d0 < thr && c0 + cl < n) | (d1 < thr && c0 + cl + 1 < n);
+    }
+    __syncwarp();                                                       // the slab stores are visible to the whole warp
+    const unsigned hb = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) mbar_arrive(sBar + 8 * (kGStages + stage));          // candidate tile and norms are free again
+    if (++stage == kGStages) { stage = 0; phase ^= 1u; }
+    // selection, only for the queries with a candidate under their threshold (after the first tiles: ~1 in 20 per tile);
+    // candidates in increasing index order, ties keep the lower index
+    if (hb != 0u) {
 #pragma unroll 1
       for (int a = 0; a < 8; ++a) {
+        if (((hb >> (4 * a)) & 0xfu) == 0u) continue;
         const int ql = 8 * warp + a;
-        if (q0 + ql < n) {
-          double* ldq = Ld + (size_t)ql * kp;
-          int* liq = Li + (size_t)ql * kp;
-          double thr = ldq[kp - 1];
+        if (q0 + ql >= n) continue;
+        double* ldq = Ld + (size_t)ql * kp;
+        int* liq = Li + (size_t)ql * kp;
+        double th = ldq[kp - 1];
 #pragma unroll
-          for (int b = 0; b < CT / 32; ++b) {
-            const int64_t cg = c0 + lane + 32 * b;
-            const double dist = (cg < n) ? Dt[(size_t)ql * DP + lane + 32 * b] : DBL_MAX;
-            const unsigned mask = __ballot_sync(0xffffffffu, dist < thr);
-            if (mask) thr = knn_insert(ldq, liq, kp, dist, (int)cg, thr, mask, lane);
-          }
+        for (int b = 0; b < CT / 32; ++b) {
+          const int64_t cg = c0 + lane + 32 * b;
+          const double dist = (cg < n) ? Dw[a * DP + lane + 32 * b] : DBL_MAX;
+          const unsigned mask = __ballot_sync(0xffffffffu, dist < th);
+          if (mask) th = knn_insert(ldq, liq, kp, dist, (int)cg, th, mask, lane);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // everybody is done with the distance tile
     }
-    for (int a = 0; a < 8; ++a) {
-      const int ql = 8 * warp + a;
-      const int64_t row = q0 + ql;
-      if (row >= n) break;
-      for (int p = lane; p < kp; p += 32) short_idx[row * kp + p] = Li[(size_t)ql * kp + p];
-      if (lane == 0) short_thr[row] = Ld[(size_t)ql * kp + kp - 1];
-    }
+    __syncwarp();                                                       // the slab is rewritten by the next tile
+  }
+  for (int a = 0; a < 8; ++a) {
+    const int ql = 8 * warp + a;
+    const int64_t row = q0 + ql;
+    if (row >= n) break;
+    for (int p = lane; p < kp; p += 32) short_idx[row * kp + p] = Li[(size_t)ql * kp + p];
+    if (lane == 0) short_thr[row] = Ld[(size_t)ql * kp + kp - 1];
   }
 }
 
@@ -466,8 +462,8 @@ static cudaError_t knn_exact_launch(const double* X, int64_t n, int d, int64_t l
 }
 
 static size_t knn_gemm_smem(int ct, int ld, int kp) {
-  size_t doubles = (size_t)kGQ * ld + (size_t)2 * ct * ld + 2 * (size_t)ct + kGQ + (size_t)kGQ * (ct + 8) + (size_t)kGQ * kp;
-  size_t bytes = doubles * 8 + ((size_t)kGQ * kp + 1) / 2 * 2 * 4 + 4 * 8;
+  size_t doubles = (size_t)kGStages * ct * ld + (size_t)kGStages * ct + (size_t)kGQ * (ct + 8) + (size_t)kGQ * kp;
+  size_t bytes = doubles * 8 + ((size_t)kGQ * kp + 1) / 2 * 2 * 4 + 2 * kGStages * 8;
   return bytes;
 }
 
@@ -488,7 +484,7 @@ cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, in
   int ct = 64;
   if (knn_gemm_smem(ct, (int)ldx, kp) > 225 * 1024) ct = 32;
   const bool gemm_ok = (env == nullptr || env[0] != '1') && scratch != nullptr && scratch_bytes >= knn_scratch_bytes(n, k) &&
-                       (ldx % 8) == 4 && ldx >= d8 && ldx <= 260 && n >= 2048 && n < ((int64_t)1 << 31) &&
+                       (ldx % 8) == 4 && ldx >= d8 && d8 <= 128 && n >= 2048 && n < ((int64_t)1 << 31) &&
                        knn_gemm_smem(ct, (int)ldx, kp) <= 225 * 1024;
   if (!gemm_ok) return knn_exact_launch(X, n, d, ldx, k, idx, nullptr, nullptr, n, s);
 
@@ -504,15 +500,15 @@ cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, in
   knn_norms_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(X, n, d, ldx, nrm2, (int64_t)n_pad, counters);
   const size_t smem = knn_gemm_smem(ct, (int)ldx, kp);
   const unsigned blocks = (unsigned)((n + kGQ - 1) / kGQ);
-  if (ct == 64) {
-    e = cudaFuncSetAttribute(knn_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    if (e != cudaSuccess) return e;
-    knn_gemm_kernel<64><<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
-  } else {
-    e = cudaFuncSetAttribute(knn_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    if (e != cudaSuccess) return e;
-    knn_gemm_kernel<32><<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
-  }
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (ee != cudaSuccess) return ee;
+    kern<<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
+    return cudaGetLastError();
+  };
+  if (ct == 64) e = (d8 <= 64) ? launch(knn_gemm_kernel<64, 16>) : launch(knn_gemm_kernel<64, 32>);
+  else e = (d8 <= 64) ? launch(knn_gemm_kernel<32, 16>) : launch(knn_gemm_kernel<32, 32>);
+  if (e != cudaSuccess) return e;
   int* qcount = reinterpret_cast<int*>(counters + 1);
   knn_rerank_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, nrm2, n, d, ldx, k, kp, sidx, thr, counters, idx, qlist, qcount);
   e = cudaGetLastError();

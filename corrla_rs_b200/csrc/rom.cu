@@ -2,6 +2,9 @@
 // (dmd_rom.rs:46-146) and POD modes/weights (pod_rom.rs:53-75).  Everything that touches the tall snapshot matrix
 // runs through the same skinny DMMA GEMM as the RSVD passes; the r x r eigendecomposition (DMDc) and the
 // n_snap x n_snap RBF interpolation (POD) stay with the caller, as they are negligible and not data-parallel.
+#include <string>
+#include <vector>
+
 #include "engine_core.cuh"
 #include "gradients.cuh"
 
@@ -161,69 +164,119 @@ int dmdc_impl(const double* x, int64_t n_x, int64_t T, int64_t x_rs, int64_t x_c
   add_timings(&acc, t1);
   add_timings(&acc, t2);
 
-  // ---- products on the tall side, all with l = r columns
+  // ---- products on the tall side.  r columns run as P column panels of padded width w <= 128 (P = 1 up to 128
+  // modes): an n x r matrix is P buffers in the engine layout, an r x r matrix one row-major buffer of pitch ldW whose
+  // w x w blocks are cut out (or assembled) as the right-hand operands of the panel products.
+  int P = 1, w = r;
+  panel_plan(r, &P, &w);
+  auto lp = [&](int pi) { return pi == P - 1 ? r - (P - 1) * w : w; };
   Core c;
   c.ctx = ctx; c.st = st; c.comm = comm;
-  ST_TRY(c.setup_dims(std::max(n_x, nn), std::min(n_x, nn), r));
+  ST_TRY(c.setup_dims(std::max(n_x, nn), std::min(n_x, nn), w));
   ST_TRY(c.alloc_workspace(true));
   const int Lc = c.Lc, ld = c.ld, L16 = c.L16;
   const size_t gx = comm ? (size_t)Lc * ld : 0;            // r x r cross products are summed over the ranks
   const int64_t nx16 = round_up(n_x, 16), nn16 = round_up(nn, 16);
-  double* Vs = rb.zeros("rom_vs", (size_t)nn16 * ld);
-  double* G2 = rb.zeros("rom_g2", (size_t)nn16 * ld);
-  double* P1 = rb.zeros("rom_p1", (size_t)nx16 * ld);
-  double* Uh = rb.zeros("rom_uh", (size_t)nx16 * ld);
-  double* U1 = rb.zeros("rom_u1", (size_t)nx16 * ld);
-  double* T0 = rb.zeros("rom_t0", (size_t)L16 * ld);
-  double* C1 = rb.zeros("rom_c1", (size_t)L16 * ld);
+  const int ldW = P * w + 4;
+  const int64_t rW16 = round_up((int64_t)P * w, 16);
+  auto panels = [&](const char* name, size_t elems, std::vector<double*>* out) -> bool {
+    out->assign(P, nullptr);
+    for (int pi = 0; pi < P; ++pi) {
+      const std::string nm = pi == 0 ? std::string(name) : std::string(name) + "_p" + std::to_string(pi);
+      (*out)[pi] = rb.zeros(nm.c_str(), elems);
+      if ((*out)[pi] == nullptr) return false;
+    }
+    return true;
+  };
+  std::vector<double*> Vs, G2, P1, Uh, U1;
+  bool ok = panels("rom_vs", (size_t)nn16 * ld, &Vs) && panels("rom_g2", (size_t)nn16 * ld, &G2) &&
+            panels("rom_p1", (size_t)nx16 * ld, &P1) && panels("rom_uh", (size_t)nx16 * ld, &Uh) &&
+            panels("rom_u1", (size_t)nx16 * ld, &U1);
+  double* T0 = rb.zeros("rom_t0", (size_t)rW16 * ldW);      // tmp_op_scale, r x r
+  double* C1 = rb.zeros("rom_c1", (size_t)rW16 * ldW);      // u_til_1^T u_hat, r x r
+  double* Blk = rb.zeros("rom_blk", (size_t)L16 * ld);      // one w x w block as a product result / right-hand operand
+  double* Bcol = rb.zeros("rom_bcol", (size_t)rW16 * ld);   // one r x w block column as a right-hand operand
   double* U2t = rb.zeros("rom_u2t", (size_t)L16 * ld);
-  if (!Vs || !G2 || !P1 || !Uh || !U1 || !T0 || !C1 || !U2t) { set_last_error("device allocation failed (DMDc products)"); return CORRLA_ERR_ALLOC; }
-  double* H = P1;   // reused once tmp_op_scale is formed
+  if (!ok || !T0 || !C1 || !Blk || !Bcol || !U2t) { set_last_error("device allocation failed (DMDc products)"); return CORRLA_ERR_ALLOC; }
+  std::vector<double*>& H = P1;   // reused once tmp_op_scale is formed
   cudaError_t e = cudaSuccess;
   auto chk = [&](const char* what) -> int {
     if (e != cudaSuccess) { set_last_error("%s failed: %s", what, cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
     return CORRLA_OK;
   };
-  // Vs = v_til * pinv(diag(s_til))      v_til(i, j) = Vttil[j + i*r]                       (:74, :86-87)
-  e = repack_launch(Vttil, nn, r, r, 1, Vs, ld, st); ST_TRY(chk("repack"));
-  scale_cols_pinv_kernel<<<(unsigned)((nn * r + 255) / 256), 256, 0, st>>>(Vs, nn, r, ld, Stil);
-  e = cudaGetLastError(); ST_TRY(chk("column scaling"));
-  // row-major padded copies of u_hat and u_til_1 (n_x x r)                                  (:75-77)
-  e = repack_launch(Uhat, n_x, r, 1, n_x, Uh, ld, st); ST_TRY(chk("repack"));
-  e = repack_launch(Util, n_x, r, 1, M, U1, ld, st); ST_TRY(chk("repack"));
-  launches += 4;
+  // block (pi, pj) of an r x r matrix as a right-hand operand (lp(pi) x lp(pj), engine layout)
+  auto load_block = [&](const double* Wd, int pi, int pj) -> int {
+    CU_TRY(cudaMemsetAsync(Blk, 0, (size_t)L16 * ld * 8, st));
+    e = repack_launch(Wd + (size_t)pi * w * ldW + (size_t)pj * w, lp(pi), lp(pj), ldW, 1, Blk, ld, st);
+    ++launches;
+    return chk("repack");
+  };
   const MatView yv{Yv, n_x, nn, ldD};                       // column-major: inner = state rows
-  // P1 = Y * v_til * s_inv  (one pass over Y);  tmp_op_scale = u_hat^T * P1                 (:90-94)
-  ST_TRY(c.mm(yv, false, Vs, P1, ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
-  ST_TRY(c.mm(c.view_rows(Uh, n_x), false, P1, T0, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
-  // C1 = u_til_1^T * u_hat;  a_til = tmp_op_scale * C1                                      (:95-97)
-  ST_TRY(c.mm(c.view_rows(U1, n_x), false, Uh, C1, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
+  for (int pi = 0; pi < P; ++pi) {
+    // Vs = v_til * pinv(diag(s_til))      v_til(i, j) = Vttil[j + i*r]                     (:74, :86-87)
+    e = repack_launch(Vttil + (size_t)pi * w, nn, lp(pi), r, 1, Vs[pi], ld, st); ST_TRY(chk("repack"));
+    scale_cols_pinv_kernel<<<(unsigned)((nn * lp(pi) + 255) / 256), 256, 0, st>>>(Vs[pi], nn, lp(pi), ld, Stil + (size_t)pi * w);
+    e = cudaGetLastError(); ST_TRY(chk("column scaling"));
+    // row-major padded copies of u_hat and u_til_1 (n_x x r)                                (:75-77)
+    e = repack_launch(Uhat + (size_t)pi * w * n_x, n_x, lp(pi), 1, n_x, Uh[pi], ld, st); ST_TRY(chk("repack"));
+    e = repack_launch(Util + (size_t)pi * w * M, n_x, lp(pi), 1, M, U1[pi], ld, st); ST_TRY(chk("repack"));
+    launches += 4;
+    // P1 = Y * v_til * s_inv  (one pass over Y per panel)                                   (:90-94)
+    ST_TRY(c.mm(yv, false, Vs[pi], P1[pi], ld, 1, Lc, nullptr, nullptr, nullptr, 0, true));
+  }
+  // tmp_op_scale = u_hat^T * P1;  C1 = u_til_1^T * u_hat   (w x w blocks, summed over the ranks)   (:90-97)
+  for (int pi = 0; pi < P; ++pi)
+    for (int pj = 0; pj < P; ++pj) {
+      ST_TRY(c.mm(c.view_rows(Uh[pi], n_x), false, P1[pj], Blk, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
+      e = repack_launch(Blk, lp(pi), lp(pj), ld, 1, T0 + (size_t)pi * w * ldW + (size_t)pj * w, ldW, st); ST_TRY(chk("repack"));
+      ST_TRY(c.mm(c.view_rows(U1[pi], n_x), false, Uh[pj], Blk, ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx));
+      e = repack_launch(Blk, lp(pi), lp(pj), ld, 1, C1 + (size_t)pi * w * ldW + (size_t)pj * w, ldW, st); ST_TRY(chk("repack"));
+      launches += 2;
+    }
+  // a_til = tmp_op_scale * C1: the r x r left operand whole, C1 one block column at a time        (:95-97)
   double* a_dev = (out_dev && a_til) ? a_til : rb.raw("rom_atil", (size_t)r * r + 8);
   if (!a_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-  ST_TRY(c.mm(MatView{T0, (int64_t)Lc, (int64_t)r, (int64_t)ld}, true, C1, a_dev, 1, r, r));
-  // modes_scale = Y * (v_til * s_inv * C1)  (second pass over Y)                            (:133-139)
+  for (int pj = 0; pj < P; ++pj) {
+    CU_TRY(cudaMemsetAsync(Bcol, 0, (size_t)rW16 * ld * 8, st));
+    e = repack_launch(C1 + (size_t)pj * w, r, lp(pj), ldW, 1, Bcol, ld, st); ST_TRY(chk("repack"));
+    ++launches;
+    ST_TRY(c.mm(MatView{T0, (int64_t)P * w, (int64_t)r, (int64_t)ldW}, true, Bcol, a_dev + (size_t)pj * w * r, 1, r, lp(pj)));
+  }
+  // modes_scale = Y * (v_til * s_inv * C1)  (second pass over Y per panel)                  (:133-139)
   double* ms_dev = nullptr;
   if (modes_scale != nullptr) {
     ms_dev = out_dev ? modes_scale : rb.raw("rom_modes", (size_t)n_x * r);
     if (!ms_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-    ST_TRY(c.mm(c.view_rows(Vs, nn), true, C1, G2, ld, 1, Lc));
-    ST_TRY(c.mm(yv, false, G2, ms_dev, 1, n_x, r, nullptr, nullptr, nullptr, 0, true));
+    for (int pj = 0; pj < P; ++pj) {
+      for (int pk = 0; pk < P; ++pk) {
+        ST_TRY(load_block(C1, pk, pj));
+        ST_TRY(c.mm(c.view_rows(Vs[pk], nn), true, Blk, G2[pj], ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, pk > 0));
+      }
+      ST_TRY(c.mm(yv, false, G2[pj], ms_dev + (size_t)pj * w * n_x, 1, n_x, lp(pj), nullptr, nullptr, nullptr, 0, true));
+    }
   }
   // _B = u_hat * (tmp_op_scale * u_til_2^T) = (u_hat * tmp_op_scale) * u_til_2^T            (:100-106)
   double* b_dev = nullptr;
   if (b != nullptr && n_u_all > 0) {
     b_dev = out_dev ? b : rb.raw("rom_b", (size_t)n_x * n_u_all);
     if (!b_dev) { set_last_error("device allocation failed"); return CORRLA_ERR_ALLOC; }
-    ST_TRY(c.mm(c.view_rows(Uh, n_x), true, T0, H, ld, 1, Lc));
-    for (int64_t j0 = 0; j0 < n_u_all; j0 += Lc) {
-      const int w = (int)std::min<int64_t>(Lc, n_u_all - j0);
-      if (j0 > 0 || comm != nullptr) CU_TRY(cudaMemsetAsync(U2t, 0, (size_t)L16 * ld * 8, st));
-      if (n_u > 0) {                                                                          // the rank that holds u_til_2
-        e = repack_launch(Util + n_x + j0, r, w, M, 1, U2t, ld, st); ST_TRY(chk("repack"));   // u_til_2^T panel: r x w
-        ++launches;
+    for (int pj = 0; pj < P; ++pj)                                                            // H = u_hat * tmp_op_scale
+      for (int pk = 0; pk < P; ++pk) {
+        ST_TRY(load_block(T0, pk, pj));
+        ST_TRY(c.mm(c.view_rows(Uh[pk], n_x), true, Blk, H[pj], ld, 1, Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, pk > 0));
       }
-      if (comm != nullptr) ST_TRY(c.allreduce(U2t, (size_t)L16 * ld));                        // zeros elsewhere: a broadcast
-      ST_TRY(c.mm(c.view_rows(H, n_x), true, U2t, b_dev + (size_t)j0 * n_x, 1, n_x, w));
+    for (int64_t j0 = 0; j0 < n_u_all; j0 += Lc) {
+      const int wu = (int)std::min<int64_t>(Lc, n_u_all - j0);
+      for (int pk = 0; pk < P; ++pk) {
+        CU_TRY(cudaMemsetAsync(U2t, 0, (size_t)L16 * ld * 8, st));
+        if (n_u > 0) {                                                                        // the rank that holds u_til_2
+          e = repack_launch(Util + n_x + j0 + (size_t)pk * w * M, lp(pk), wu, M, 1, U2t, ld, st); ST_TRY(chk("repack"));   // u_til_2^T block
+          ++launches;
+        }
+        if (comm != nullptr) ST_TRY(c.allreduce(U2t, (size_t)L16 * ld));                      // zeros elsewhere: a broadcast
+        ST_TRY(c.mm(c.view_rows(H[pk], n_x), true, U2t, b_dev + (size_t)j0 * n_x, 1, n_x, wu, nullptr, nullptr, nullptr, 0, false,
+                    nullptr, 0, 0, pk > 0));
+      }
     }
   }
   launches += c.launches;
@@ -298,35 +351,47 @@ int pod_impl(const double* x, int64_t n_snap, int64_t n_points, int64_t rs, int6
     ST_TRY(rsvd_impl(xv.p, n_points, n_snap, dcs, drs, (size_t)r, 10, 10, &oi, m_col, Sd, vt_small, &t1, false, nullptr));
   }
 
+  // modes and weights in P column panels of padded width w <= 128 (P = 1 up to 128 modes)
+  int P = 1, w = r;
+  panel_plan(r, &P, &w);
+  auto lp = [&](int pi) { return pi == P - 1 ? r - (P - 1) * w : w; };
   Core c;
   c.ctx = ctx; c.st = st; c.comm = comm;
-  ST_TRY(c.setup_dims(std::max(n_snap, n_points), thin_cols, r));
+  ST_TRY(c.setup_dims(std::max(n_snap, n_points), thin_cols, w));
   ST_TRY(c.alloc_workspace(true));
   const int64_t np16 = round_up(n_points, 16);
-  double* Mp = rb.zeros("rom_uh", (size_t)np16 * c.ld);
+  double* Mp = rb.raw("rom_uh", (size_t)np16 * c.ld);
   double* m_dev = m_col ? m_col : ((out_dev && modes) ? modes : rb.raw("rom_modes", (size_t)n_points * r));
   double* w_dev = (out_dev && weights) ? weights : rb.raw("rom_b", (size_t)n_snap * r);
   if (!Mp || !m_dev || !w_dev) { set_last_error("device allocation failed (POD products)"); return CORRLA_ERR_ALLOC; }
-  cudaError_t e;
-  if (comm == nullptr) {
-    // modes(i, j) = Vt[j + i*r]  (v.transpose().to_owned(), :57)
-    e = repack_launch(Vt, n_points, r, r, 1, Mp, c.ld, st);
-    if (e == cudaSuccess && modes != nullptr) e = scatter_launch(Mp, n_points, r, c.ld, m_dev, 1, n_points, st);
-  } else {
-    e = repack_launch(m_col, n_points, r, 1, n_points, Mp, c.ld, st);
-  }
-  launches += 2;
-  if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
-  // weights = x * modes: one more pass over the snapshots (:61-75); summed over the point blocks of the ranks
-  if (weights != nullptr && comm == nullptr) ST_TRY(c.mm(xv, rm, Mp, w_dev, 1, n_snap, r, nullptr, nullptr, nullptr, 0, true));
+  const int64_t ns16 = round_up(n_snap, 16);
+  double* Wt = nullptr;
   if (weights != nullptr && comm != nullptr) {
-    const int64_t ns16 = round_up(n_snap, 16);
-    double* Wt = rb.zeros("rom_p1", (size_t)ns16 * c.ld);
+    Wt = rb.raw("rom_p1", (size_t)ns16 * c.ld);
     if (!Wt) { set_last_error("device allocation failed (POD weights)"); return CORRLA_ERR_ALLOC; }
-    ST_TRY(c.mm(xv, rm, Mp, Wt, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 0, true, nullptr, (size_t)ns16 * c.ld));
-    e = scatter_launch(Wt, n_snap, r, c.ld, w_dev, 1, n_snap, st);
-    ++launches;
-    if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  }
+  for (int pi = 0; pi < P; ++pi) {
+    cudaError_t e;
+    CU_TRY(cudaMemsetAsync(Mp, 0, (size_t)np16 * c.ld * 8, st));
+    if (comm == nullptr) {
+      // modes(i, j) = Vt[j + i*r]  (v.transpose().to_owned(), :57)
+      e = repack_launch(Vt + (size_t)pi * w, n_points, lp(pi), r, 1, Mp, c.ld, st);
+      if (e == cudaSuccess && modes != nullptr) e = scatter_launch(Mp, n_points, lp(pi), c.ld, m_dev + (size_t)pi * w * n_points, 1, n_points, st);
+    } else {
+      e = repack_launch(m_col + (size_t)pi * w * n_points, n_points, lp(pi), 1, n_points, Mp, c.ld, st);
+    }
+    launches += 2;
+    if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    // weights = x * modes: one more pass over the snapshots per panel (:61-75); summed over the point blocks of the ranks
+    if (weights != nullptr && comm == nullptr)
+      ST_TRY(c.mm(xv, rm, Mp, w_dev + (size_t)pi * w * n_snap, 1, n_snap, lp(pi), nullptr, nullptr, nullptr, 0, true));
+    if (weights != nullptr && comm != nullptr) {
+      CU_TRY(cudaMemsetAsync(Wt, 0, (size_t)ns16 * c.ld * 8, st));
+      ST_TRY(c.mm(xv, rm, Mp, Wt, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 0, true, nullptr, (size_t)ns16 * c.ld));
+      e = scatter_launch(Wt, n_snap, lp(pi), c.ld, w_dev + (size_t)pi * w * n_snap, 1, n_snap, st);
+      ++launches;
+      if (e != cudaSuccess) { set_last_error("scatter failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+    }
   }
   launches += c.launches;
 

@@ -26,11 +26,7 @@ struct Wide {
   explicit Wide(Core& core) : c(core) {}
 
   // panel geometry for l columns: P panels of padded width w (multiple of 8, <= 128)
-  static void plan(int l, int* P, int* w) {
-    const int lc = (l + 7) / 8 * 8;
-    *P = (lc + 127) / 128;
-    *w = ((l + *P - 1) / *P + 7) / 8 * 8;
-  }
+  static void plan(int l, int* P, int* w) { panel_plan(l, P, w); }
   int lp(int p) const { return p == P - 1 ? l_last : w; }
   bool multi() const { return c.comm != nullptr && c.comm->nranks > 1; }
 

@@ -35,7 +35,7 @@ CASES = [
     (100, 100, (10, 12, 8), "C"),       # BASELINE config C1 (README example)
     (100, 100, (10, 12, 8), "F"),
     (60, 200, (7, 5, 6), "C"),          # fat: transposed view, roles of U and V swap
-    (233, 37, (12, 4, 10), "C"),        # ragged, l = 22
+    (203, 37, (12, 4, 10), "C"),        # ragged, l = 22
     (100, 64, (32, 3, 0), "C"),         # l = k = 32: the widest sketch the path takes
     (40, 9, (4, 20, 10), "C"),          # l clamps to n = 9 (PCA-like q = 20)
     (3, 2, (1, 2, 1), "C"),
@@ -130,3 +130,39 @@ def test_fused_small_is_not_taken_outside_its_limits(cb):
     assert cb.last_timings()["fused_small"] == 0
     cb.rsvd(b, 10, 2, 8, seed=1, center=True)                 # centring: the general path owns the rank-1 corrections
     assert cb.last_timings()["fused_small"] == 0
+
+
+def test_fused_small_choleskyqr2_and_householder_paths_agree(cb):
+    """Inside the fused kernel thin-Q is CholeskyQR2 when its Cholesky probe passes and Householder otherwise
+    (CORRLA_B200_FUSED_NO_CHOL=1 forces Householder): same sigma and subspaces on a benign input."""
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((100, 100))
+    omega = rng.standard_normal((100, 18))
+    ref = ref_rsvd.random_svd(a, 10, 12, 8, omega=omega)
+    fast = cb.rsvd(a, 10, 12, 8, omega=omega)
+    os.environ["CORRLA_B200_FUSED_NO_CHOL"] = "1"
+    try:
+        house = cb.rsvd(a, 10, 12, 8, omega=omega)
+        assert cb.last_timings()["fused_small"] == 1
+    finally:
+        os.environ.pop("CORRLA_B200_FUSED_NO_CHOL", None)
+    check(fast, ref, 10)
+    check(house, ref, 10)
+    assert ref_rsvd.sigma_rel_err(house[1], fast[1]) < 1e-12
+
+
+def test_fused_small_ill_conditioned_falls_back_to_householder_inside_the_kernel(cb):
+    """sigma_j = 2^-j: after three raw power iterations cond(Y) is ~1e16 at the first QR, the Cholesky probe fails and
+    the kernel's Householder path must take over.  Leading singular values against the exact ones (the reference
+    schedule itself is not reproducible to 1e-10 on such spectra)."""
+    rng = np.random.default_rng(10)
+    m, n = 160, 48
+    u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sig = 2.0 ** -np.arange(n)
+    a = (u0 * sig) @ v0.T
+    u, s, vt = cb.rsvd(a, 8, 6, 8, seed=5)
+    assert cb.last_timings()["fused_small"] == 1
+    assert np.max(np.abs(s.ravel() - sig[:8]) / sig[:8]) < 1e-9
+    assert np.max(np.abs(u.T @ u - np.eye(8))) < 1e-12 and np.max(np.abs(vt @ vt.T - np.eye(8))) < 1e-12
+    assert ref_rsvd.subspace_sine(u0[:, :4], np.asarray(u)[:, :4]) < 1e-7

@@ -247,3 +247,55 @@ def test_rom_fuzz(cb):
         rows = rng.choice(n, size=12, replace=False)
         g0 = np.stack([est.grad_at(xg[i]).ravel() for i in rows], axis=1)
         assert np.max(np.abs(g[:, rows] - g0)) < 1e-8 * max(1.0, np.max(np.abs(g0))), (trial, n, d, k)
+
+
+# ------------------------------------------------------------------ more modes than one 128-column panel holds
+def _wide_dmd_data(rng, n_x, n_u, nt, r_true):
+    """Snapshots of numerical rank r_true with a gently graded spectrum (the planted linear systems above lose rank
+    when a couple of inputs drive hundreds of modes); DMDc of arbitrary data is still a well-defined least-squares fit."""
+    q, _ = np.linalg.qr(rng.standard_normal((n_x, r_true)))
+    x = (q * (10.0 * 0.99 ** np.arange(r_true))) @ rng.standard_normal((r_true, nt))
+    u = rng.standard_normal((n_u, nt))
+    return x, u
+
+
+@pytest.mark.parametrize("n_x,n_u,nt,r_true", [(1200, 2, 400, 150), (1400, 2, 600, 256)])
+def test_dmdc_more_modes_than_one_panel(cb, n_x, n_u, nt, r_true):
+    """n_modes = 152 (sketch l = 164: two column panels) and 258 (l = 270: three) -- the reference has no cap on n_modes
+    (dmd_rom.rs:45-61).  Same comparisons as the single-panel test, on basis-independent quantities."""
+    rng = np.random.default_rng(n_x)
+    x, u = _wide_dmd_data(rng, n_x, n_u, nt, r_true)
+    r = r_true + n_u
+    omegas = dmd_omegas(rng, n_x, n_u, nt, r)
+    ref = ref_rom.DMDc(x, u, 1.0, r, 4, omegas=omegas)
+    ops = cb.dmdc_operators(x, u, r, 4, omegas=omegas)
+    assert ops["a_til"].shape == (r, r) and ops["b"].shape == (n_x, n_u) and ops["modes_scale"].shape == (n_x, r)
+    assert ref_rsvd.sigma_rel_err(ref.s_til, ops["s_til"]) < 1e-10
+    assert ref_rsvd.subspace_sine(ref.u_hat[:, :r_true], ops["u_hat"][:, :r_true]) < 1e-8
+    assert np.max(np.abs(ops["u_hat"].T @ ops["u_hat"] - np.eye(r))) < 1e-11
+    scale = np.max(np.abs(full_operator(ref.u_hat, ref.a_til)))
+    assert np.max(np.abs(full_operator(ops["u_hat"], ops["a_til"]) - full_operator(ref.u_hat, ref.a_til))) < 1e-8 * scale
+    assert np.max(np.abs(ops["b"] - ref.b)) < 1e-8 * max(1.0, np.max(np.abs(ref.b)))
+    lift, lift0 = ops["modes_scale"] @ ops["u_hat"].T, ref.modes_scale @ ref.u_hat.T
+    assert np.max(np.abs(lift - lift0)) < 1e-8 * np.max(np.abs(lift0))
+    assert abs(np.trace(ops["a_til"]) - np.trace(ref.a_til)) < 1e-8 * max(1.0, abs(np.trace(ref.a_til)))
+
+
+@pytest.mark.parametrize("r", [150, 260])
+def test_pod_more_modes_than_one_panel(cb, r):
+    import torch
+    rng = np.random.default_rng(r)
+    n_snap, n_points, rank = 320, 5000, 280
+    base = rng.standard_normal((n_snap, rank)) * (10.0 * 0.985 ** np.arange(rank))
+    x = base @ np.linalg.qr(rng.standard_normal((n_points, rank)))[0].T
+    omega = rng.standard_normal((n_snap, min(r + 10, n_snap)))
+    t = np.linspace(0.0, 1.0, n_snap).reshape(-1, 1)
+    ref = ref_rom.PodI(x, t, r, omega=omega)
+    modes, weights, s = cb.pod_modes_weights(x, r, omega=omega)
+    assert modes.shape == (n_points, r) and weights.shape == (n_snap, r) and s.shape == (r, 1)
+    assert ref_rsvd.subspace_sine(ref.modes, modes) < 1e-8
+    assert np.max(np.abs(modes.T @ modes - np.eye(r))) < 1e-11
+    assert np.max(np.abs(weights - x @ modes)) < 1e-11 * np.max(np.abs(x))
+    assert np.max(np.abs(weights @ modes.T - ref.mode_weights @ ref.modes.T)) < 1e-8 * np.max(np.abs(x))
+    md, wd, _ = cb.pod_modes_weights(torch.from_numpy(x).cuda(), r, omega=torch.from_numpy(omega).cuda())
+    assert np.array_equal(md.cpu().numpy(), np.asarray(modes)) and np.array_equal(wd.cpu().numpy(), np.asarray(weights))
