@@ -21,7 +21,7 @@ import numpy as np
 from . import _ffi
 from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 
-__all__ = ["rsvd", "random_svd", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
+__all__ = ["rsvd", "random_svd", "rsvd_f32", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
            "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings", "release_buffers",
            "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights",
            "cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "active_ss", "active_ss_fit"]
@@ -322,6 +322,47 @@ def rsvd(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, se
 
 
 random_svd = rsvd
+
+
+def rsvd_f32(a_mat, n_rank: int, n_iters: int, n_oversamples: int, *, omega=None, seed: int | None = None,
+             schedule="reference", ctx: Context | None = None):
+    """`random_svd::<f32>` (random_svd.rs:63-66 is generic over T: RealField + Float): a_mat is a 2-D float32 numpy array
+    or torch CUDA tensor, the factors come back as float32 with the reference's shapes.  (The pyo3 `rsvd` itself takes
+    float64 only; this is the instantiation a Rust caller reaches with f32 matrices.)  The arithmetic runs on the FP64
+    tensor pipe: the data are widened once on the device and the factors rounded on the way out."""
+    lib = _ffi.load()
+    for name, v in (("n_rank", n_rank), ("n_iters", n_iters), ("n_oversamples", n_oversamples)):
+        if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
+            raise TypeError(f"{name} must be an int")
+        if v < 0:
+            raise OverflowError(f"can't convert negative int to unsigned ({name})")
+    k = max(int(n_rank), 1)
+    if _is_torch(a_mat):
+        import torch
+        if a_mat.dtype != torch.float32 or a_mat.dim() != 2 or not a_mat.is_cuda:
+            raise TypeError("a_mat must be a 2-D float32 CUDA tensor or numpy array")
+        on_device, ptr, shape, strides, device = True, a_mat.data_ptr(), tuple(a_mat.shape), tuple(a_mat.stride()), a_mat.device.index
+        mk = lambda r, c: torch.empty((c, r), dtype=torch.float32, device=a_mat.device).t()
+    else:
+        if not isinstance(a_mat, np.ndarray) or a_mat.dtype != np.float32 or a_mat.ndim != 2:
+            raise TypeError("a_mat must be a 2-D float32 CUDA tensor or numpy array")
+        if any(st % 4 or st < 0 for st in a_mat.strides):
+            a_mat = np.ascontiguousarray(a_mat)
+        on_device, ptr, shape, strides, device = False, a_mat.ctypes.data, a_mat.shape, tuple(st // 4 for st in a_mat.strides), None
+        mk = lambda r, c: np.empty((r, c), dtype=np.float32, order="F")
+    nrows, ncols = shape
+    ctx = ctx or _context_for(device)
+    stream = _current_stream(device) if on_device else None
+    o, keep = _make_opts(ctx=ctx, on_device=on_device, out_on_device=on_device, omega=omega, seed=seed, schedule=schedule,
+                         comm=None, global_rows=None, stream=stream, device=device)
+    u, s, vt = mk(nrows, k), mk(k, 1), mk(k, ncols)
+    t = Timings()
+    st = lib.corrla_rsvd_f32(ptr, nrows, ncols, strides[0], strides[1], int(n_rank), int(n_iters), int(n_oversamples),
+                             C.byref(o), _ptr(u), _ptr(s), _ptr(vt), C.byref(t))
+    del keep
+    _ffi.check(st)
+    _tls.timings = t.as_dict()
+    return u, s, vt
 
 
 def rpca(a_mat, n_rank: int, n_iters: int = 0, n_oversamples: int = 0, *, omega=None, seed: int | None = None,

@@ -64,6 +64,11 @@ SYMBOLS = {
                                   C.POINTER(Timings)]),
     "corrla_power_iter_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
                                         C.c_size_t, C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(Timings)]),
+    "corrla_rsvd_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t, C.c_size_t,
+                                  C.c_size_t, C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(Timings)]),
+    "corrla_power_iter_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
+                                        C.c_size_t, C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(Timings)]),
     "corrla_rpca_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_size_t,
                                   C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Timings)]),
     "corrla_par_matmul_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,

@@ -364,6 +364,109 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
 
 using namespace corrla_eng;
 
+
+// ---------------------------------------------------------------------------------------------
+// f32 instantiation of the generic reference functions (random_svd<T>, power_iter<T>: T = f32).  The contraction
+// hardware of this path is the FP64 tensor pipe, so single-precision data are widened once on the device, the f64
+// engine runs unchanged, and the factors are rounded to f32 on the way out: results at least as accurate as an
+// all-f32 evaluation (faer's f32 GEMM / QR / SVD) at the cost of an f64 copy of A on the device.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+widen_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double* __restrict__ dst) {
+  const int64_t total = rows * cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / cols, j = e - i * cols;
+    dst[e] = (double)src[i * rs + j * cs];
+  }
+}
+__global__ void __launch_bounds__(256)
+narrow_kernel(const double* __restrict__ src, int64_t count, float* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) dst[e] = (float)src[e];
+}
+
+int f32_impl(const float* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t cs, size_t n_rank, size_t n_iter,
+             size_t n_oversamples, const corrla_rsvd_opts* opts_in, float* u, float* s, float* vt, corrla_timings* tm,
+             bool power_only, float* q_out) {
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  if (a == nullptr || nrows <= 0 || ncols <= 0) { set_last_error("empty or null input matrix"); return CORRLA_ERR_INVALID; }
+  if (power_only ? (q_out == nullptr) : (u == nullptr || s == nullptr || vt == nullptr)) { set_last_error("null output"); return CORRLA_ERR_INVALID; }
+  if (o.comm != nullptr) { set_last_error("the f32 entry points do not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  const bool in_dev = o.a_on_device != 0, out_dev = o.out_on_device != 0;
+  const size_t k = n_rank;
+  const size_t n_a = (size_t)nrows * ncols;
+  const size_t n_u = power_only ? (size_t)nrows * k : (size_t)nrows * k, n_v = power_only ? 0 : (size_t)ncols * k;
+  double* a64 = static_cast<double*>(ctx->get("f32_a64", n_a * 8));
+  double* o64 = static_cast<double*>(ctx->get("f32_o64", (n_u + n_v + k + 8) * 8));
+  if (!a64 || !o64) { set_last_error("device allocation failed (f32 widening buffers)"); return CORRLA_ERR_ALLOC; }
+  Timer th2d;
+  const float* asrc = a;
+  int64_t srs = rs, scs = cs;
+  if (!in_dev) {
+    // host: move the floats as they lie when they are one dense block (either orientation), else pack on the host
+    float* a32 = static_cast<float*>(ctx->get("f32_a32", n_a * 4));
+    if (!a32) { set_last_error("device allocation failed (f32 staging)"); return CORRLA_ERR_ALLOC; }
+    const bool dense_rm = (cs == 1 && rs == ncols), dense_cm = (rs == 1 && cs == nrows);
+    if (dense_rm || dense_cm) {
+      CU_TRY(cudaMemcpyAsync(a32, a, n_a * 4, cudaMemcpyHostToDevice, st));
+    } else {
+      std::vector<float> tmp;
+      try { tmp.resize(n_a); } catch (...) { set_last_error("host allocation failed"); return CORRLA_ERR_ALLOC; }
+      for (int64_t i = 0; i < nrows; ++i)
+        for (int64_t j = 0; j < ncols; ++j) tmp[(size_t)i * ncols + j] = a[i * rs + j * cs];
+      CU_TRY(cudaMemcpyAsync(a32, tmp.data(), n_a * 4, cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      srs = ncols; scs = 1;
+    }
+    asrc = a32;
+  }
+  widen_kernel<<<(unsigned)std::min<int64_t>((int64_t)(n_a + 255) / 256, 148 * 32), 256, 0, st>>>(asrc, nrows, ncols, srs, scs, a64);
+  CU_TRY(cudaGetLastError());
+  const double h2d_ms = in_dev ? 0.0 : th2d.ms();
+  corrla_rsvd_opts oi = o;
+  oi.a_on_device = 1; oi.out_on_device = 1; oi.ctx = ctx; oi.stream = st; oi.device = ctx->device;
+  double *u64 = o64, *v64 = o64 + n_u, *s64 = o64 + n_u + n_v;
+  int status;
+  if (power_only) status = rsvd_impl(a64, nrows, ncols, ncols, 1, n_rank, n_iter, 0, &oi, nullptr, nullptr, nullptr, tm, true, u64);
+  else status = rsvd_impl(a64, nrows, ncols, ncols, 1, n_rank, n_iter, n_oversamples, &oi, u64, s64, v64, tm, false, nullptr);
+  if (status != CORRLA_OK) return status;
+  const size_t n_out = power_only ? n_u : n_u + n_v + k;
+  float* o32 = out_dev ? nullptr : static_cast<float*>(ctx->get("f32_o32", (n_out + 8) * 4));
+  if (!out_dev && !o32) { set_last_error("device allocation failed (f32 outputs)"); return CORRLA_ERR_ALLOC; }
+  auto narrow = [&](const double* src, size_t count, float* dst) -> int {
+    if (count == 0) return CORRLA_OK;
+    narrow_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 148 * 32), 256, 0, st>>>(src, (int64_t)count, dst);
+    CU_TRY(cudaGetLastError());
+    return CORRLA_OK;
+  };
+  Timer td2h;
+  if (out_dev) {
+    if (power_only) ST_TRY(narrow(u64, n_u, q_out));
+    else { ST_TRY(narrow(u64, n_u, u)); ST_TRY(narrow(v64, n_v, vt)); ST_TRY(narrow(s64, k, s)); }
+    CU_TRY(cudaStreamSynchronize(st));
+  } else {
+    ST_TRY(narrow(o64, n_out, o32));
+    if (power_only) CU_TRY(cudaMemcpyAsync(q_out, o32, n_u * 4, cudaMemcpyDeviceToHost, st));
+    else {
+      CU_TRY(cudaMemcpyAsync(u, o32, n_u * 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(vt, o32 + n_u, n_v * 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(s, o32 + n_u + n_v, k * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  if (tm) { tm->h2d_ms = h2d_ms; tm->d2h_ms = out_dev ? 0.0 : td2h.ms(); }
+  return CORRLA_OK;
+}
+
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -387,6 +490,23 @@ int corrla_power_iter_f64(const double* a, int64_t nrows, int64_t ncols, int64_t
   try {
     return rsvd_impl(a, nrows, ncols, row_stride, col_stride, omega_rank, n_iter, 0, opts, nullptr, nullptr, nullptr,
                      timings, true, q);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+int corrla_rsvd_f32(const float* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride, size_t n_rank,
+                    size_t n_iter, size_t n_oversamples, const corrla_rsvd_opts* opts, float* u, float* s, float* vt,
+                    corrla_timings* timings) {
+  try {
+    return f32_impl(a, nrows, ncols, row_stride, col_stride, n_rank, n_iter, n_oversamples, opts, u, s, vt, timings, false, nullptr);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+int corrla_power_iter_f32(const float* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                          size_t omega_rank, size_t n_iter, const corrla_rsvd_opts* opts, float* q, corrla_timings* timings) {
+  try {
+    return f32_impl(a, nrows, ncols, row_stride, col_stride, omega_rank, n_iter, 0, opts, nullptr, nullptr, nullptr, timings, true, q);
   } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
   catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
 }

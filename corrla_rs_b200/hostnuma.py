@@ -62,12 +62,47 @@ def gpu_numa_node(device: int) -> int | None:
     return node if node >= 0 else None
 
 
+def _topo_cpu_affinity(device: int) -> set[int] | None:
+    """CPU affinity of the GPU from `nvidia-smi topo -m` (the driver's own view; works where sysfs hides numa_node)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        lines = [ln for ln in out.splitlines() if ln.strip()]
+        header = next(ln for ln in lines if "CPU Affinity" in ln)
+        cols = [c.strip() for c in header.split("\t")]
+        idx = cols.index("CPU Affinity")
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if device < len(ids) and ids[device].strip().isdigit():
+                phys = int(ids[device])
+        row = next(ln for ln in lines if ln.startswith(f"GPU{phys}\t") or ln.startswith(f"GPU{phys} "))
+        cells = [c.strip() for c in row.split("\t")]
+        # the header has one leading empty cell for the row labels
+        cell = cells[idx] if len(cells) > idx else ""
+        cpus = _parse_cpulist(cell)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(device: int) -> dict | None:
     """Restrict this process to the CPUs of the NUMA node of GPU `device` (sched_setaffinity); memory touched afterwards
     is placed on that node by the kernel's first-touch policy.  Returns {"node", "cpus"} or None when nothing was done."""
     node = gpu_numa_node(device)
     if node is None:
-        return None
+        cpus = _topo_cpu_affinity(device)
+        if not cpus:
+            return None
+        try:
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if not cpus or cpus == allowed:
+                return {"node": None, "cpus": len(allowed), "changed": False, "source": "nvidia-smi topo"}
+            os.sched_setaffinity(0, cpus)
+            return {"node": None, "cpus": len(cpus), "changed": True, "source": "nvidia-smi topo"}
+        except Exception:
+            return None
     try:
         cpus = _parse_cpulist((Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text())
         allowed = os.sched_getaffinity(0)

@@ -109,6 +109,17 @@ CORRLA_API int corrla_power_iter_f64(const double* a, int64_t nrows, int64_t nco
                           size_t omega_rank, size_t n_iter, const corrla_rsvd_opts* opts, double* q,
                           corrla_timings* timings);
 
+/* T = f32 instantiation of random_svd<T> / power_iter<T> (random_svd.rs:15-18, :63-66 are generic over
+ * T: faer::RealField + Float).  Same arguments with float matrices; opts->omega, when given, is still a double matrix.
+ * The data are widened to f64 once on the device, the f64 engine runs, and the factors are rounded to f32 on the way
+ * out: at least as accurate as an all-f32 evaluation.  No communicator. */
+CORRLA_API int corrla_rsvd_f32(const float* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                    size_t n_rank, size_t n_iter, size_t n_oversamples, const corrla_rsvd_opts* opts,
+                    float* u, float* s, float* vt, corrla_timings* timings);
+CORRLA_API int corrla_power_iter_f32(const float* a, int64_t nrows, int64_t ncols, int64_t row_stride, int64_t col_stride,
+                          size_t omega_rank, size_t n_iter, const corrla_rsvd_opts* opts, float* q,
+                          corrla_timings* timings);
+
 /* res = beta * lhs * rhs (alpha = None: the destination is overwritten); rhs is skinny (column panels of <= 128).
  * lhs is m x kk, rhs is kk x rhs_cols, res is m x rhs_cols; all strided, all on the host or all on the device
  * (on_device).  opts may be NULL (defaults) -- only device/stream/ctx are read. */

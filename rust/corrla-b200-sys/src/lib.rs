@@ -65,6 +65,12 @@ extern "C" {
     pub fn corrla_power_iter_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                                  omega_rank: usize, n_iter: usize, opts: *const corrla_rsvd_opts, q: *mut f64,
                                  timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_rsvd_f32(a: *const f32, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
+                           n_rank: usize, n_iter: usize, n_oversamples: usize, opts: *const corrla_rsvd_opts,
+                           u: *mut f32, s: *mut f32, vt: *mut f32, timings: *mut corrla_timings) -> c_int;
+    pub fn corrla_power_iter_f32(a: *const f32, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
+                                 omega_rank: usize, n_iter: usize, opts: *const corrla_rsvd_opts, q: *mut f32,
+                                 timings: *mut corrla_timings) -> c_int;
     pub fn corrla_rpca_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64, n_rank: usize,
                            opts: *const corrla_rsvd_opts, s: *mut f64, components: *mut f64, means: *mut f64,
                            timings: *mut corrla_timings) -> c_int;

@@ -41,6 +41,25 @@ pub fn random_svd(a_mat: MatRef<f64>, omega_rank: usize, n_iter: usize, n_oversa
     (u, s, vt)
 }
 
+/// `random_svd::<f32>`: the reference function is generic over `T: RealField + Float` (random_svd.rs:63-66).
+pub fn random_svd_f32(a_mat: MatRef<f32>, omega_rank: usize, n_iter: usize, n_oversamples: usize)
+    -> (Mat<f32>, Mat<f32>, Mat<f32>)
+{
+    let (m, n) = (a_mat.nrows(), a_mat.ncols());
+    let mut u = Mat::<f32>::zeros(m, omega_rank);
+    let mut s = Mat::<f32>::zeros(omega_rank, 1);
+    let mut vt = Mat::<f32>::zeros(omega_rank, n);
+    let mut opts = default_opts();
+    opts.seed = rand_seed();
+    let st = unsafe {
+        sys::corrla_rsvd_f32(a_mat.as_ptr(), m as i64, n as i64, a_mat.row_stride() as i64, a_mat.col_stride() as i64,
+                             omega_rank, n_iter, n_oversamples, &opts, u.as_mut().as_ptr_mut(),
+                             s.as_mut().as_ptr_mut(), vt.as_mut().as_ptr_mut(), std::ptr::null_mut())
+    };
+    check(st);
+    (u, s, vt)
+}
+
 /// Replaces random_svd.rs:15-59.
 pub fn power_iter(a_mat: MatRef<f64>, omega_rank: usize, n_iter: usize) -> Mat<f64> {
     let m = a_mat.nrows();

@@ -117,3 +117,29 @@ def test_timings_report_convergence(cb):
     t = cb.last_timings()
     assert t["jacobi_converged"] == 1 and 1 <= t["jacobi_sweeps"] < 30
     assert t["fused_small"] in (0, 1)
+
+
+def test_f32_instantiation(cb):
+    """random_svd::<f32>: float32 in, float32 out (host and device, row- and column-major, fat), against the f64 oracle
+    on the widened data at single-precision tolerances."""
+    import torch
+    from oracle import ref_rsvd
+    rng = np.random.default_rng(8)
+    for shape, order in (((3000, 200), "C"), ((2500, 130), "F"), ((90, 1500), "C")):
+        a32 = rng.standard_normal(shape).astype(np.float32)
+        if order == "F":
+            a32 = np.asfortranarray(a32)
+        k, q, p = 12, 3, 8
+        omega = rng.standard_normal((min(shape), k + p))
+        ref = ref_rsvd.random_svd(np.ascontiguousarray(a32).astype(np.float64), k, q, p, omega=omega)
+        u, s, vt = cb.rsvd_f32(a32, k, q, p, omega=omega)
+        assert u.dtype == np.float32 and s.dtype == np.float32 and vt.dtype == np.float32
+        assert u.shape == (shape[0], k) and s.shape == (k, 1) and vt.shape == (k, shape[1])
+        assert ref_rsvd.sigma_rel_err(ref[1], s.astype(np.float64)) < 1e-6
+        assert ref_rsvd.subspace_sine(ref[0], np.linalg.qr(u.astype(np.float64))[0]) < 1e-5
+        ud, sd, vd = cb.rsvd_f32(torch.from_numpy(np.ascontiguousarray(a32)).cuda(), k, q, p, omega=torch.from_numpy(omega).cuda())
+        assert ud.dtype == torch.float32
+        assert np.max(np.abs(sd.cpu().numpy() - s)) < 1e-5 * s[0, 0]
+        assert ref_rsvd.subspace_sine(ref[0], np.linalg.qr(ud.cpu().numpy().astype(np.float64))[0]) < 1e-5
+    with pytest.raises(TypeError):
+        cb.rsvd_f32(np.zeros((4, 4)), 1, 1, 1)

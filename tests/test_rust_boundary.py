@@ -13,7 +13,7 @@ WRAP = (ROOT / "rust" / "corrla-b200" / "src" / "lib.rs").read_text()
 # C type (normalised) -> the Rust FFI type that has the same ABI
 C2RUST = {
     "int": "c_int", "double": "f64", "int64_t": "i64", "uint64_t": "u64", "size_t": "usize",
-    "const double*": "*const f64", "double*": "*mut f64", "void*": "*mut c_void", "int*": "*mut c_int",
+    "const double*": "*const f64", "double*": "*mut f64", "const float*": "*const f32", "float*": "*mut f32", "void*": "*mut c_void", "int*": "*mut c_int",
     "const char*": "*const c_char", "corrla_ctx*": "*mut corrla_ctx", "corrla_comm*": "*mut corrla_comm",
     "const corrla_comm*": "*const corrla_comm", "corrla_ctx**": "*mut *mut corrla_ctx",
     "corrla_comm**": "*mut *mut corrla_comm", "const corrla_rsvd_opts*": "*const corrla_rsvd_opts",
