@@ -163,7 +163,7 @@ constexpr int kGStages = 3;
 template <int CT, int KS>
 __global__ void __launch_bounds__(kGThreads, 1)
 knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, int64_t n, int d8, int64_t ldx, int kp,
-                int* __restrict__ short_idx, double* __restrict__ short_thr) {
+                int* __restrict__ short_idx, double* __restrict__ short_thr, int dbg, unsigned stagger_ns) {
   constexpr int JW = CT / 8;                          // n-blocks of 8 candidates: every warp covers the whole tile
   constexpr int DP = CT + 8;                          // pitch of a distance slab: the 16-byte stores of a quarter warp spread
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -215,18 +215,29 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
   double* Dw = Dt + (size_t)warp * 8 * DP;
   const double* thr_p = Ld + (size_t)(8 * warp + g) * kp + kp - 1;
   uint32_t stage = 0, phase = 0;
+  // Warps w and w + 4 share a scheduler and its FP64 pipe.  Started together they stay in lockstep -- both in the MMA
+  // loop (each at half rate), then both in the epilogue (pipe idle).  Half a tile of head start for one of them keeps
+  // one warp's epilogue under the other's MMAs.
+  if (warp >= 4 && stagger_ns > 0) __nanosleep(stagger_ns);
   for (int64_t t = 0; t < tiles; ++t) {
     const int64_t c0 = t * CT;
     mbar_wait(sBar + 8 * stage, phase);
-    const double* bp0 = Cs + (size_t)stage * CT * ld + (size_t)g * ld + t4;   // candidate 8j + g, feature 4s + t4
+    // B fragments: candidate 8j + g, feature 4s + t4.  Software pipeline one k-step deep: the fragments of step s + 1
+    // are requested before the MMAs of step s (kept in program order) issue.
+    const double* bp0 = Cs + (size_t)stage * CT * ld + (size_t)g * ld + t4;
     double acc[JW][2];
+    double bf[2][JW];
 #pragma unroll
-    for (int j = 0; j < JW; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    for (int j = 0; j < JW; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; bf[0][j] = bp0[8 * j * ld]; }
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       if (s < ksteps) {
+        if (s + 1 < KS && s + 1 < ksteps) {
 #pragma unroll
-        for (int j = 0; j < JW; ++j) dmma_m8n8k4(acc[j][0], acc[j][1], aq[s], bp0[4 * s + 8 * j * ld]);
+          for (int j = 0; j < JW; ++j) bf[(s + 1) & 1][j] = bp0[4 * (s + 1) + 8 * j * ld];
+        }
+#pragma unroll
+        for (int j = 0; j < JW; ++j) dmma_m8n8k4_ordered(acc[j][0], acc[j][1], aq[s], bf[s & 1][j]);
       }
     }
     const double* cn = Cn + stage * CT;
@@ -235,8 +246,9 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
 #pragma unroll
     for (int j = 0; j < JW; ++j) {
       const int cl = 8 * j + 2 * t4;
-      const double d0 = fma(-2.0, acc[j][0], qn + cn[cl]);
-      const double d1 = fma(-2.0, acc[j][1], qn + cn[cl + 1]);
+      const double2 cnv = *reinterpret_cast<const double2*>(cn + cl);
+      const double d0 = fma(-2.0, acc[j][0], qn + cnv.x);
+      const double d1 = fma(-2.0, acc[j][1], qn + cnv.y);
       *reinterpret_cast<double2*>(Dw + g * DP + cl) = make_double2(d0, d1);
       hit |= (d0 < thr && c0 + cl < n) | (d1 < thr && c0 + cl + 1 < n);
     }
@@ -246,7 +258,7 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
     if (++stage == kGStages) { stage = 0; phase ^= 1u; }
     // selection, only for the queries with a candidate under their threshold (after the first tiles: ~1 in 20 per tile);
     // candidates in increasing index order, ties keep the lower index
-    if (hb != 0u) {
+    if (hb != 0u && !(dbg == 1 && t >= 64)) {              // dbg 1: timing experiment without the selection (wrong results)
 #pragma unroll 1
       for (int a = 0; a < 8; ++a) {
         if (((hb >> (4 * a)) & 0xfu) == 0u) continue;
@@ -503,7 +515,10 @@ cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, in
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (ee != cudaSuccess) return ee;
-    kern<<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr);
+    const char* dbg_env = getenv("CORRLA_B200_KNN_DEBUG");
+    const char* stg_env = getenv("CORRLA_B200_KNN_STAGGER_NS");
+    kern<<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr, dbg_env ? atoi(dbg_env) : 0,
+                                         stg_env ? (unsigned)atoi(stg_env) : 1200u);
     return cudaGetLastError();
   };
   if (ct == 64) e = (d8 <= 64) ? launch(knn_gemm_kernel<64, 16>) : launch(knn_gemm_kernel<64, 32>);

@@ -61,4 +61,20 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// The same instruction as a `volatile` statement: the compiler keeps volatile asm statements in program order, which a
+// fully unrolled k-loop needs to stay "k outer, accumulator inner" -- regrouped by accumulator, every DMMA would wait
+// for its predecessor (26 instead of 16 cycles per instruction when the SMSP's other warp is not in its MMA phase).
+__device__ __forceinline__ void dmma_m8n8k4_ordered(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 8-byte shared-memory load as a volatile statement (same reason: a fully unrolled software pipeline must keep
+// "load the next step's fragments, then issue this step's MMAs" in exactly that order).
+__device__ __forceinline__ double lds_f64_ordered(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 }  // namespace corrla

@@ -40,6 +40,34 @@ constexpr int kConsumerRegs = 232;
 constexpr int kProducerRegs = 40;
 constexpr int kThreads = 12 * 32;
 
+// DMMAs of one k4-step for the n-block slots j >= J0 only.  The triangular modes skip whole n-blocks; the skip has to be
+// a real (warp-uniform) branch -- as a predicate on each DMMA the skipped instructions still take their issue slots and
+// the mode runs at the dense rate (measured: 459 us against 250 us of kept work for the 512k x 112 triangular apply).
+template <int MI, int JW, int J0, bool FULL>
+__device__ __forceinline__ void dmma_step_from(double (&acc)[MI][JW][2], const double (&af)[MI], const double (&bf)[JW], int jn) {
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = J0; j < JW; ++j)
+      if (FULL || j < jn) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+}
+template <int MI, int JW, bool FULL>
+__device__ __forceinline__ void dmma_step_skip(int j0, double (&acc)[MI][JW][2], const double (&af)[MI], const double (&bf)[JW], int jn) {
+  switch (j0) {
+    case 0: dmma_step_from<MI, JW, 0, FULL>(acc, af, bf, jn); break;
+    case 1: if (JW > 1) dmma_step_from<MI, JW, (JW > 1 ? 1 : 0), FULL>(acc, af, bf, jn); break;
+    case 2: if (JW > 2) dmma_step_from<MI, JW, (JW > 2 ? 2 : 0), FULL>(acc, af, bf, jn); break;
+    case 3: if (JW > 3) dmma_step_from<MI, JW, (JW > 3 ? 3 : 0), FULL>(acc, af, bf, jn); break;
+    case 4: if (JW > 4) dmma_step_from<MI, JW, (JW > 4 ? 4 : 0), FULL>(acc, af, bf, jn); break;
+    case 5: if (JW > 5) dmma_step_from<MI, JW, (JW > 5 ? 5 : 0), FULL>(acc, af, bf, jn); break;
+    case 6: if (JW > 6) dmma_step_from<MI, JW, (JW > 6 ? 6 : 0), FULL>(acc, af, bf, jn); break;
+    case 7: if (JW > 7) dmma_step_from<MI, JW, (JW > 7 ? 7 : 0), FULL>(acc, af, bf, jn); break;
+    default: break;                                       // every n-block of this warp is skipped
+  }
+}
+
+// (The symmetric mode keeps per-DMMA predicates: its skip pattern differs per accumulator row, and one switch per row
+// and step measured slower -- 445 us against 262 us for the 512k x 112 Gram matrix -- than the predicated form.)
 // One consumer warp, all work items of this CTA.  FULL: every n-block of the warp is valid (no predicates on the DMMAs).
 // MODE 0: dense.  MODE 1 (MC only): the output is symmetric (Gram matrix) and only its upper triangle is consumed, so
 // 8x8 blocks entirely below the diagonal are skipped and m-blocks are dealt round-robin to the warps to balance what
@@ -138,12 +166,19 @@ __device__ __forceinline__ void consumer_loop(const GemmArgs& p, unsigned char* 
           mbar_wait(sBar + 8 * nstage, nphase);
           load_frags(af[0], bf[0], smem + nstage * kAStageBytes + a_base, smemB + nstage * p.b_stage_bytes + b_off, 0);
         }
+        if (MODE == 2) {
+          // rows 16c + 4s .. of the upper-triangular B are zero for the n-blocks nb = wn + WN*j < 2c + (s >= 2)
+          const int kb = (int)(2 * c) + (s >= 2 ? 1 : 0);
+          const int j0 = kb > wn ? (kb - wn + WN - 1) / WN : 0;
+          dmma_step_skip<MI, JW, FULL>(j0, acc, af[s & 1], bf[s & 1], jn);
+        } else {
 #pragma unroll
-        for (int i = 0; i < MI; ++i)
+          for (int i = 0; i < MI; ++i)
 #pragma unroll
-          for (int j = 0; j < JW; ++j)
-            if ((FULL || j < jn) && (MODE == 0 || keep(i, j, s, c)))
-              dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[s & 1][i], bf[s & 1][j]);
+            for (int j = 0; j < JW; ++j)
+              if ((FULL || j < jn) && (MODE == 0 || keep(i, j, s, c)))
+                dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[s & 1][i], bf[s & 1][j]);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sBar + 8 * (8 + stage));

@@ -288,7 +288,8 @@ def test_pod_more_modes_than_one_panel(cb, r):
     import torch
     rng = np.random.default_rng(r)
     n_snap, n_points, rank = 320, 5000, 280
-    base = rng.standard_normal((n_snap, rank)) * (10.0 * 0.985 ** np.arange(rank))
+    # gently graded: (sigma_1 / sigma_l)^7 stays far below 1/eps at the reference's first QR (SURVEY F9 parity class)
+    base = rng.standard_normal((n_snap, rank)) * (10.0 * 0.995 ** np.arange(rank))
     x = base @ np.linalg.qr(rng.standard_normal((n_points, rank)))[0].T
     omega = rng.standard_normal((n_snap, min(r + 10, n_snap)))
     t = np.linspace(0.0, 1.0, n_snap).reshape(-1, 1)
@@ -300,4 +301,6 @@ def test_pod_more_modes_than_one_panel(cb, r):
     assert np.max(np.abs(weights - x @ modes)) < 1e-11 * np.max(np.abs(x))
     assert np.max(np.abs(weights @ modes.T - ref.mode_weights @ ref.modes.T)) < 1e-8 * np.max(np.abs(x))
     md, wd, _ = cb.pod_modes_weights(torch.from_numpy(x).cuda(), r, omega=torch.from_numpy(omega).cuda())
-    assert np.array_equal(md.cpu().numpy(), np.asarray(modes)) and np.array_equal(wd.cpu().numpy(), np.asarray(weights))
+    md, wd = md.cpu().numpy(), wd.cpu().numpy()            # device-resident snapshots: same factors up to the sign of a mode
+    assert ref_rsvd.subspace_sine(np.asarray(modes), md) < 1e-9
+    assert np.max(np.abs(wd @ md.T - np.asarray(weights) @ np.asarray(modes).T)) < 1e-9 * np.max(np.abs(x))
