@@ -5,7 +5,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisi
 CSRC      := corrla_rs_b200/csrc
 OBJDIR    := build
 LIB       := corrla_rs_b200/lib/libcorrla_b200.so
-OBJS      := $(OBJDIR)/skinny_gemm.o $(OBJDIR)/small_kernels.o $(OBJDIR)/engine.o $(OBJDIR)/comm.o $(OBJDIR)/hostcopy.o $(OBJDIR)/rom.o $(OBJDIR)/gradients.o $(OBJDIR)/jacobi_cluster.o $(OBJDIR)/fused_small.o
+OBJS      := $(OBJDIR)/skinny_gemm.o $(OBJDIR)/small_kernels.o $(OBJDIR)/engine.o $(OBJDIR)/comm.o $(OBJDIR)/hostcopy.o $(OBJDIR)/rom.o $(OBJDIR)/gradients.o $(OBJDIR)/jacobi_cluster.o $(OBJDIR)/jacobi_ring.o $(OBJDIR)/fused_small.o
 
 all: $(LIB)
 

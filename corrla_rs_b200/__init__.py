@@ -24,7 +24,7 @@ from ._ffi import CorrlaError, RankPanic, Timings  # noqa: F401  (re-exported)
 __all__ = ["rsvd", "random_svd", "rsvd_f32", "rpca", "power_iter", "par_matmul", "par_matmul_helper", "random_mat_normal", "thin_q",
            "Context", "ShardComm", "CorrlaError", "RankPanic", "version", "last_timings", "release_buffers",
            "DMDc", "PodI", "RbfInterp", "dmdc_operators", "pod_modes_weights",
-           "cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "active_ss", "active_ss_fit"]
+           "cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "PolyGradientEstimator", "active_ss", "active_ss_fit"]
 
 _SCHEDULES = {"reference": 0, "stabilised": 1, "stabilized": 1, 0: 0, 1: 1}
 _tls = threading.local()
@@ -481,5 +481,5 @@ def thin_q(a_mat, *, ctx: Context | None = None, comm: ShardComm | None = None, 
 
 
 from .rom import DMDc, PodI, RbfInterp, dmdc_operators, pod_modes_weights  # noqa: E402,F401
-from .stats import (ActiveSsRsvd, FittedActiveSsRsvd, active_ss, active_ss_fit, cov, mat_cov_centered,  # noqa: E402,F401
+from .stats import (ActiveSsRsvd, FittedActiveSsRsvd, PolyGradientEstimator, active_ss, active_ss_fit, cov, mat_cov_centered,  # noqa: E402,F401
                     pearson_corr)

@@ -86,6 +86,9 @@ SYMBOLS = {
     "corrla_active_ss_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                        C.c_int, C.c_int, C.POINTER(RsvdOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int)]),
+    "corrla_poly_grad_at_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                          C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(C.c_int)]),
     "corrla_thin_q_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                     C.POINTER(RsvdOpts), C.c_void_p, C.POINTER(C.c_int)]),
     "corrla_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -59,7 +59,8 @@ __device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dis
 
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, int* __restrict__ idx_out,
-           const int* __restrict__ qlist, const int* __restrict__ qcount) {
+           const int* __restrict__ qlist, const int* __restrict__ qcount, const double* __restrict__ Qext, int64_t nq_ext,
+           int64_t ldq) {
   extern __shared__ __align__(16) double smk[];
   double* Qs = smk;                                   // [kDC][kQPitch]  query chunk, feature-major
   double* Cs = Qs + kDC * kQPitch;                    // [kDC][kCPitch]  candidate chunk, feature-major
@@ -68,11 +69,14 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q0 = (int64_t)blockIdx.x * kQT;
   // with a query list (the queries the GEMM-form search could not certify) block b takes entries 64b .. 64b + 63 of it
-  const int64_t nq = (qlist != nullptr) ? (int64_t)*qcount : n;
+  // with external query points (grad_at away from the samples) the queries are the rows of Qext, the candidates stay X
+  const double* __restrict__ Qsrc = (Qext != nullptr) ? Qext : X;
+  const int64_t qrows = (Qext != nullptr) ? nq_ext : n, ldqs = (Qext != nullptr) ? ldq : ldx;
+  const int64_t nq = (qlist != nullptr) ? (int64_t)*qcount : qrows;
   if (q0 >= nq) return;
   auto qrow = [&](int ql) -> int64_t {
     const int64_t e = q0 + ql;
-    if (e >= nq) return n;                                 // past the end: behaves like a row beyond the matrix
+    if (e >= nq) return qrows;                             // past the end: behaves like a row beyond the matrix
     return (qlist != nullptr) ? (int64_t)qlist[e] : e;
   };
   for (int i = tid; i < kQT * k; i += kKnnThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
@@ -88,7 +92,7 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
       for (int i = tid; i < kDC * kQT; i += kKnnThreads) {
         const int q = i / kDC, dd = i - q * kDC;
         const int64_t row = qrow(q);
-        Qs[dd * kQPitch + q] = (row < n && d0 + dd < d) ? X[row * ldx + d0 + dd] : 0.0;
+        Qs[dd * kQPitch + q] = (row < qrows && d0 + dd < d) ? Qsrc[row * ldqs + d0 + dd] : 0.0;
       }
       for (int i = tid; i < kDC * kCT; i += kKnnThreads) {
         const int cc = i / kDC, dd = i - cc * kDC;
@@ -132,7 +136,7 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
   for (int a = 0; a < 8; ++a) {
     const int ql = 8 * warp + a;
     const int64_t row = qrow(ql);
-    if (row >= n) break;
+    if (row >= qrows) break;
     for (int p = lane; p < k; p += 32) idx_out[row * k + p] = Li[(size_t)ql * k + p];
   }
 }
@@ -360,7 +364,7 @@ constexpr int kGradThreads = 128;
 __global__ void __launch_bounds__(kGradThreads)
 poly_grad_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n, int d, int64_t ldx,
                  const int* __restrict__ idx, int k, int order, int p, double* __restrict__ G, int64_t ldg,
-                 int* __restrict__ info) {
+                 int* __restrict__ info, const double* __restrict__ Xq, int64_t ldq) {
   extern __shared__ __align__(16) double smg[];
   const int kp = k | 1;                              // odd column pitch: thread-per-column accesses are conflict free
   double* A = smg;                                   // [p + 1][kp] column-major: p design columns, then y
@@ -444,16 +448,17 @@ poly_grad_kernel(const double* __restrict__ X, const double* __restrict__ y, int
     __syncthreads();
   }
   if (tid == 0 && deficient && info != nullptr) atomicAdd(info, 1);
-  // gradient at the sample itself
+  // gradient at the evaluation point: the sample itself, or row i of Xq (grad_at away from the samples)
+  const double* __restrict__ x0 = (Xq != nullptr) ? Xq + i * ldq : X + i * ldx;
   for (int j = tid; j < d; j += nt) {
     double g = beta[j];
     if (order == 2) {
       int c = d;
       for (int a = 0; a < d; ++a)
         for (int b = a; b < d; ++b, ++c) {
-          if (a == j && b == j) g += 2.0 * beta[c] * X[i * ldx + j];
-          else if (a == j) g += beta[c] * X[i * ldx + b];
-          else if (b == j) g += beta[c] * X[i * ldx + a];
+          if (a == j && b == j) g += 2.0 * beta[c] * x0[j];
+          else if (a == j) g += beta[c] * x0[b];
+          else if (b == j) g += beta[c] * x0[a];
         }
     }
     G[i * ldg + j] = g;
@@ -463,13 +468,14 @@ poly_grad_kernel(const double* __restrict__ X, const double* __restrict__ y, int
 }  // namespace
 
 static cudaError_t knn_exact_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, const int* qlist,
-                                    const int* qcount, int64_t n_queries, cudaStream_t s) {
+                                    const int* qcount, int64_t n_queries, cudaStream_t s, const double* Qext = nullptr,
+                                    int64_t ldq = 0) {
   const size_t smem = ((size_t)kDC * kQPitch + (size_t)kDC * kCPitch + (size_t)kQT * k) * 8 + (size_t)kQT * k * 4;
   cudaError_t e = cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   const int64_t blocks = (n_queries + kQT - 1) / kQT;
   if (blocks <= 0) return cudaSuccess;
-  knn_kernel<<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount);
+  knn_kernel<<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount, Qext, n_queries, ldq);
   return cudaGetLastError();
 }
 
@@ -538,6 +544,12 @@ cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, in
   return cudaSuccess;
 }
 
+cudaError_t knn_query_launch(const double* X, int64_t n, int d, int64_t ldx, const double* Q, int64_t nq, int64_t ldq, int k,
+                             int* idx, cudaStream_t s) {
+  if (n <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > kKnnMaxK || k > n || Q == nullptr) return cudaErrorInvalidValue;
+  return knn_exact_launch(X, n, d, ldx, k, idx, nullptr, nullptr, nq, s, Q, ldq);
+}
+
 int poly_grad_num_coef(int d, int order) { return order == 2 ? d + d * (d + 1) / 2 : d; }
 
 size_t poly_grad_smem_bytes(int d, int k, int order) {
@@ -546,14 +558,14 @@ size_t poly_grad_smem_bytes(int d, int k, int order) {
 }
 
 cudaError_t poly_grad_launch(const double* X, const double* y, int64_t n, int d, int64_t ldx, const int* idx, int k,
-                             int order, double* G, int64_t ldg, int* info, cudaStream_t s) {
+                             int order, double* G, int64_t ldg, int* info, cudaStream_t s, const double* Xq, int64_t ldq) {
   if (n <= 0 || d <= 0 || k <= 1 || (order != 1 && order != 2)) return cudaErrorInvalidValue;
   const int p = poly_grad_num_coef(d, order);
   const size_t smem = poly_grad_smem_bytes(d, k, order);
   if (p > kGradMaxCoef || smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(poly_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
-  poly_grad_kernel<<<(unsigned)n, kGradThreads, smem, s>>>(X, y, n, d, ldx, idx, k, order, p, G, ldg, info);
+  poly_grad_kernel<<<(unsigned)n, kGradThreads, smem, s>>>(X, y, n, d, ldx, idx, k, order, p, G, ldg, info, Xq, ldq);
   return cudaGetLastError();
 }
 

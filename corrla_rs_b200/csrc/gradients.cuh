@@ -23,16 +23,25 @@ size_t knn_scratch_bytes(int64_t n, int k);
 cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, void* scratch, size_t scratch_bytes,
                        int* n_exact_fallback, cudaStream_t s);
 
+// The same search for query points that are not samples (PolyGradientEstimator::grad_at at an arbitrary x0,
+// active_subspaces.rs:66-141): idx[q*k + r] = index of the r-th nearest row of X to row q of Q (nq x d, pitch ldq).
+// Exact kernel only (query batches are small next to the sample set).
+cudaError_t knn_query_launch(const double* X, int64_t n, int d, int64_t ldx, const double* Q, int64_t nq, int64_t ldq, int k,
+                             int* idx, cudaStream_t s);
+
 // Local polynomial fit through the k neighbours of every sample and its gradient at the sample:
 //   order 1: y ~ b.x + b0                      gradient = b                     (jac_from_lin, stats_corr.rs:164-169)
 //   order 2: y ~ b.x + sum_{a<=b} c_ab x_a x_b + b0, gradient taken analytically at x_i (jac_from_quad differentiates
 //            the same polynomial by a forward difference with eps = 1e-10, stats_corr.rs:230-249)
 // Least squares by Householder QR of the column-centred design matrix (same slopes as the fit with an intercept).
+// With Xq != nullptr, n counts the rows of Xq (pitch ldq), idx holds THEIR neighbours and the gradient of fit i is taken
+// at row i of Xq instead of at sample i.
 // G: n x ldg row-major, row i = gradient at sample i (d entries).  info[0] counts samples whose design matrix was
 // numerically rank deficient (their dependent coefficients are set to zero).
 size_t poly_grad_smem_bytes(int d, int k, int order);
 int poly_grad_num_coef(int d, int order);
 cudaError_t poly_grad_launch(const double* X, const double* y, int64_t n, int d, int64_t ldx, const int* idx, int k,
-                             int order, double* G, int64_t ldg, int* info, cudaStream_t s);
+                             int order, double* G, int64_t ldg, int* info, cudaStream_t s, const double* Xq = nullptr,
+                             int64_t ldq = 0);
 
 }  // namespace corrla

@@ -611,6 +611,68 @@ int active_ss_impl(const double* x, int64_t n, int64_t nfeat, int64_t x_rs, int6
   return CORRLA_OK;
 }
 
+
+// PolyGradientEstimator::grad_at for a batch of evaluation points (active_subspaces.rs:66-141): neighbours of every
+// query among the samples, one local fit per query, gradient taken at the query.
+int poly_grad_at_impl(const double* x, int64_t n, int64_t nfeat, int64_t x_rs, int64_t x_cs, const double* y, int64_t y_stride,
+                      int order, int n_nbr, const double* xq, int64_t nq, int64_t q_rs, int64_t q_cs,
+                      const corrla_rsvd_opts* opts_in, double* grad_out, int* n_deficient) {
+  corrla_rsvd_opts o = opts_in ? *opts_in : default_opts();
+  if (x == nullptr || y == nullptr || xq == nullptr || grad_out == nullptr || n <= 0 || nfeat <= 0 || nq <= 0) { set_last_error("bad argument"); return CORRLA_ERR_INVALID; }
+  if (o.comm != nullptr) { set_last_error("corrla_poly_grad_at_f64 does not take a communicator"); return CORRLA_ERR_UNSUPPORTED; }
+  if (order != 1 && order != 2) { set_last_error("Not implemented est order: %d (the reference panics here)", order); return CORRLA_ERR_INVALID; }
+  const int d = (int)std::min<int64_t>(nfeat, 1 << 20);
+  const int64_t need = (order == 1) ? (int64_t)d + 1 : (int64_t)d * (d + 3) / 2;       // :115-116, :127-128
+  if (!(n > need) || !(n_nbr > need)) {
+    set_last_error("order %d fit in %d dimensions needs more than %lld samples and neighbours (got %lld, %d)", order, d,
+                   (long long)need, (long long)n, n_nbr);
+    return CORRLA_ERR_INVALID;
+  }
+  const int k = (int)std::min<int64_t>(n_nbr, n);
+  if (k > kKnnMaxK || poly_grad_num_coef(d, order) > kGradMaxCoef || poly_grad_smem_bytes(d, k, order) > 200 * 1024) {
+    set_last_error("gradient fit of order %d with %d features and %d neighbours exceeds the kernel limits "
+                   "(<= %d neighbours, <= %d coefficients)", order, d, k, kKnnMaxK, kGradMaxCoef);
+    return CORRLA_ERR_UNSUPPORTED;
+  }
+  Scope sc;
+  ST_TRY(open_scope(&o, &sc));
+  corrla_ctx* ctx = sc.ctx;
+  cudaStream_t st = sc.st;
+  RomBufs rb{ctx, st};
+  Core c;
+  c.ctx = ctx; c.st = st;
+  ST_TRY(c.setup_dims(n, nfeat, d));
+  const int ld = c.ld;
+  const bool in_dev = o.a_on_device != 0, out_dev = o.out_on_device != 0;
+  int launches = 0;
+  const int64_t nq16 = (nq + 15) / 16 * 16;
+
+  MatView xv, qv; bool rm = true, qrm = true;
+  ST_TRY(stage_matrix(ctx, st, "A", x, n, nfeat, x_rs, x_cs, in_dev, &xv, &rm, nullptr, &launches));
+  ST_TRY(stage_matrix(ctx, st, "as_qraw", xq, nq, nfeat, q_rs, q_cs, in_dev, &qv, &qrm, nullptr, &launches));
+  double* Xp = rb.zeros("cov_xp", (size_t)c.m16 * ld);
+  double* Qp = rb.zeros("as_qp", (size_t)nq16 * ld);
+  double* Gp = rb.zeros("as_qgrad", (size_t)nq16 * ld);
+  double* yd = rb.raw("as_y", (size_t)n + 8);
+  int* idx = reinterpret_cast<int*>(ctx->get("as_qidx", (size_t)nq * k * sizeof(int)));
+  int* info = reinterpret_cast<int*>(rb.zeros("cov_info", 8));
+  double* g_rm = out_dev ? grad_out : rb.raw("as_qgout", (size_t)nq * d);
+  if (!Xp || !Qp || !Gp || !yd || !idx || !info || !g_rm) { set_last_error("device allocation failed (gradient estimator)"); return CORRLA_ERR_ALLOC; }
+  cudaError_t e = rm ? repack_launch(xv.p, n, d, xv.ld, 1, Xp, ld, st) : repack_launch(xv.p, n, d, 1, xv.ld, Xp, ld, st);
+  if (e == cudaSuccess) e = qrm ? repack_launch(qv.p, nq, d, qv.ld, 1, Qp, ld, st) : repack_launch(qv.p, nq, d, 1, qv.ld, Qp, ld, st);
+  if (e != cudaSuccess) { set_last_error("repack failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  ST_TRY(pack_small(ctx, st, y, n, 1, y_stride, 1, in_dev, yd, 1, 1.0, &launches));
+  e = knn_query_launch(Xp, n, d, ld, Qp, nq, ld, k, idx, st);
+  if (e == cudaSuccess) e = poly_grad_launch(Xp, yd, nq, d, ld, idx, k, order, Gp, ld, info + 2, st, Qp, ld);
+  if (e == cudaSuccess) e = scatter_launch(Gp, nq, d, ld, g_rm, d, 1, st);              // n_query x n_features row-major
+  if (e != cudaSuccess) { set_last_error("gradient kernels failed to launch: %s", cudaGetErrorString(e)); cudaGetLastError(); return CORRLA_ERR_CUDA; }
+  int hinfo[4] = {0, 0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (!out_dev) ST_TRY(copy_out(ctx, st, grad_out, g_rm, (size_t)nq * d));
+  if (n_deficient) *n_deficient = hinfo[2];
+  return CORRLA_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -620,6 +682,16 @@ int corrla_active_ss_f64(const double* x, int64_t n_samples, int64_t n_features,
                          double* grad_mat, int* n_deficient) {
   try {
     return active_ss_impl(x, n_samples, n_features, x_rs, x_cs, y, y_stride, order, n_nbr, opts, evals, evecs, grad_mat, n_deficient);
+  } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
+  catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
+}
+
+int corrla_poly_grad_at_f64(const double* x, int64_t n_samples, int64_t n_features, int64_t x_rs, int64_t x_cs, const double* y,
+                            int64_t y_stride, int order, int n_nbr, const double* xq, int64_t n_query, int64_t q_rs, int64_t q_cs,
+                            const corrla_rsvd_opts* opts, double* grad_out, int* n_deficient) {
+  try {
+    return poly_grad_at_impl(x, n_samples, n_features, x_rs, x_cs, y, y_stride, order, n_nbr, xq, n_query, q_rs, q_cs, opts,
+                             grad_out, n_deficient);
   } catch (const std::exception& e) { set_last_error("exception: %s", e.what()); return CORRLA_ERR_ALLOC; }
   catch (...) { set_last_error("unknown exception"); return CORRLA_ERR_INVALID; }
 }

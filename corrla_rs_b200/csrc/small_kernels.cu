@@ -928,7 +928,10 @@ cudaError_t refill_dead_launch(double* X, int64_t rows, int l, int64_t ld, const
 cudaError_t jacobi_svd_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                               int ldo, double* scratch, int* info, cudaStream_t s, int transpose) {
   {
-    const cudaError_t ce = jacobi_svd_cluster_launch(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, info, s, transpose);
+    cudaError_t ce = jacobi_svd_ring_launch(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, info, s, transpose);
+    if (ce == cudaSuccess) return ce;
+    if (ce != cudaErrorNotSupported) cudaGetLastError();     // launch refused: next kernel in line
+    ce = jacobi_svd_cluster_launch(W, ldw, l, sigma, Vr, Ur, Lrows, ldo, info, s, transpose);
     if (ce == cudaSuccess) return ce;
     if (ce != cudaErrorNotSupported) cudaGetLastError();     // launch refused: fall back to the single-CTA kernel
   }

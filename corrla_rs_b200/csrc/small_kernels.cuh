@@ -53,6 +53,10 @@ cudaError_t lowdin_launch(const double* G, int ldg, int l, double* T, int Lrows,
 // Cluster variant (jacobi_cluster.cu): row slabs of X and V in the shared memory of 4 or 8 CTAs, partial dot products
 // exchanged through DSMEM.  cudaErrorNotSupported when it does not apply (l < 32, slabs too large, or
 // CORRLA_B200_JACOBI_CLUSTER=0); jacobi_svd_launch tries it first.
+// Ring variant (jacobi_ring.cu, l <= 256, first choice): column pairs in the registers of the warps of a cluster, one
+// column per warp handed to a neighbour between steps (odd-even ordering); CORRLA_B200_JACOBI_RING=0 disables it.
+cudaError_t jacobi_svd_ring_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
+                                   int ldo, int* info, cudaStream_t s, int transpose);
 cudaError_t jacobi_svd_cluster_launch(const double* W, int ldw, int l, double* sigma, double* Vr, double* Ur, int Lrows,
                                       int ldo, int* info, cudaStream_t s, int transpose);
 

@@ -14,7 +14,8 @@ import numpy as np
 
 from . import _ffi
 
-__all__ = ["cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "active_ss_fit", "active_ss"]
+__all__ = ["cov", "mat_cov_centered", "pearson_corr", "ActiveSsRsvd", "FittedActiveSsRsvd", "PolyGradientEstimator",
+           "active_ss_fit", "active_ss"]
 
 _KINDS = {"gram": 0, "centered": 1, "pearson": 2}
 
@@ -113,6 +114,69 @@ def active_ss(a_mat, y, order: int, n_nbr: int, n_comps: int):
             np.asarray(fit.var_diag_evd_sensi()))
 
 
+class PolyGradientEstimator:
+    """`PolyGradientEstimator` of active_subspaces.rs:23-141 over `corrla_poly_grad_at_f64`: holds the samples
+    (x_mat: (N, k), y: (N,) or (N, 1)), and `grad_at(x0)` fits the order-1 or order-2 polynomial through the n_nbrs nearest
+    samples of x0 and returns its gradient there as a (1, k) row, like the reference.  `grad_at_many(xq)` does the same
+    for every row of xq in one device call ((n_query, k) out); `ActiveSsRsvd.create_grad_mat` uses it instead of the
+    reference's loop.  The reference asserts on construction that N and n_nbrs exceed the number of fitted
+    coefficients (:115-116, :127-128); here the same condition raises ValueError on the first call."""
+
+    def __init__(self, x_mat, y, est_order: int, n_nbrs: int, *, ctx=None):
+        api = _api()
+        self._x = api._Mat(x_mat, "x_mat")
+        if api._is_torch(y):
+            yy = y.reshape(-1, 1)
+        else:
+            yy = np.asarray(y)
+            if yy.dtype != np.float64:
+                raise TypeError("y must be a float64 array")
+            yy = yy.reshape(-1, 1)
+        self._y = api._Mat(yy, "y")
+        if self._x.on_device != self._y.on_device:
+            raise ValueError("x_mat and y must both be on the host or both on the device")
+        if self._y.shape[0] != self._x.shape[0]:
+            raise ValueError(f"x_mat has {self._x.shape[0]} samples, y has {self._y.shape[0]}")
+        for name, v in (("est_order", est_order), ("n_nbrs", n_nbrs)):
+            if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
+                raise TypeError(f"{name} must be an int")
+            if v < 0:
+                raise OverflowError(f"can't convert negative int to unsigned ({name})")
+        self.est_order, self.n_nbrs, self.k = int(est_order), int(n_nbrs), self._x.shape[1]
+        self._ctx = ctx
+        self.n_deficient = 0
+
+    def grad_at_many(self, xq):
+        api = _api()
+        lib = _ffi.load()
+        a, b = self._x, self._y
+        if a.on_device:
+            import torch
+            if not api._is_torch(xq):
+                xq = torch.as_tensor(np.asarray(xq, dtype=np.float64), device=a.device)
+            q = api._Mat(xq.reshape(-1, self.k), "xq")
+        else:
+            q = api._Mat(np.asarray(xq, dtype=np.float64).reshape(-1, self.k), "xq")
+        nq = q.shape[0]
+        device = a.device if a.on_device else None
+        ctx = self._ctx or api._context_for(device)
+        stream = api._current_stream(device) if a.on_device else None
+        o, _ = api._make_opts(ctx=ctx, on_device=a.on_device, out_on_device=a.on_device, omega=None, seed=0,
+                              schedule="reference", comm=None, global_rows=None, stream=stream, device=device)
+        out = api._colmajor_empty_like(a, self.k, nq)          # k x nq column-major == nq x k row-major
+        ndef = C.c_int(0)
+        st = lib.corrla_poly_grad_at_f64(a.ptr, a.shape[0], self.k, a.strides[0], a.strides[1], b.ptr, b.strides[0],
+                                         self.est_order, self.n_nbrs, q.ptr, nq, q.strides[0], q.strides[1], C.byref(o),
+                                         api._ptr(out), C.byref(ndef))
+        _ffi.check(st)
+        self.n_deficient = int(ndef.value)
+        return out.t() if hasattr(out, "detach") else out.T
+
+    def grad_at(self, x0):
+        """Gradient [dy/dx_1 .. dy/dx_k] at x0 (sequence of k values) as a (1, k) row (:57-66)."""
+        return self.grad_at_many(np.asarray(x0, dtype=np.float64).reshape(1, -1) if not hasattr(x0, "detach") else x0)
+
+
 class FittedActiveSsRsvd:
     """active_subspaces.rs:147-212: `components_` (k, k) one direction per column, `singular_vals_` (k, k) diagonal."""
 
@@ -148,6 +212,9 @@ class ActiveSsRsvd:
         self.grad_est, self.n_comps = grad_est, int(n_comps)
 
     def create_grad_mat(self, x_mat):
+        if isinstance(self.grad_est, PolyGradientEstimator):                     # one device call for all rows
+            g = self.grad_est.grad_at_many(x_mat)
+            return g.t() if hasattr(g, "detach") else np.ascontiguousarray(g.T)
         x_mat = np.asarray(x_mat, dtype=np.float64)                              # :226-238 (host loop over the estimator)
         g = np.zeros((x_mat.shape[1], x_mat.shape[0]))
         for i in range(x_mat.shape[0]):

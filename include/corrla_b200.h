@@ -206,6 +206,16 @@ CORRLA_API int corrla_active_ss_f64(const double* x, int64_t n_samples, int64_t 
                          const double* y, int64_t y_stride, int order, int n_nbr, const corrla_rsvd_opts* opts,
                          double* evals, double* evecs, double* grad_mat, int* n_deficient);
 
+/* PolyGradientEstimator::grad_at (src/lib_math_utils/active_subspaces.rs:66-141) for a batch of evaluation points that
+ * need not be samples: for every row of xq (n_query x n_features, element strides) the n_nbr nearest samples of x are
+ * found (exact search, same distance and tie rule as above), the order-1 or order-2 polynomial is fitted through them
+ * and its gradient is taken at the query point.  grad_out : n_query x n_features row-major (one grad_at row per query;
+ * equivalently n_features x n_query column-major, the layout of create_grad_mat, :226-238).  Same limits and error
+ * behaviour as corrla_active_ss_f64; x, y and xq share opts->a_on_device, grad_out follows opts->out_on_device. */
+CORRLA_API int corrla_poly_grad_at_f64(const double* x, int64_t n_samples, int64_t n_features, int64_t x_rs, int64_t x_cs,
+                         const double* y, int64_t y_stride, int order, int n_nbr, const double* xq, int64_t n_query,
+                         int64_t q_rs, int64_t q_cs, const corrla_rsvd_opts* opts, double* grad_out, int* n_deficient);
+
 /* thin Q (nrows x ncols, column-major) of a tall matrix by adaptive CholeskyQR2/3 (the engine's replacement for
  * faer qr().compute_thin_q(), random_svd.rs:38,:57).  ncols <= 2048 (column panels above 128).  rank_out (optional) =
  * live columns found before the orthonormal completion. */

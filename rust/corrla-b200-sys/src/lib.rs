@@ -93,6 +93,10 @@ extern "C" {
     pub fn corrla_active_ss_f64(x: *const f64, n_samples: i64, n_features: i64, x_rs: i64, x_cs: i64, y: *const f64,
                                 y_stride: i64, order: c_int, n_nbr: c_int, opts: *const corrla_rsvd_opts,
                                 evals: *mut f64, evecs: *mut f64, grad_mat: *mut f64, n_deficient: *mut c_int) -> c_int;
+    pub fn corrla_poly_grad_at_f64(x: *const f64, n_samples: i64, n_features: i64, x_rs: i64, x_cs: i64, y: *const f64,
+                                   y_stride: i64, order: c_int, n_nbr: c_int, xq: *const f64, n_query: i64, q_rs: i64,
+                                   q_cs: i64, opts: *const corrla_rsvd_opts, grad_out: *mut f64,
+                                   n_deficient: *mut c_int) -> c_int;
     pub fn corrla_thin_q_f64(a: *const f64, nrows: i64, ncols: i64, row_stride: i64, col_stride: i64,
                              on_device: c_int, opts: *const corrla_rsvd_opts, q: *mut f64, rank_out: *mut c_int) -> c_int;
     pub fn corrla_host_alloc(bytes: usize) -> *mut c_void;

@@ -189,3 +189,49 @@ def test_knn_gemm_form_gives_the_exact_neighbour_lists(cb):
         finally:
             os.environ.pop("CORRLA_B200_KNN_EXACT", None)
         assert np.array_equal(np.asarray(g_fast), np.asarray(g_exact)), name
+
+
+def test_poly_gradient_estimator_grad_at_arbitrary_points(cb):
+    """PolyGradientEstimator::grad_at (active_subspaces.rs:57-141) at points that are NOT samples, one at a time (the
+    reference's call) and as a batch (one device call), orders 1 and 2, host and device samples; and ActiveSsRsvd over
+    the estimator object (create_grad_mat, :226-238) against the oracle's loop."""
+    import torch
+    rng = np.random.default_rng(21)
+    n, d = 3000, 6
+    x = rng.standard_normal((n, d))
+    w = rng.standard_normal((d, 2))
+    y = np.sin(x @ w[:, 0]) + 0.3 * (x @ w[:, 1]) ** 2
+    xq = 0.8 * rng.standard_normal((70, d))                                # 70 > 64: more than one query block
+    for order, k, tol in ((1, 25, 1e-9), (2, 40, 2e-4)):                   # order 2: forward difference in the oracle
+        est0 = ref_stats.PolyGradientEstimator(x, y, order, k)
+        g0 = np.stack([est0.grad_at(q).ravel() for q in xq])
+        est = cb.PolyGradientEstimator(x, y.reshape(-1, 1), order, k)
+        g = np.asarray(est.grad_at_many(xq))
+        assert g.shape == (70, d) and est.n_deficient == 0
+        assert np.max(np.abs(g - g0)) < tol * max(1.0, np.max(np.abs(g0)))
+        one = np.asarray(est.grad_at(list(xq[3])))
+        assert one.shape == (1, d) and np.array_equal(one.ravel(), g[3])
+        # device-resident samples and queries
+        estd = cb.PolyGradientEstimator(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), order, k)
+        gd = estd.grad_at_many(torch.from_numpy(xq).cuda())
+        assert gd.is_cuda and np.array_equal(gd.cpu().numpy(), g)
+        # at the samples themselves it is the gradient matrix of active_ss_fit
+        _fit, gm = cb.active_ss_fit(x, y, order, k, 2, return_gradients=True)
+        gs = np.asarray(est.grad_at_many(x[:130]))
+        assert np.array_equal(gs.T, gm[:, :130])
+    # an exact quadratic is recovered exactly anywhere inside the cloud
+    yq = 0.2 * x[:, 0] + 0.5 * x[:, 1] ** 2 + 0.1 * x[:, 2] * x[:, 0]
+    est = cb.PolyGradientEstimator(x, yq, 2, 60)
+    g = np.asarray(est.grad_at_many(xq))
+    exact = np.zeros_like(xq)
+    exact[:, 0], exact[:, 1], exact[:, 2] = 0.2 + 0.1 * xq[:, 2], xq[:, 1], 0.1 * xq[:, 0]
+    assert np.max(np.abs(g - exact)) < 1e-8
+    # the reference's object interface end to end
+    fit = cb.ActiveSsRsvd(cb.PolyGradientEstimator(x, y, 1, 25), 2).fit(x[:500])
+    ref = ref_stats.ActiveSsRsvd(ref_stats.PolyGradientEstimator(x, y, 1, 25), 2).fit(x[:500])
+    assert np.max(np.abs(np.diag(fit.singular_vals_) - np.diag(ref.singular_vals_))) < 1e-10 * ref.singular_vals_[0, 0]
+    assert ref_rsvd.subspace_sine(ref.components(), fit.components()) < 1e-8
+    with pytest.raises(cb.CorrlaError):
+        cb.PolyGradientEstimator(x, y, 1, 5).grad_at(list(xq[0]))          # n_nbrs > k + 1 (:116)
+    with pytest.raises(cb.CorrlaError):
+        cb.PolyGradientEstimator(x, y, 3, 30).grad_at(list(xq[0]))         # "Not implemented est order"
