@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 #include "small_kernels.cuh"
@@ -37,7 +38,6 @@ namespace {
 
 constexpr int kRJMaxSweeps = 60;
 constexpr int kRJMaxWarps = 16;               // warps per CTA
-constexpr int kRJMaxCluster = 8;
 constexpr unsigned kRJSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t rj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,7 +63,7 @@ __device__ __forceinline__ bool rj_mbar_try_wait(uint32_t bar, uint32_t parity) 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
@@ -77,11 +77,13 @@ __device__ __forceinline__ double rj_warp_sum(double a) {
 
 // NR = rows per lane (rows 32k + lane, k < NR): l <= 32 NR.  A mailbox holds one column: [2 NR][32] doubles stored as
 // 16-byte pairs (k2, lane) -> X rows (2 k2, 2 k2 + 1) of that lane, then the same for the rotation part.
-template <int NR>
-__global__ void __launch_bounds__(NR <= 4 ? 256 : 32 * kRJMaxWarps)     // l <= 128: at most 8 warps per CTA
+template <int NR, bool kDbg>
+__global__ void __launch_bounds__(32 * kRJMaxWarps, 1)
 jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                    double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, int transpose, int* info,
-                   unsigned spin_limit) {
+                   unsigned spin_limit, long long* dbg) {
+  long long t_rot = 0, t_send = 0, t_wait = 0, t_loop = 0, t_mark = 0;      // kDbg: cycles per phase of this warp
+  auto tick = [&](long long& acc) { if (kDbg) { const long long now = clock64(); acc += now - t_mark; t_mark = now; } };
   cg::cluster_group cluster = cg::this_cluster();
   constexpr int COLW = 2 * NR * 32;                 // doubles per mailbox
   constexpr uint32_t kColBytes = COLW * 8;
@@ -250,32 +252,40 @@ jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __res
   if (*reinterpret_cast<volatile int*>(&fail_s)) dead = 1;
   for (; sweeps < kRJMaxSweeps; ++sweeps) {
     if (active && !dead) {
+      if (kDbg) { t_mark = clock64(); t_loop -= t_mark; }
       for (int t = 0; t < n && !dead; t += 2) {
         // even step: pairs (2g, 2g+1).  Afterwards the column now in position 2g is the RIGHT register set.
         rotate();
+        tick(t_rot);
         if (first) {
 #pragma unroll
           for (int k = 0; k < NR; ++k) { park[(2 * k) * 32 + lane] = xr[k]; park[(2 * k + 1) * 32 + lane] = vr[k]; }
         } else {
           send(xr, vr, left_box, left_bar, left_remote);
         }
+        tick(t_send);
         bool have_right = false;
         if (!last) { have_right = receive(xr, vr, my_box_r, my_bar_r, phase_r, right_remote); if (!have_right) { dead = 1; break; } }
+        tick(t_wait);
         // odd step: pairs (2g+1, 2g+2); the last warp idles with position n-1 in its LEFT set
         if (!last) rotate();
+        tick(t_rot);
         // afterwards the column in position 2g+2 is the LEFT register set: it goes right, position 2g comes from the left
         if (!last) send(xl, vl, right_box, right_bar, right_remote);
         else {
 #pragma unroll
           for (int k = 0; k < NR; ++k) { xr[k] = xl[k]; vr[k] = vl[k]; }
         }
+        tick(t_send);
         if (first) {
 #pragma unroll
           for (int k = 0; k < NR; ++k) { xl[k] = park[(2 * k) * 32 + lane]; vl[k] = park[(2 * k + 1) * 32 + lane]; }
         } else {
           if (!receive(xl, vl, my_box_l, my_bar_l, phase_l, left_remote)) { dead = 1; break; }
         }
+        tick(t_wait);
       }
+      if (kDbg) t_loop += clock64();
       if (lane < C && (any | big)) atomicOr(cluster.map_shared_rank(&flags_s[sweeps % 3][0], lane), any);
       if (lane < C && big) atomicOr(cluster.map_shared_rank(&flags_s[sweeps % 3][1], lane), big);
     }
@@ -330,6 +340,9 @@ jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __res
     }
   }
   if (rank == 0 && tid == 0 && info != nullptr) { info[0] = sweeps; info[1] = failed ? -1 : converged; }
+  if (kDbg && dbg != nullptr && active && lane == 0) {
+    dbg[4 * g + 0] = t_rot; dbg[4 * g + 1] = t_send; dbg[4 * g + 2] = t_wait; dbg[4 * g + 3] = t_loop;
+  }
   // exactly zero singular values leave zero columns in Ux: rank 0 completes them to an orthonormal basis (unit vectors,
   // two Gram-Schmidt passes), like the other kernels
   int nz = 0;
@@ -393,31 +406,70 @@ cudaError_t jacobi_svd_ring_launch(const double* W, int ldw, int l, double* sigm
   static const int enabled = [] { const char* e = getenv("CORRLA_B200_JACOBI_RING"); return e == nullptr ? 1 : atoi(e); }();
   if (!enabled || l < 4 || l > 256) return cudaErrorNotSupported;
   const int h = (l + 1) / 2, n = 2 * h;
-  int C = 1;
-  while (C < kRJMaxCluster && ((h + C - 1) / C > kRJMaxWarps || (h + C - 1) / C > 7)) C *= 2;   // <= 7 warps per SM while the cluster can grow
-  const int wpc = (h + C - 1) / C;
-  if (wpc > kRJMaxWarps) return cudaErrorNotSupported;
+  // One warp per SM sub-partition when the cluster can grow that far: the step is a chain of dependent FP64 instructions
+  // and two warps on one sub-partition get in each other's way (l = 110: 7 warps per CTA on 8 CTAs 0.97 M cycles, 4 warps
+  // per CTA on 16 CTAs 0.89 M).  A cluster of 16 is a non-portable size: it is used only when the occupancy query says
+  // the device can place it.  CORRLA_B200_JACOBI_RING_WPC=n / CORRLA_B200_JACOBI_RING_MAXC=8 override the plan.
+  static const int wpc_target = [] { const char* e = getenv("CORRLA_B200_JACOBI_RING_WPC"); const int v = e == nullptr ? 4 : atoi(e); return (v >= 1 && v <= kRJMaxWarps) ? v : 4; }();
+  static const int c_limit = [] { const char* e = getenv("CORRLA_B200_JACOBI_RING_MAXC"); const int v = e == nullptr ? 16 : atoi(e); return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 16; }();
   const int nr = (l <= 64) ? 2 : (l <= 128 ? 4 : 8);
   const size_t colw = (size_t)2 * nr * 32;
-  const size_t smem = ((size_t)2 * wpc * colw + colw + (size_t)n) * 8 + (size_t)2 * wpc * 8 + (size_t)n * 4 + 16;
-  auto kern = (nr == 2) ? jacobi_ring_kernel<2> : (nr == 4 ? jacobi_ring_kernel<4> : jacobi_ring_kernel<8>);
+  // CORRLA_B200_JACOBI_DEBUG=1: per-warp phase clocks of the step loop, printed to stderr (synchronises the stream)
+  static const int debug = [] { const char* e = getenv("CORRLA_B200_JACOBI_DEBUG"); return e == nullptr ? 0 : atoi(e); }();
+  static long long* dbg_dev = nullptr;
+  if (debug && dbg_dev == nullptr && cudaMalloc(&dbg_dev, 4 * 128 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); dbg_dev = nullptr; }
+  const bool dbg_on = debug && dbg_dev != nullptr;
+  auto kern = dbg_on ? ((nr == 2) ? jacobi_ring_kernel<2, true> : (nr == 4 ? jacobi_ring_kernel<4, true> : jacobi_ring_kernel<8, true>))
+                     : ((nr == 2) ? jacobi_ring_kernel<2, false> : (nr == 4 ? jacobi_ring_kernel<4, false> : jacobi_ring_kernel<8, false>));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)C, 1, 1);
-  cfg.blockDim = dim3((unsigned)(32 * wpc), 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  int C = 0, wpc = 0;
+  for (int cmax = c_limit; cmax >= 1; cmax = (cmax > 8 ? 8 : 0)) {
+    C = 1;
+    while (C < cmax && (h + C - 1) / C > wpc_target) C *= 2;
+    wpc = (h + C - 1) / C;
+    if (wpc > kRJMaxWarps) { if (cmax > 8) continue; return cudaErrorNotSupported; }
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)C, 1, 1);
+    cfg.blockDim = dim3((unsigned)(32 * wpc), 1, 1);
+    cfg.dynamicSmemBytes = ((size_t)2 * wpc * colw + colw + (size_t)n) * 8 + (size_t)2 * wpc * 8 + (size_t)n * 4 + 16;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (C <= 8) break;
+    // 16 CTAs: allowed and placeable?  (asked once per kernel variant and device)
+    static int ok16[3][64];                          // [variant][device]: 0 unknown, 1 yes, -1 no
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& ok = ok16[nr == 2 ? 0 : (nr == 4 ? 1 : 2)][dev & 63];
+    if (ok == 0) {
+      int nclusters = 0;
+      cudaError_t q = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (q == cudaSuccess) q = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+      if (q != cudaSuccess) cudaGetLastError();
+      ok = (q == cudaSuccess && nclusters >= 1) ? 1 : -1;
+    }
+    if (ok == 1) break;
+  }
   // CORRLA_B200_TEST_JACOBI_SPIN_LIMIT: test hook -- 0 forces the failure path from the start
   static const unsigned spin_limit = [] { const char* e = getenv("CORRLA_B200_TEST_JACOBI_SPIN_LIMIT"); return e == nullptr ? kRJSpinLimit : (unsigned)strtoul(e, nullptr, 10); }();
-  return cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info, spin_limit);
+  e = cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info, spin_limit, dbg_on ? dbg_dev : nullptr);
+  if (dbg_on && e == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
+    static long long hb[4 * 128];
+    if (cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[jacobi_ring] l=%d cluster=%d warps/CTA=%d; cycles per warp in the step loops (rotate, send, wait, total):\n", l, C, wpc);
+      for (int g = 0; g < h; ++g)
+        if (g < 2 || g >= h - 2 || g % wpc == 0 || g % wpc == wpc - 1 || g == h / 2)
+          fprintf(stderr, "  warp %3d: %9lld %9lld %9lld %9lld\n", g, hb[4 * g], hb[4 * g + 1], hb[4 * g + 2], hb[4 * g + 3]);
+    }
+  }
+  return e;
 }
 
 }  // namespace corrla
