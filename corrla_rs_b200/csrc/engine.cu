@@ -173,6 +173,7 @@ int rsvd_impl(const double* a, int64_t nrows, int64_t ncols, int64_t rs, int64_t
   c.ctx = sc.ctx; c.st = sc.st; c.comm = o.comm;
   c.refill_seed = o.seed ^ 0x9e3779b97f4a7c15ull;
   c.refill_stream = o.comm ? (uint64_t)o.comm->rank : 0;
+  { const char* e = getenv("CORRLA_B200_INLOOP_CHOLQR2"); c.basis_only_qr = !(e != nullptr && e[0] == '1'); }   // A/B switch, read per call
   // more than 128 sketch columns: P column panels of padded width w <= 128 (wide.cuh); c then describes ONE panel
   const bool wide = l > 8 * kMaxNblk;
   if (wide && l > 2048) { set_last_error("n_rank + n_oversamples = %d exceeds the supported 2048 sketch columns", l); return CORRLA_ERR_UNSUPPORTED; }

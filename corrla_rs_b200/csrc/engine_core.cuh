@@ -405,16 +405,22 @@ struct Core {
     return CORRLA_OK;
   }
 
+  // basis_only: the caller only needs a well-conditioned basis of range(X), not an orthonormal one (the re-orthonormalisation
+  // INSIDE the power loop, random_svd.rs:38: the next product A^T(X*Tfold) depends on the range alone).  When the probe
+  // passes (cond(X) below ~1e4) one Cholesky pass is then enough: X stays untouched, Tfold = R^-1, X*Tfold is orthonormal to
+  // cond(X)^2 * eps <~ 1e-8 -- a basis of condition 1 + 1e-8.  That removes the apply, the second Gram product and the
+  // first-order correction from every in-loop QR (two passes over the m x l iterate).
   int qr_inplace(double* X, int64_t rows, bool distributed, double rows_for_shift, double* Tfold,
-                 bool refill_from_a = false, bool complete = false) {
+                 bool refill_from_a = false, bool complete = false, bool basis_only = false) {
     const MatView vx = view_rows(X, rows);
     const size_t gx = distributed ? (size_t)Lc * ld : 0;
     CU_TRY(cudaMemsetAsync(flags, 0, 8 * sizeof(int), st));      // f2 (0), liveness (1..3), refill-stage f2 (6) start clear
     int* fs = flags + 16;                                        // [0] robust stage needed, [1] fast path ok
     ST_TRY(gram(vx, X, nullptr, gx));
-    ST_TRY(chol(kCholProbe, rows_for_shift, T1, nullptr, true, fs));
+    ST_TRY(chol(kCholProbe, rows_for_shift, basis_only ? Tfold : T1, nullptr, true, fs));
     int robust = 0;
     ST_TRY(read_flags(fs, &robust, nullptr));                    // identical on every rank: G is the all-reduced Gram
+    if (!robust && basis_only) { ++qr_calls; return CORRLA_OK; }
     if (!robust) {
       // fast path: CholeskyQR2
       // ... with the second Cholesky replaced by its first-order expansion: the probe bounds cond(G) by ~1e8, so after
@@ -477,6 +483,7 @@ struct Core {
   }
 
   int n_robust = 0, n_refill = 0;
+  bool basis_only_qr = true;      // in-loop QR as one Cholesky pass when the probe allows (CORRLA_B200_INLOOP_CHOLQR2=1: two)
 
 
   // Omega (n x l, standard normal, Philox counter = element index) into Za     random_svd.rs:27
@@ -551,7 +558,7 @@ struct Core {
     for (int i = 0; i < n_iter; ++i) {                        // :35
       const bool do_qr = (schedule == 1) || (i > 2);          // :37
       if (do_qr) {
-        ST_TRY(qr_inplace(Y, m, true, grows, Tf, true));      // :38
+        ST_TRY(qr_inplace(Y, m, true, grows, Tf, true, false, basis_only_qr));   // :38
         ST_TRY(mm_AtY(Y, Zb));                                // :42-46 (on the pre-fold iterate), all-reduced
         ST_TRY(mm(view_rows(Zb, n), true, Tf, Za, ld, 1, Lc)); // fold R^-1 into the small side
         ST_TRY(mm_AX(Za, Y, nullptr, nu2));                   // :47-51

@@ -121,7 +121,7 @@ def hqr_inv(sk: np.ndarray):
 
 
 def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None,
-            refill_a: np.ndarray | None = None, complete: bool = False):
+            refill_a: np.ndarray | None = None, complete: bool = False, basis_only: bool = False):
     """CholeskyQR2 when a Cholesky probe says cond(x) is below ~1e4, else sketch-preconditioned CholeskyQR with refill
     of numerically dependent columns (Core::qr_inplace in engine.cu).
     Returns (x_last, t_fold, second_pass, live): the orthonormal factor is x_last @ t_fold."""
@@ -130,6 +130,9 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
     _, _, probe = chol_factor(g, np.diag(g).copy(), False, TOL_DEAD_PER_COL * x.shape[1])
     if probe >= 1e-8:
         t1, _, _ = chol_inv(g, False, global_rows)
+        if basis_only:
+            # in-loop QR: a basis of range(x) of condition 1 + cond(x)^2 eps is all the next product needs -- one pass
+            return x, t1, False, x.shape[1]
         x = x @ t1
         g = distributed_allreduce(x.T @ x)
         e = g - np.eye(g.shape[0])
@@ -239,7 +242,7 @@ def engine_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: in
     nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
     for i in range(n_iter):
         if schedule == 1 or i > 2:
-            y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a)
+            y, tf, _, _ = qr_fold(y, allreduce, grows, refill_a=a, basis_only=True)
             z = allreduce(a.T @ y) @ tf
             y = a @ z
         else:
