@@ -55,6 +55,7 @@ static bool try_fused_small(Scope& sc, const corrla_rsvd_opts& o, const double* 
   fa.seed = o.seed;
   fa.debug = getenv("CORRLA_B200_FUSED_PROFILE") != nullptr ? 1 : 0;
   { const char* e = getenv("CORRLA_B200_FUSED_NO_CHOL"); fa.no_chol = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  { const char* e = getenv("CORRLA_B200_INLOOP_CHOLQR2"); fa.basis_only = (e != nullptr && e[0] == '1') ? 0 : 1; }
   // staging: [A m*n | Omega n*l] in, [U m*k | V n*k | S k | Q m*l] out
   const size_t in_elems = (in_dev ? 0 : (size_t)m * n) + ((o.omega != nullptr && !o.omega_on_device) ? (size_t)n * l : 0);
   const size_t out_elems = out_dev ? 0 : (power_only ? (size_t)m * l : (size_t)(m + n + 1) * kk);

@@ -242,8 +242,10 @@ __device__ bool fs_chol_inv_warp(double* G, double* Wm, int pl, int l, int lane)
 // F (rows x l, column-major, pitch p) <- orthonormal basis of its span by CholeskyQR2 with the first-order second pass
 // (T2 = 3/2 I - 1/2 G2, exact to (3/8)|G2 - I|^2).  Returns 0: done, the basis is in F.  1: not applicable, F untouched.
 // 2: the second pass found |G2 - I| too large: `Other` holds F * R^-1 (same span, condition number ~1) for Householder.
+// basis_only (the QR inside the power loop, whose consumer needs range(F) only -- engine_core.cuh::qr_inplace): stop after
+// the first pass and return 3: `Other` holds F * R^-1, a basis of condition 1 + cond(F)^2 eps <= 1 + 1e-8.
 __device__ int fs_cholqr2(double* F, double* Other, int p, int rows8, int l, int l8, double* sG, double* sT1, double* sT2,
-                          int pl, double* red, int* sflag, int warp, int lane) {
+                          int pl, double* red, int* sflag, int warp, int lane, bool basis_only) {
   const int tid = warp * 32 + lane;
   const int nbl = l8 >> 3;
   fs_gram(F, p, rows8, l8, F, sG, pl, warp, lane);
@@ -258,6 +260,7 @@ __device__ int fs_cholqr2(double* F, double* Other, int p, int rows8, int l, int
   // Other = F * R^-1:   b(kk, j) = R^-1[kk][j] = W[j][kk] = sT1[j*pl + kk]
   fs_gemm(nbl, F, 1, p, sT1, 1, pl, Other, 1, p, rows8 >> 3, l8 >> 2, rows8, l8, 1.0, warp, lane);
   __syncthreads();
+  if (basis_only) return 3;
   fs_gram(Other, p, rows8, l8, Other, sG, pl, warp, lane);
   __syncthreads();
   double e2 = 0.0;
@@ -420,9 +423,11 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     tick(2);
   };
   // F <- thin Q of F: CholeskyQR2 when its Cholesky probe passes, else Householder (the buffers may swap)
-  auto thin_q = [&](double*& F, double*& Other, int pitch, int rows, int rows8) {
-    const int st = p.no_chol ? 1 : fs_cholqr2(F, Other, pitch, rows8, l, L.l8, sG, sT1, sT2, L.pl, red, s_info + 6, warp, lane);
-    if (st != 0) {
+  auto thin_q = [&](double*& F, double*& Other, int pitch, int rows, int rows8, bool basis_only) {
+    const int st = p.no_chol ? 1 : fs_cholqr2(F, Other, pitch, rows8, l, L.l8, sG, sT1, sT2, L.pl, red, s_info + 6, warp, lane,
+                                              basis_only);
+    if (st == 3) { double* tmp = F; F = Other; Other = tmp; }
+    else if (st != 0) {
       if (st == 2) { double* tmp = F; F = Other; Other = tmp; }
       fs_house_factor(F, pitch, rows, l, hv0, hden, warp, lane);
       fs_house_form_q(F, pitch, rows, l, hv0, hden, Other, warp, lane);
@@ -433,7 +438,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
 
   mm_AZ(sZ, sY);
   for (int it = 0; it < p.n_iter; ++it) {                      // :35
-    if (p.schedule == 1 || it > 2) thin_q(sY, sY2, L.pm, m, L.m8);   // :37-39
+    if (p.schedule == 1 || it > 2) thin_q(sY, sY2, L.pm, m, L.m8, p.basis_only != 0);   // :37-39
     mm_AtY(sY, sZ);
     mm_AZ(sZ, sY);
     // Y <- Y / ||Y||_F                                         :53-55
@@ -453,7 +458,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
     __syncthreads();
     tick(4);
   }
-  thin_q(sY, sY2, L.pm, m, L.m8);                              // :57   sY = Q
+  thin_q(sY, sY2, L.pm, m, L.m8, false);                       // :57   sY = Q
 
   if (p.power_only) {
     for (int idx = tid; idx < m * l; idx += kFsThreads) {
@@ -469,7 +474,7 @@ fused_small_rsvd_kernel(const FusedSmallArgs p) {
   // whichever QR produced Qz), one-sided Jacobi on W^T, then U = Q * Vr, V = Qz * Ur
   for (int idx = tid; idx < L.l8 * L.pn; idx += kFsThreads) sY2[idx] = sZ[idx];     // keep B^T (sY2 is free: sY holds Q)
   __syncthreads();
-  thin_q(sZ, sZ2, L.pn, n, L.n8);                              // sZ = Qz
+  thin_q(sZ, sZ2, L.pn, n, L.n8, false);                       // sZ = Qz
   {
     double* Qz = sZ;
     // W[i][j] = sum_kk Qz[kk][i] * Bt[kk][j]  ->  X column i, row j  (X = W^T as columns: X[i*lp + j] = W[i][j])

@@ -26,6 +26,7 @@ struct FusedSmallArgs {
   double* s;                              // k singular values
   double* qout;                           // power_only: Q, m x l column-major
   int no_chol;                            // 1: Householder QR only (CORRLA_B200_FUSED_NO_CHOL=1; tests compare the two)
+  int basis_only;                         // 1: the in-loop QR stops after one Cholesky pass (0: CORRLA_B200_INLOOP_CHOLQR2=1)
   int debug;                              // 1: thread 0 prints a clock64 phase breakdown (CORRLA_B200_FUSED_PROFILE=1)
   int* info;                              // [0] Jacobi sweeps, [1] converged, [2] 1 => result unusable, take the general path
 };
