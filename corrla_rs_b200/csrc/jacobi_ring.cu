@@ -81,7 +81,7 @@ template <int NR, bool kDbg>
 __global__ void __launch_bounds__(32 * kRJMaxWarps, 1)
 jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __restrict__ sigma_out,
                    double* __restrict__ Vr_out, double* __restrict__ Ur_out, int Lrows, int ldo, int transpose, int* info,
-                   unsigned spin_limit, long long* dbg) {
+                   unsigned spin_limit, long long* dbg, int fail_at_sweep) {
   long long t_rot = 0, t_send = 0, t_wait = 0, t_loop = 0, t_mark = 0;      // kDbg: cycles per phase of this warp
   auto tick = [&](long long& acc) { if (kDbg) { const long long now = clock64(); acc += now - t_mark; t_mark = now; } };
   cg::cluster_group cluster = cg::this_cluster();
@@ -172,7 +172,7 @@ jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __res
 
   const double tol = sqrt((double)l) * DBL_EPSILON;
   const double tol2 = tol * tol;
-  unsigned phase_l = 0, phase_r = 0;
+  unsigned phase_l = 0, phase_r = 0;               // columns received so far from the left / right (mbarrier phase parity)
   int dead = 0;                                     // warp-uniform: this warp gave up (or saw the CTA's fail flag)
   int any = 0, big = 0;
 
@@ -251,6 +251,8 @@ jacobi_ring_kernel(const double* __restrict__ Win, int ldw, int l, double* __res
   int sweeps = 0, converged = 0;
   if (*reinterpret_cast<volatile int*>(&fail_s)) dead = 1;
   for (; sweeps < kRJMaxSweeps; ++sweeps) {
+    // test hook: warp 1 behaves as if a wait had timed out at the start of this sweep -- its neighbours are left waiting
+    if (sweeps == fail_at_sweep && g == 1 && !dead) { fail_everywhere(); dead = 1; }
     if (active && !dead) {
       if (kDbg) { t_mark = clock64(); t_loop -= t_mark; }
       for (int t = 0; t < n && !dead; t += 2) {
@@ -459,7 +461,9 @@ cudaError_t jacobi_svd_ring_launch(const double* W, int ldw, int l, double* sigm
   }
   // CORRLA_B200_TEST_JACOBI_SPIN_LIMIT: test hook -- 0 forces the failure path from the start
   static const unsigned spin_limit = [] { const char* e = getenv("CORRLA_B200_TEST_JACOBI_SPIN_LIMIT"); return e == nullptr ? kRJSpinLimit : (unsigned)strtoul(e, nullptr, 10); }();
-  e = cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info, spin_limit, dbg_on ? dbg_dev : nullptr);
+  // CORRLA_B200_TEST_JACOBI_FAIL_SWEEP=s: test hook -- one warp gives up at the start of sweep s (failure from inside the iteration)
+  static const int fail_at = [] { const char* e = getenv("CORRLA_B200_TEST_JACOBI_FAIL_SWEEP"); return e == nullptr ? -1 : atoi(e); }();
+  e = cudaLaunchKernelEx(&cfg, kern, W, ldw, l, sigma, Vr, Ur, Lrows, ldo, transpose, info, spin_limit, dbg_on ? dbg_dev : nullptr, fail_at);
   if (dbg_on && e == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
     static long long hb[4 * 128];
     if (cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost) == cudaSuccess) {

@@ -61,6 +61,16 @@ def test_jacobi_cluster_timeout_is_reported_without_timings():
     assert ok_null == 0 and ok_tm == 0
 
 
+def test_jacobi_failure_in_the_middle_of_the_iteration_fails_cleanly():
+    """CORRLA_B200_TEST_JACOBI_FAIL_SWEEP=1: one warp of the ring Jacobi kernel gives up at the start of the second sweep, as
+    after a timed-out wait -- the failure path taken from INSIDE the iteration, with its neighbours still waiting for the
+    columns it will never send.  The call must come back (no hang, the waits poll the failure flag) with an error status,
+    never with CORRLA_OK and garbage."""
+    st_null, st_tm, msg = _run_raw({"CORRLA_B200_TEST_JACOBI_FAIL_SWEEP": "1"})
+    assert st_null == -3 and st_tm == -3, (st_null, st_tm, msg)
+    assert "Jacobi" in msg
+
+
 def test_ctx_trim_releases_and_recovers(cb):
     rng = np.random.default_rng(4)
     a = rng.standard_normal((20000, 256))
