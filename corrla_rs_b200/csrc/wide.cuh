@@ -105,15 +105,18 @@ struct Wide {
     return CORRLA_OK;
   }
 
-  // X (rows x l in P panels) <- its thin-Q factor, explicitly
-  int block_qr(std::vector<double*>& X, int64_t rows, bool distributed, double rows_for_shift, bool from_a, bool complete) {
+  // X (rows x l in P panels) <- its thin-Q factor, explicitly.  basis_only (the QR inside the power loop): a well-conditioned
+  // basis of the same range is enough (engine_core.cuh::qr_inplace) -- one projection sweep against the finished panels
+  // instead of two and one Cholesky pass per panel; the result is orthonormal to ~1e-8 instead of 1e-15.
+  int block_qr(std::vector<double*>& X, int64_t rows, bool distributed, double rows_for_shift, bool from_a, bool complete,
+               bool basis_only = false) {
     const size_t gx = (distributed && multi()) ? (size_t)c.Lc * c.ld : 0;
     const int l_keep = c.l;
     int status = CORRLA_OK;
     for (int j = 0; j < P && status == CORRLA_OK; ++j) {
       c.l = lp(j);
       for (int attempt = 0; attempt < 3 && status == CORRLA_OK; ++attempt) {
-        for (int rep = 0; rep < 2 && status == CORRLA_OK; ++rep)
+        for (int rep = 0; rep < (basis_only ? 1 : 2) && status == CORRLA_OK; ++rep)
           for (int i = 0; i < j && status == CORRLA_OK; ++i) {
             const MatView qi = c.view_rows(X[i], rows);
             status = c.mm(qi, false, X[j], Cb, c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 0, false, nullptr, gx);   // Q_i^T X_j
@@ -125,7 +128,7 @@ struct Wide {
           }
         if (status != CORRLA_OK) break;
         const int refills = c.n_refill;
-        status = c.qr_inplace(X[j], rows, distributed, rows_for_shift, Tq, from_a, complete);
+        status = c.qr_inplace(X[j], rows, distributed, rows_for_shift, Tq, from_a, complete, basis_only);
         if (status == CORRLA_OK)      // Tq may be the symmetric first-order factor of the fast path: general product, in place
           status = c.mm(c.view_rows(X[j], rows), true, Tq, X[j], c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 1);
         // columns refilled inside the panel QR are not orthogonal to the earlier panels yet: project and factor again
@@ -142,7 +145,7 @@ struct Wide {
     ST_TRY(passes_AX(Za, false));                                   // :31
     for (int i = 0; i < n_iter; ++i) {                              // :35
       const bool do_qr = (o.schedule == 1) || (i > 2);              // :37
-      if (do_qr) ST_TRY(block_qr(Y, c.m, true, c.grows, true, false));
+      if (do_qr) ST_TRY(block_qr(Y, c.m, true, c.grows, true, false, c.basis_only_qr));
       ST_TRY(passes_AtY());                                         // :42-46
       ST_TRY(passes_AX(Zb, !do_qr));                                // :47-51 (+ the deferred :53-55 scaling)
     }

@@ -317,18 +317,20 @@ def wide_plan(l: int):
     return p, w
 
 
-def block_qr(x: np.ndarray, w: int, allreduce, global_rows: float, refill_a=None, complete=False):
+def block_qr(x: np.ndarray, w: int, allreduce, global_rows: float, refill_a=None, complete=False, basis_only=False):
     """Wide::block_qr: block classical Gram-Schmidt with two projection sweeps against the finished panels, then the
-    adaptive CholeskyQR of the single-panel path (qr_fold) on the panel; Q is formed explicitly."""
+    adaptive CholeskyQR of the single-panel path (qr_fold) on the panel; Q is formed explicitly.  basis_only (in-loop
+    QR): one sweep and one Cholesky pass -- a basis of condition ~1 of the same range."""
     q = np.array(x, dtype=np.float64, copy=True)
     l = q.shape[1]
     for j0 in range(0, l, w):
         j1 = min(l, j0 + w)
-        for _rep in range(2):
+        for _rep in range(1 if basis_only else 2):
             for i0 in range(0, j0, w):
                 qi = q[:, i0:i0 + w]
                 q[:, j0:j1] -= qi @ allreduce(qi.T @ q[:, j0:j1])
-        xj, tf, _, _ = qr_fold(q[:, j0:j1].copy(), allreduce, global_rows, refill_a=refill_a, complete=complete)
+        xj, tf, _, _ = qr_fold(q[:, j0:j1].copy(), allreduce, global_rows, refill_a=refill_a, complete=complete,
+                               basis_only=basis_only)
         q[:, j0:j1] = xj @ tf
     return q
 
@@ -346,7 +348,7 @@ def wide_rsvd(a_local: np.ndarray, n_rank: int, n_iter: int, n_oversamples: int,
     for i in range(n_iter):
         do_qr = schedule == 1 or i > 2
         if do_qr:
-            y = block_qr(y, w, allreduce, grows, refill_a=a)
+            y = block_qr(y, w, allreduce, grows, refill_a=a, basis_only=True)
         z = allreduce(a.T @ y)
         y = a @ z if do_qr else (a @ z) * (1.0 / np.sqrt(nu2))
         nu2 = float(allreduce(np.array([np.sum(y * y)]))[0])
