@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 namespace corrla {
@@ -22,11 +23,11 @@ constexpr int kKnnMargin = 16;    // extra shortlist entries of the GEMM-form se
 
 // Warp-collective insertion of the lanes flagged in `mask` (lowest lane first = increasing candidate index) into the
 // sorted list (ld, li) of length k; returns the new k-th best distance.  Equal distances keep the lower index first.
-__device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dist, int cand, double thr, unsigned mask,
-                                          int lane) {
+template <typename T>
+__device__ __noinline__ T knn_insert_t(T* ld, int* li, int k, T dist, int cand, T thr, unsigned mask, int lane) {
   while (mask) {
     const int src = __ffs(mask) - 1;
-    const double dv = __shfl_sync(0xffffffffu, dist, src);
+    const T dv = __shfl_sync(0xffffffffu, dist, src);
     const int iv = __shfl_sync(0xffffffffu, cand, src);
     if (dv < thr) {
       int cnt = 0;
@@ -34,11 +35,11 @@ __device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dis
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       const int pos = cnt;
-      double td[kKnnSlots]; int ti[kKnnSlots];
+      T td[kKnnSlots]; int ti[kKnnSlots];
 #pragma unroll
       for (int j = 0; j < kKnnSlots; ++j) {
         const int p = lane + 32 * j;
-        td[j] = 0.0; ti[j] = 0;
+        td[j] = (T)0; ti[j] = 0;
         if (p > pos && p < k) { td[j] = ld[p - 1]; ti[j] = li[p - 1]; }
       }
       __syncwarp();
@@ -55,6 +56,9 @@ __device__ __noinline__ double knn_insert(double* ld, int* li, int k, double dis
     mask &= __ballot_sync(0xffffffffu, dist < thr);
   }
   return thr;
+}
+__device__ __forceinline__ double knn_insert(double* ld, int* li, int k, double dist, int cand, double thr, unsigned mask, int lane) {
+  return knn_insert_t<double>(ld, li, k, dist, cand, thr, mask, lane);
 }
 
 __global__ void __launch_bounds__(kKnnThreads)
@@ -291,6 +295,209 @@ knn_gemm_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same shortlist search on the TF32 tensor-core path
+// ------------------------------------------------------------------------------------------------
+// The shortlist only has to CONTAIN the k nearest; the exact re-rank and the certificate decide.  So the N^2 d inner
+// products do not need 53 bits: with the samples rounded to TF32 (cvt.rna, relative error 2^-11 per element) and
+// mma.sync.m16n8k8 accumulating in FP32, |approximate - exact| <= delta with
+//   delta = kTf32DeltaRel(d8) * (|q|^2 + max|c|^2),  kTf32DeltaRel = 1.5 * 2^-10 + (d8 + 24) * 2^-22
+// (2 * [2^-10 + 2^-22] |q||c| from the two roundings of every product, |q||c| <= (|q|^2 + |c|^2)/2, the FP32
+// accumulation and the FP32 norms in the second term, a factor 1.5 of slack on the first).  The certificate of
+// knn_rerank_kernel takes that delta; the shortlist carries kKnnMarginTf32 = 32 extra entries for the candidates the
+// coarser distances can misplace (Gaussian samples in 64 dimensions, k = 72 of 2^20: ~12 candidates within 2 delta of the
+// k-th distance).  One m16n8k8 does 1024 FMAs where one DMMA.8x8x4 does 256 at a sixteenth of the issue rate.
+// Layout: a float copy of the samples with pitch d8 + 4 (== 4 mod 8: conflict-free B-fragment loads), zero padded to
+// whole tiles; a CTA owns 128 queries (8 autonomous warps x 16), otherwise as knn_gemm_kernel.
+constexpr int kTQ = 128;
+constexpr int kKnnMarginTf32 = 32;
+
+__host__ __device__ inline double knn_tf32_delta_rel(int d8) { return 1.5 * 0x1.0p-10 + (double)(d8 + 24) * 0x1.0p-22; }
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Distances do not change under a common shift, the error bound above does (it scales with the norms): the float copy
+// holds the samples minus their column means.  Column sums first (any summation order will do: whichever shift comes
+// out, it is applied consistently) ...
+__global__ void __launch_bounds__(256)
+knn_colsum_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, double* __restrict__ colsum) {
+  __shared__ double part[8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * 8 + w; i < n; i += (int64_t)gridDim.x * 8)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { const int c = lane + 32 * b; if (c < d) acc[b] += X[i * ldx + c]; }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) part[w][lane + 32 * b] = acc[b];
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += 256) {
+    double t = 0.0;
+    for (int ww = 0; ww < 8; ++ww) t += part[ww][c];
+    atomicAdd(colsum + c, t);
+  }
+}
+
+// ... then, one warp per row: Xf[i][c] = tf32(x_ic - mean_c) as float bits (rows >= n and columns >= d zero), the FP64
+// squared norm of the shifted row, its float copy, and the maximum of those norms (what the certificate needs)
+__global__ void __launch_bounds__(256)
+knn_center_tf32_kernel(const double* __restrict__ X, const double* __restrict__ colsum, int64_t n, int d, int64_t ldx,
+                       float* __restrict__ Xf, float* __restrict__ nf, double* __restrict__ nrm2c, int64_t n_pad, int ldf,
+                       unsigned long long* __restrict__ max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n_pad) return;
+  const double inv_n = 1.0 / (double)n;
+  double a = 0.0;
+  for (int c = lane; c < ldf; c += 32) {
+    float v = 0.0f;
+    if (i < n && c < d) {
+      const double t = X[i * ldx + c] - colsum[c] * inv_n;
+      a = fma(t, t, a);
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"((float)t));
+      v = __uint_as_float(r);
+    }
+    Xf[i * ldf + c] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) {
+    nrm2c[i] = a;
+    nf[i] = (float)a;
+    atomicMax(max_bits, (unsigned long long)__double_as_longlong(a));      // non-negative doubles order like their bits
+  }
+}
+
+template <int CT, int KS>                               // KS k-steps of 8 features (d8 <= 8 KS)
+__global__ void __launch_bounds__(kGThreads, 1)
+knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int64_t n, int d8, int ldf, int kp,
+                int* __restrict__ short_idx, double* __restrict__ short_thr) {
+  constexpr int JW = CT / 8;
+  constexpr int DP = CT + 8;                            // == 8 (mod 32): the 8-byte slab stores of a half warp hit 32 banks
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* Cs = reinterpret_cast<float*>(smraw);                           // [stages][CT][ldf]
+  float* Cn = Cs + (size_t)kGStages * CT * ldf;                          // [stages][CT]
+  float* Dt = Cn + kGStages * CT;                                        // [8 warps][16][DP]
+  float* Ld = Dt + (size_t)kTQ * DP;                                     // [128][kp]
+  int* Li = reinterpret_cast<int*>(Ld + (size_t)kTQ * kp);               // [128][kp]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(Li + (size_t)kTQ * kp) + 7) & ~(uintptr_t)7);                     // full[3], empty[3]
+  const uint32_t sBar = smem_u32(bars);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q0 = (int64_t)blockIdx.x * kTQ;
+  const int64_t tiles = (n + CT - 1) / CT;
+
+  if (tid == 0) {
+    for (int s = 0; s < kGStages; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 8 * (kGStages + s), 8); }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < kTQ * kp; i += kGThreads) { Ld[i] = FLT_MAX; Li[i] = -1; }
+  __syncthreads();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t bytes = (uint32_t)CT * (uint32_t)ldf * 4u, nbytes = (uint32_t)CT * 4u;    // whole tiles: Xf is padded
+      for (int64_t t = 0; t < tiles; ++t) {
+        mbar_wait(sBar + 8 * (kGStages + stage), phase ^ 1u);
+        const int64_t c0 = t * CT;
+        mbar_arrive_expect_tx(sBar + 8 * stage, bytes + nbytes);
+        bulk_load(smem_u32(Cs + (size_t)stage * CT * ldf), Xf + c0 * ldf, bytes, sBar + 8 * stage);
+        bulk_load(smem_u32(Cn + stage * CT), nf + c0, nbytes, sBar + 8 * stage);
+        if (++stage == kGStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+  // ------------------------------ consumers: warp w owns queries 16w .. 16w + 15 ------------------------------
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ksteps = d8 >> 3;
+  const int64_t row_a = q0 + 16 * warp + g, row_b = row_a + 8;           // the two query rows of this lane's fragments
+  uint32_t aq[KS][4];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const bool on = s < ksteps;
+    // rows beyond n are zero rows of the padded copy (n_pad >= tiles * CT + 128 is guaranteed by the launcher)
+    aq[s][0] = on ? __float_as_uint(Xf[row_a * ldf + 8 * s + t4]) : 0u;
+    aq[s][1] = on ? __float_as_uint(Xf[row_b * ldf + 8 * s + t4]) : 0u;
+    aq[s][2] = on ? __float_as_uint(Xf[row_a * ldf + 8 * s + t4 + 4]) : 0u;
+    aq[s][3] = on ? __float_as_uint(Xf[row_b * ldf + 8 * s + t4 + 4]) : 0u;
+  }
+  const float qn_a = nf[row_a], qn_b = nf[row_b];
+  float* Dw = Dt + (size_t)warp * 16 * DP;
+  const float* thr_pa = Ld + (size_t)(16 * warp + g) * kp + kp - 1;
+  const float* thr_pb = thr_pa + (size_t)8 * kp;
+  uint32_t stage = 0, phase = 0;
+  for (int64_t t = 0; t < tiles; ++t) {
+    const int64_t c0 = t * CT;
+    mbar_wait(sBar + 8 * stage, phase);
+    const float* bp0 = Cs + (size_t)stage * CT * ldf + (size_t)g * ldf + t4;     // candidate 8j + g, feature 8s + t4 (+4)
+    float acc[JW][4];
+#pragma unroll
+    for (int j = 0; j < JW; ++j) { acc[j][0] = 0.0f; acc[j][1] = 0.0f; acc[j][2] = 0.0f; acc[j][3] = 0.0f; }
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      if (s < ksteps) {
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+          const float* bp = bp0 + 8 * j * ldf + 8 * s;
+          mma_tf32_m16n8k8(acc[j], aq[s], __float_as_uint(bp[0]), __float_as_uint(bp[4]));
+        }
+      }
+    }
+    const float* cn = Cn + stage * CT;
+    const float thr_a = *thr_pa, thr_b = *thr_pb;
+    bool hit_a = false, hit_b = false;
+#pragma unroll
+    for (int j = 0; j < JW; ++j) {
+      const int cl = 8 * j + 2 * t4;
+      const float2 cnv = *reinterpret_cast<const float2*>(cn + cl);
+      const float a0 = fmaf(-2.0f, acc[j][0], qn_a + cnv.x), a1 = fmaf(-2.0f, acc[j][1], qn_a + cnv.y);
+      const float b0 = fmaf(-2.0f, acc[j][2], qn_b + cnv.x), b1 = fmaf(-2.0f, acc[j][3], qn_b + cnv.y);
+      *reinterpret_cast<float2*>(Dw + g * DP + cl) = make_float2(a0, a1);
+      *reinterpret_cast<float2*>(Dw + (g + 8) * DP + cl) = make_float2(b0, b1);
+      const bool in0 = c0 + cl < n, in1 = c0 + cl + 1 < n;
+      hit_a |= (a0 < thr_a && in0) | (a1 < thr_a && in1);
+      hit_b |= (b0 < thr_b && in0) | (b1 < thr_b && in1);
+    }
+    __syncwarp();
+    const unsigned hba = __ballot_sync(0xffffffffu, hit_a), hbb = __ballot_sync(0xffffffffu, hit_b);
+    if (lane == 0) mbar_arrive(sBar + 8 * (kGStages + stage));
+    if (++stage == kGStages) { stage = 0; phase ^= 1u; }
+    if ((hba | hbb) != 0u) {
+#pragma unroll 1
+      for (int a = 0; a < 16; ++a) {
+        const unsigned hb = (a < 8) ? hba : hbb;
+        if (((hb >> (4 * (a & 7))) & 0xfu) == 0u) continue;
+        const int ql = 16 * warp + a;
+        if (q0 + ql >= n) continue;
+        float* ldq = Ld + (size_t)ql * kp;
+        int* liq = Li + (size_t)ql * kp;
+        float th = ldq[kp - 1];
+#pragma unroll
+        for (int b = 0; b < CT / 32; ++b) {
+          const int64_t cg = c0 + lane + 32 * b;
+          const float dist = (cg < n) ? Dw[a * DP + lane + 32 * b] : FLT_MAX;
+          const unsigned mask = __ballot_sync(0xffffffffu, dist < th);
+          if (mask) th = knn_insert_t<float>(ldq, liq, kp, dist, (int)cg, th, mask, lane);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int a = 0; a < 16; ++a) {
+    const int ql = 16 * warp + a;
+    const int64_t row = q0 + ql;
+    if (row >= n) break;
+    for (int p = lane; p < kp; p += 32) short_idx[row * kp + p] = Li[(size_t)ql * kp + p];
+    if (lane == 0) short_thr[row] = (double)Ld[(size_t)ql * kp + kp - 1];
+  }
+}
+
 // squared norms of the rows (the same d-term sums the distance identity needs) and their maximum
 __global__ void __launch_bounds__(256)
 knn_norms_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, double* __restrict__ nrm2, int64_t n_pad,
@@ -315,7 +522,7 @@ __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double* __restrict__ X, const double* __restrict__ nrm2, int64_t n, int d, int64_t ldx, int k, int kp,
                   const int* __restrict__ short_idx, const double* __restrict__ short_thr,
                   const unsigned long long* __restrict__ max_bits, int* __restrict__ idx_out, int* __restrict__ qlist,
-                  int* __restrict__ qcount) {
+                  int* __restrict__ qcount, double delta_rel) {
   __shared__ double sd[8][160];
   __shared__ int si[8][160];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -346,10 +553,11 @@ knn_rerank_kernel(const double* __restrict__ X, const double* __restrict__ nrm2,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dk = fmin(dk, __shfl_xor_sync(0xffffffffu, dk, o));
   if (lane == 0) {
-    // |approximate - exact| <= (2d + 8) eps (|q|^2 + |c|^2) for every pair; a candidate outside the shortlist has an
-    // approximate distance >= thr.  With fewer than kp samples the shortlist is the whole set: nothing was left out.
+    // |approximate - exact| <= delta_rel (|q|^2 + |c|^2) for every pair ((2d + 8) eps for the DMMA shortlist,
+    // knn_tf32_delta_rel for the TF32 one); a candidate outside the shortlist has an approximate distance >= thr.
+    // With fewer than kp samples the shortlist is the whole set: nothing was left out.
     const double nmax = __longlong_as_double((long long)*max_bits);
-    const double delta = (2.0 * d + 8.0) * DBL_EPSILON * (nrm2[q] + nmax);
+    const double delta = delta_rel * (nrm2[q] + nmax);
     const double thr = short_thr[q];
     const bool certified = (n <= kp) || (dk < thr - 2.0 * delta);
     if (!certified) qlist[atomicAdd(qcount, 1)] = (int)q;
@@ -485,53 +693,112 @@ static size_t knn_gemm_smem(int ct, int ld, int kp) {
   return bytes;
 }
 
-size_t knn_scratch_bytes(int64_t n, int k) {
-  const int kp = k + kKnnMargin;
-  const size_t n_pad = (size_t)((n + 63) / 64 * 64 + 64);
-  // norms | shortlist thresholds | shortlist indices | query list | counters
-  return (n_pad + (size_t)n) * 8 + ((size_t)n * kp + (size_t)n) * 4 + 64 + 256;
+static size_t knn_tf32_smem(int ct, int ldf, int kp) {
+  return ((size_t)kGStages * ct * ldf + (size_t)kGStages * ct + (size_t)kTQ * (ct + 8)) * 4 + (size_t)kTQ * kp * 8 + 8 +
+         2 * kGStages * 8;
 }
+
+// scratch layout shared by knn_scratch_bytes and knn_launch
+struct KnnScratch {
+  size_t n_pad, off_nrm2, off_thr, off_sidx, off_qlist, off_counters, off_mu, off_nrm2c, off_xf, off_nf, total;
+  int ldf;
+  KnnScratch(int64_t n, int k, int d) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    n_pad = (size_t)((n + 127) / 128 * 128 + 128);
+    ldf = (d + 7) / 8 * 8 + 4;
+    const size_t kp = (size_t)k + kKnnMarginTf32;                          // the larger of the two margins
+    size_t o = 0;
+    off_nrm2 = o; o = up(o + n_pad * 8);
+    off_thr = o; o = up(o + (size_t)n * 8);
+    off_sidx = o; o = up(o + (size_t)n * kp * 4);
+    off_qlist = o; o = up(o + (size_t)n * 4);
+    off_counters = o; o = up(o + 64);                                      // [0] max |x|^2, [1] query count, [2] max centred |x|^2
+    off_mu = o; o = up(o + 128 * 8);
+    off_nrm2c = o; o = up(o + n_pad * 8);
+    off_xf = o; o = up(o + n_pad * (size_t)ldf * 4);
+    off_nf = o; o = up(o + n_pad * 4);
+    total = o;
+  }
+};
+
+size_t knn_scratch_bytes(int64_t n, int k, int d) { return KnnScratch(n, k, d).total + 256; }
 
 cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, void* scratch, size_t scratch_bytes,
                        int* n_exact_fallback, cudaStream_t s) {
   if (n <= 0 || d <= 0 || k <= 0 || k > kKnnMaxK || k > n) return cudaErrorInvalidValue;
   if (n_exact_fallback) *n_exact_fallback = -1;                           // -1: the exact kernel did everything
   const char* env = getenv("CORRLA_B200_KNN_EXACT");
-  const int kp = k + kKnnMargin;
+  const char* env32 = getenv("CORRLA_B200_KNN_TF32");                     // "0": shortlist on the FP64 tensor pipe instead
   const int d8 = (d + 7) / 8 * 8;
+  const int ldf = d8 + 4;
+  // TF32 shortlist (default): tile of 64 or 32 candidates, whichever fits next to the 128 selection lists
+  int kp = k + kKnnMarginTf32;
+  int ct32 = 64;
+  if (knn_tf32_smem(ct32, ldf, kp) > 225 * 1024) ct32 = 32;
+  bool tf32_ok = !(env32 != nullptr && env32[0] == '0') && knn_tf32_smem(ct32, ldf, kp) <= 225 * 1024;
+  if (!tf32_ok) kp = k + kKnnMargin;
   int ct = 64;
   if (knn_gemm_smem(ct, (int)ldx, kp) > 225 * 1024) ct = 32;
-  const bool gemm_ok = (env == nullptr || env[0] != '1') && scratch != nullptr && scratch_bytes >= knn_scratch_bytes(n, k) &&
-                       (ldx % 8) == 4 && ldx >= d8 && d8 <= 128 && n >= 2048 && n < ((int64_t)1 << 31) &&
-                       knn_gemm_smem(ct, (int)ldx, kp) <= 225 * 1024;
-  if (!gemm_ok) return knn_exact_launch(X, n, d, ldx, k, idx, nullptr, nullptr, n, s);
+  const bool common_ok = (env == nullptr || env[0] != '1') && scratch != nullptr && scratch_bytes >= knn_scratch_bytes(n, k, d) &&
+                         d8 <= 128 && n >= 2048 && n < ((int64_t)1 << 31);
+  const bool dmma_ok = (ldx % 8) == 4 && ldx >= d8 && knn_gemm_smem(ct, (int)ldx, kp) <= 225 * 1024;
+  if (!common_ok || (!tf32_ok && !dmma_ok)) return knn_exact_launch(X, n, d, ldx, k, idx, nullptr, nullptr, n, s);
 
-  const size_t n_pad = (size_t)((n + 63) / 64 * 64 + 64);
-  unsigned char* base = static_cast<unsigned char*>(scratch);
-  double* nrm2 = reinterpret_cast<double*>(base);
-  double* thr = nrm2 + n_pad;
-  int* sidx = reinterpret_cast<int*>(thr + n);
-  int* qlist = sidx + (size_t)n * kp;
-  unsigned long long* counters = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(qlist + n) + 63) & ~(uintptr_t)63);
+  const KnnScratch L(n, k, d);
+  const size_t n_pad = L.n_pad;
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
+  double* nrm2 = reinterpret_cast<double*>(base + L.off_nrm2);
+  double* thr = reinterpret_cast<double*>(base + L.off_thr);
+  int* sidx = reinterpret_cast<int*>(base + L.off_sidx);
+  int* qlist = reinterpret_cast<int*>(base + L.off_qlist);
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(base + L.off_counters);
+  double* mu = reinterpret_cast<double*>(base + L.off_mu);
+  double* nrm2c = reinterpret_cast<double*>(base + L.off_nrm2c);
+  float* Xf = reinterpret_cast<float*>(base + L.off_xf);
+  float* nf = reinterpret_cast<float*>(base + L.off_nf);
   cudaError_t e = cudaMemsetAsync(counters, 0, 64, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(mu, 0, 128 * 8, s);
   if (e != cudaSuccess) return e;
   knn_norms_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(X, n, d, ldx, nrm2, (int64_t)n_pad, counters);
-  const size_t smem = knn_gemm_smem(ct, (int)ldx, kp);
-  const unsigned blocks = (unsigned)((n + kGQ - 1) / kGQ);
-  auto launch = [&](auto kern) -> cudaError_t {
-    cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    if (ee != cudaSuccess) return ee;
-    const char* dbg_env = getenv("CORRLA_B200_KNN_DEBUG");
-    const char* stg_env = getenv("CORRLA_B200_KNN_STAGGER_NS");
-    kern<<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr, dbg_env ? atoi(dbg_env) : 0,
-                                         stg_env ? (unsigned)atoi(stg_env) : 1200u);
-    return cudaGetLastError();
-  };
-  if (ct == 64) e = (d8 <= 64) ? launch(knn_gemm_kernel<64, 16>) : launch(knn_gemm_kernel<64, 32>);
-  else e = (d8 <= 64) ? launch(knn_gemm_kernel<32, 16>) : launch(knn_gemm_kernel<32, 32>);
+  const double* cert_nrm2 = nrm2;                        // norms and their maximum as the certificate's bound sees them
+  const unsigned long long* cert_max = counters;
+  double delta_rel;
+  if (tf32_ok) {
+    knn_colsum_kernel<<<148 * 4, 256, 0, s>>>(X, n, d, ldx, mu);
+    knn_center_tf32_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, s>>>(X, mu, n, d, ldx, Xf, nf, nrm2c, (int64_t)n_pad, ldf, counters + 2);
+    cert_nrm2 = nrm2c;
+    cert_max = counters + 2;
+    const size_t smem = knn_tf32_smem(ct32, ldf, kp);
+    const unsigned blocks = (unsigned)((n + kTQ - 1) / kTQ);
+    auto launch = [&](auto kern) -> cudaError_t {
+      cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      if (ee != cudaSuccess) return ee;
+      kern<<<blocks, kGThreads, smem, s>>>(Xf, nf, n, d8, ldf, kp, sidx, thr);
+      return cudaGetLastError();
+    };
+    if (ct32 == 64) e = (d8 <= 64) ? launch(knn_tf32_kernel<64, 8>) : launch(knn_tf32_kernel<64, 16>);
+    else e = (d8 <= 64) ? launch(knn_tf32_kernel<32, 8>) : launch(knn_tf32_kernel<32, 16>);
+    delta_rel = knn_tf32_delta_rel(d8);
+  } else {
+    const size_t smem = knn_gemm_smem(ct, (int)ldx, kp);
+    const unsigned blocks = (unsigned)((n + kGQ - 1) / kGQ);
+    auto launch = [&](auto kern) -> cudaError_t {
+      cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      if (ee != cudaSuccess) return ee;
+      const char* dbg_env = getenv("CORRLA_B200_KNN_DEBUG");
+      const char* stg_env = getenv("CORRLA_B200_KNN_STAGGER_NS");
+      kern<<<blocks, kGThreads, smem, s>>>(X, nrm2, n, d8, ldx, kp, sidx, thr, dbg_env ? atoi(dbg_env) : 0,
+                                           stg_env ? (unsigned)atoi(stg_env) : 1200u);
+      return cudaGetLastError();
+    };
+    if (ct == 64) e = (d8 <= 64) ? launch(knn_gemm_kernel<64, 16>) : launch(knn_gemm_kernel<64, 32>);
+    else e = (d8 <= 64) ? launch(knn_gemm_kernel<32, 16>) : launch(knn_gemm_kernel<32, 32>);
+    delta_rel = (2.0 * d + 8.0) * DBL_EPSILON;
+  }
   if (e != cudaSuccess) return e;
   int* qcount = reinterpret_cast<int*>(counters + 1);
-  knn_rerank_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, nrm2, n, d, ldx, k, kp, sidx, thr, counters, idx, qlist, qcount);
+  knn_rerank_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, cert_nrm2, n, d, ldx, k, kp, sidx, thr, cert_max, idx, qlist, qcount,
+                                                            delta_rel);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // queries without a certificate go through the exact kernel (normally none)
@@ -540,6 +807,10 @@ cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, in
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return e;
   if (n_exact_fallback) *n_exact_fallback = hcount;
+  { const char* v = getenv("CORRLA_B200_KNN_VERBOSE");
+    if (v != nullptr && v[0] == '1')
+      fprintf(stderr, "[knn] n=%lld d=%d k=%d shortlist=%d on %s: %d queries without a certificate go to the exact kernel\n",
+              (long long)n, d, k, kp, tf32_ok ? "TF32 mma.sync" : "FP64 DMMA", hcount); }
   if (hcount > 0) return knn_exact_launch(X, n, d, ldx, k, idx, qlist, qcount, hcount, s);
   return cudaSuccess;
 }

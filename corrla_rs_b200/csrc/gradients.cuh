@@ -14,12 +14,13 @@ constexpr int kGradMaxCoef = 136;    // fitted coefficients per sample (without 
 // idx[i*k + r] = index of the r-th nearest row of X to row i (squared Euclidean distance accumulated as sum (a-b)^2 in
 // the order of the features, like kdtree::distance::squared_euclidean; ties go to the lower index; the sample itself is
 // its own nearest neighbour).  X: n x d row-major with pitch ldx.  k <= min(n, kKnnMaxK).
-// With `scratch` (knn_scratch_bytes(n, k) bytes of device memory) and the engine's packed layout (ldx == 4 mod 8, zero
-// padded to a multiple of 8 features, rows padded to a multiple of 16) the search runs in GEMM form on the FP64 tensor
-// pipe -- shortlist by |q|^2 + |c|^2 - 2 q.c, exact re-rank, certificate -- and only uncertified queries (counted in
+// With `scratch` (knn_scratch_bytes(n, k, d) bytes of device memory) the search runs in GEMM form on the tensor cores --
+// shortlist by |q|^2 + |c|^2 - 2 q.c, exact FP64 re-rank, certificate -- and only uncertified queries (counted in
 // *n_exact_fallback; -1 = the exact kernel did the whole job) are redone by the exact kernel: the result is the same
-// neighbour lists either way.  CORRLA_B200_KNN_EXACT=1 forces the exact kernel.
-size_t knn_scratch_bytes(int64_t n, int k);
+// neighbour lists either way.  The shortlist pass runs on TF32 mma.sync with FP32 accumulation over a TF32-rounded copy
+// of the samples (default), or, with CORRLA_B200_KNN_TF32=0 and the engine's packed layout (ldx == 4 mod 8), on the FP64
+// tensor pipe; the certificate's error bound follows the precision.  CORRLA_B200_KNN_EXACT=1 forces the exact kernel.
+size_t knn_scratch_bytes(int64_t n, int k, int d);
 cudaError_t knn_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, void* scratch, size_t scratch_bytes,
                        int* n_exact_fallback, cudaStream_t s);
 

@@ -577,7 +577,7 @@ int active_ss_impl(const double* x, int64_t n, int64_t nfeat, int64_t x_rs, int6
   ST_TRY(pack_small(ctx, st, y, n, 1, y_stride, 1, in_dev, yd, 1, 1.0, &launches));
 
   // neighbours, local fits, gradient matrix (row i = gradient at sample i)
-  const size_t knn_bytes = knn_scratch_bytes(n, k);
+  const size_t knn_bytes = knn_scratch_bytes(n, k, d);
   void* knn_scratch = ctx->get("as_knn", knn_bytes);       // optional: without it the exact kernel does the whole search
   int knn_fallback = 0;
   e = knn_launch(Xp, n, d, ld, k, idx, knn_scratch, knn_scratch ? knn_bytes : 0, &knn_fallback, st);

@@ -180,15 +180,24 @@ def test_knn_gemm_form_gives_the_exact_neighbour_lists(cb):
         "lattice_d3": (rng.integers(0, 6, size=(3000, 3)).astype(np.float64), 10),
         "wide_d100_k104": (rng.standard_normal((2500, 100)), 104),     # 32-candidate tiles
     }
+    cases["gauss_d64_20k"] = (rng.standard_normal((20000, 64)), 72)
+    cases["scaled_d16"] = (rng.standard_normal((5000, 16)) * np.logspace(-3, 3, 16), 30)      # features of very different scale
+    cases["clusters_d8"] = (np.repeat(rng.standard_normal((40, 8)), 100, axis=0) + 1e-6 * rng.standard_normal((4000, 8)), 20)
     for name, (x, k) in cases.items():
         y = np.sin(x[:, 0]) + x[:, 1] * x[:, 2] + 0.1 * x.sum(axis=1)
-        _, g_fast = cb.active_ss_fit(x, y, 1, k, 2, return_gradients=True)
         os.environ["CORRLA_B200_KNN_EXACT"] = "1"
         try:
             _, g_exact = cb.active_ss_fit(x, y, 1, k, 2, return_gradients=True)
         finally:
             os.environ.pop("CORRLA_B200_KNN_EXACT", None)
-        assert np.array_equal(np.asarray(g_fast), np.asarray(g_exact)), name
+        # shortlist on TF32 mma.sync over the centred float copy (default), and on the FP64 tensor pipe
+        for tf32 in ("1", "0"):
+            os.environ["CORRLA_B200_KNN_TF32"] = tf32
+            try:
+                _, g_fast = cb.active_ss_fit(x, y, 1, k, 2, return_gradients=True)
+            finally:
+                os.environ.pop("CORRLA_B200_KNN_TF32", None)
+            assert np.array_equal(np.asarray(g_fast), np.asarray(g_exact)), (name, tf32)
 
 
 def test_poly_gradient_estimator_grad_at_arbitrary_points(cb):

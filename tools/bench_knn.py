@@ -33,5 +33,5 @@ for name, env in (("gemm_form", None), ("exact", "1")):
 out["n"] = n; out["d"] = d; out["n_nbr"] = k
 out["pair_feature_products"] = float(n) * n * d
 if "gemm_form" in out:
-    out["gemm_form"]["tflops_dmma"] = 2.0 * n * n * d / out["gemm_form"]["seconds"] * 1e-12
+    out["gemm_form"]["tflops_equiv"] = 2.0 * n * n * d / out["gemm_form"]["seconds"] * 1e-12
 print(json.dumps(out))
