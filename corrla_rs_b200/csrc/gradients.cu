@@ -17,7 +17,7 @@ constexpr int kQT = 64;           // queries per CTA: 8 warps x 8 queries
 constexpr int kCT = 128;          // candidates per tile: 4 per lane
 constexpr int kDC = 32;           // features per staged chunk
 constexpr int kKnnThreads = 256;
-constexpr int kQPitch = kQT + 1, kCPitch = kCT + 1;   // odd pitches: the transposing stores are conflict free
+constexpr int kCPitch = kCT + 1;   // odd pitches (also the query chunk: QT + 1): the transposing stores are conflict free
 constexpr int kKnnSlots = 5;      // list entries per lane in the insertion routine: lists of up to 160 entries
 constexpr int kKnnMargin = 16;    // extra shortlist entries of the GEMM-form search (see knn_gemm_kernel)
 
@@ -61,17 +61,21 @@ __device__ __forceinline__ double knn_insert(double* ld, int* li, int k, double 
   return knn_insert_t<double>(ld, li, k, dist, cand, thr, mask, lane);
 }
 
+// QPW = queries per warp: 8 for the full search; 1 for short query lists (the uncertified queries of the GEMM-form search:
+// a CTA then streams the candidates ~8x faster, and eight times as many CTAs share the list).
+template <int QPW>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, int* __restrict__ idx_out,
            const int* __restrict__ qlist, const int* __restrict__ qcount, const double* __restrict__ Qext, int64_t nq_ext,
            int64_t ldq) {
   extern __shared__ __align__(16) double smk[];
-  double* Qs = smk;                                   // [kDC][kQPitch]  query chunk, feature-major
-  double* Cs = Qs + kDC * kQPitch;                    // [kDC][kCPitch]  candidate chunk, feature-major
-  double* Ld = Cs + kDC * kCPitch;                    // [kQT][k]        sorted distances of the current best k
-  int* Li = reinterpret_cast<int*>(Ld + (size_t)kQT * k);   // [kQT][k]  their indices
+  constexpr int QT = 8 * QPW, QP = QT + 1;             // queries per CTA, odd pitch of the query chunk
+  double* Qs = smk;                                   // [kDC][QP]  query chunk, feature-major
+  double* Cs = Qs + kDC * QP;                    // [kDC][kCPitch]  candidate chunk, feature-major
+  double* Ld = Cs + kDC * kCPitch;                    // [QT][k]         sorted distances of the current best k
+  int* Li = reinterpret_cast<int*>(Ld + (size_t)QT * k);    // [QT][k]   their indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t q0 = (int64_t)blockIdx.x * kQT;
+  const int64_t q0 = (int64_t)blockIdx.x * QT;
   // with a query list (the queries the GEMM-form search could not certify) block b takes entries 64b .. 64b + 63 of it
   // with external query points (grad_at away from the samples) the queries are the rows of Qext, the candidates stay X
   const double* __restrict__ Qsrc = (Qext != nullptr) ? Qext : X;
@@ -83,20 +87,20 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
     if (e >= nq) return qrows;                             // past the end: behaves like a row beyond the matrix
     return (qlist != nullptr) ? (int64_t)qlist[e] : e;
   };
-  for (int i = tid; i < kQT * k; i += kKnnThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
+  for (int i = tid; i < QT * k; i += kKnnThreads) { Ld[i] = DBL_MAX; Li[i] = -1; }
 
   for (int64_t c0 = 0; c0 < n; c0 += kCT) {
-    double acc[8][4];
+    double acc[QPW][4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < QPW; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
     for (int d0 = 0; d0 < d; d0 += kDC) {
       __syncthreads();
-      for (int i = tid; i < kDC * kQT; i += kKnnThreads) {
+      for (int i = tid; i < kDC * QT; i += kKnnThreads) {
         const int q = i / kDC, dd = i - q * kDC;
         const int64_t row = qrow(q);
-        Qs[dd * kQPitch + q] = (row < qrows && d0 + dd < d) ? Qsrc[row * ldqs + d0 + dd] : 0.0;
+        Qs[dd * QP + q] = (row < qrows && d0 + dd < d) ? Qsrc[row * ldqs + d0 + dd] : 0.0;
       }
       for (int i = tid; i < kDC * kCT; i += kKnnThreads) {
         const int cc = i / kDC, dd = i - cc * kDC;
@@ -106,22 +110,22 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
       __syncthreads();
 #pragma unroll 4
       for (int dd = 0; dd < kDC; ++dd) {
-        double cv[4], qv[8];
+        double cv[4], qv[QPW];
 #pragma unroll
         for (int b = 0; b < 4; ++b) cv[b] = Cs[dd * kCPitch + lane + 32 * b];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) qv[a] = Qs[dd * kQPitch + 8 * warp + a];
+        for (int a = 0; a < QPW; ++a) qv[a] = Qs[dd * QP + QPW * warp + a];
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < QPW; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) { const double t = qv[a] - cv[b]; acc[a][b] = fma(t, t, acc[a][b]); }
       }
     }
-    // selection: warp w owns queries 8w .. 8w+7; candidates are visited in increasing index order.  Only the threshold
+    // selection: warp w owns queries QPW w .. QPW w + QPW - 1; candidates are visited in increasing index order.  Only the threshold
     // test is unrolled; the (rare) insertion is one out-of-line routine, which keeps the hot loop in the instruction cache
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int ql = 8 * warp + a;
+    for (int a = 0; a < QPW; ++a) {
+      const int ql = QPW * warp + a;
       if (q0 + ql < nq) {                                             // uniform in the warp
         double* ld = Ld + (size_t)ql * k;
         int* li = Li + (size_t)ql * k;
@@ -137,8 +141,8 @@ knn_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx, int k, i
     }
   }
   __syncwarp();
-  for (int a = 0; a < 8; ++a) {
-    const int ql = 8 * warp + a;
+  for (int a = 0; a < QPW; ++a) {
+    const int ql = QPW * warp + a;
     const int64_t row = qrow(ql);
     if (row >= qrows) break;
     for (int p = lane; p < k; p += 32) idx_out[row * k + p] = Li[(size_t)ql * k + p];
@@ -678,12 +682,17 @@ poly_grad_kernel(const double* __restrict__ X, const double* __restrict__ y, int
 static cudaError_t knn_exact_launch(const double* X, int64_t n, int d, int64_t ldx, int k, int* idx, const int* qlist,
                                     const int* qcount, int64_t n_queries, cudaStream_t s, const double* Qext = nullptr,
                                     int64_t ldq = 0) {
-  const size_t smem = ((size_t)kDC * kQPitch + (size_t)kDC * kCPitch + (size_t)kQT * k) * 8 + (size_t)kQT * k * 4;
-  cudaError_t e = cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  // short query lists (fewer than one query per warp of a full grid): one query per warp, eight times the CTAs
+  const bool few = n_queries <= 8 * 148;
+  const int qt = few ? 8 : kQT;
+  const size_t smem = ((size_t)kDC * (qt + 1) + (size_t)kDC * kCPitch + (size_t)qt * k) * 8 + (size_t)qt * k * 4;
+  cudaError_t e = cudaFuncSetAttribute(knn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
-  const int64_t blocks = (n_queries + kQT - 1) / kQT;
+  const int64_t blocks = (n_queries + qt - 1) / qt;
   if (blocks <= 0) return cudaSuccess;
-  knn_kernel<<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount, Qext, n_queries, ldq);
+  if (few) knn_kernel<1><<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount, Qext, n_queries, ldq);
+  else knn_kernel<8><<<(unsigned)blocks, kKnnThreads, smem, s>>>(X, n, d, ldx, k, idx, qlist, qcount, Qext, n_queries, ldq);
   return cudaGetLastError();
 }
 
