@@ -388,8 +388,10 @@ knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int6
   float* Dt = Cn + kGStages * CT;                                        // [8 warps][16][DP]
   float* Ld = Dt + (size_t)kTQ * DP;                                     // [128][kp]
   int* Li = reinterpret_cast<int*>(Ld + (size_t)kTQ * kp);               // [128][kp]
+  float* Thr = reinterpret_cast<float*>(Li + (size_t)kTQ * kp);          // [128] largest distance of each pool = its threshold
+  int* Mp = reinterpret_cast<int*>(Thr + kTQ);                           // [128] where that entry sits
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-      (reinterpret_cast<uintptr_t>(Li + (size_t)kTQ * kp) + 7) & ~(uintptr_t)7);                     // full[3], empty[3]
+      (reinterpret_cast<uintptr_t>(Mp + kTQ) + 7) & ~(uintptr_t)7);                                  // full[3], empty[3]
   const uint32_t sBar = smem_u32(bars);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q0 = (int64_t)blockIdx.x * kTQ;
@@ -400,6 +402,7 @@ knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int6
     mbar_fence_init();
   }
   for (int i = tid; i < kTQ * kp; i += kGThreads) { Ld[i] = FLT_MAX; Li[i] = -1; }
+  for (int i = tid; i < kTQ; i += kGThreads) { Thr[i] = FLT_MAX; Mp[i] = 0; }
   __syncthreads();
 
   if (warp == 8) {
@@ -433,8 +436,8 @@ knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int6
   }
   const float qn_a = nf[row_a], qn_b = nf[row_b];
   float* Dw = Dt + (size_t)warp * 16 * DP;
-  const float* thr_pa = Ld + (size_t)(16 * warp + g) * kp + kp - 1;
-  const float* thr_pb = thr_pa + (size_t)8 * kp;
+  const float* thr_pa = Thr + 16 * warp + g;
+  const float* thr_pb = thr_pa + 8;
   uint32_t stage = 0, phase = 0;
   for (int64_t t = 0; t < tiles; ++t) {
     const int64_t c0 = t * CT;
@@ -479,16 +482,41 @@ knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int6
         if (((hb >> (4 * (a & 7))) & 0xfu) == 0u) continue;
         const int ql = 16 * warp + a;
         if (q0 + ql >= n) continue;
+        // The shortlist is an UNSORTED pool (the re-rank sorts by exact distance anyway): a candidate under the threshold
+        // replaces the pool's largest entry, then the new largest entry is found with one pass over the pool and one
+        // REDUX on order-preserving keys -- about a third of the work of a sorted insertion.
         float* ldq = Ld + (size_t)ql * kp;
         int* liq = Li + (size_t)ql * kp;
-        float th = ldq[kp - 1];
+        float th = Thr[ql];
+        int mp = Mp[ql];
+        bool changed = false;
 #pragma unroll
         for (int b = 0; b < CT / 32; ++b) {
           const int64_t cg = c0 + lane + 32 * b;
           const float dist = (cg < n) ? Dw[a * DP + lane + 32 * b] : FLT_MAX;
-          const unsigned mask = __ballot_sync(0xffffffffu, dist < th);
-          if (mask) th = knn_insert_t<float>(ldq, liq, kp, dist, (int)cg, th, mask, lane);
+          unsigned mask = __ballot_sync(0xffffffffu, dist < th);
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            const float dv = __shfl_sync(0xffffffffu, dist, src);
+            if (lane == 0) { ldq[mp] = dv; liq[mp] = (int)(c0 + src + 32 * b); }
+            __syncwarp();
+            unsigned best = 0u;
+            int bpos = 0;
+            for (int p = lane; p < kp; p += 32) {
+              const unsigned bits = __float_as_uint(ldq[p]);
+              const unsigned key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);      // unsigned order == float order
+              if (key > best) { best = key; bpos = p; }
+            }
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, best);
+            const unsigned who = __ballot_sync(0xffffffffu, best == kmax);
+            mp = __shfl_sync(0xffffffffu, bpos, __ffs(who) - 1);
+            th = __uint_as_float((kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax);
+            changed = true;
+            mask &= mask - 1;
+            mask &= __ballot_sync(0xffffffffu, dist < th);
+          }
         }
+        if (changed && lane == 0) { Thr[ql] = th; Mp[ql] = mp; }
       }
     }
     __syncwarp();
@@ -498,7 +526,7 @@ knn_tf32_kernel(const float* __restrict__ Xf, const float* __restrict__ nf, int6
     const int64_t row = q0 + ql;
     if (row >= n) break;
     for (int p = lane; p < kp; p += 32) short_idx[row * kp + p] = Li[(size_t)ql * kp + p];
-    if (lane == 0) short_thr[row] = (double)Ld[(size_t)ql * kp + kp - 1];
+    if (lane == 0) short_thr[row] = (double)Thr[ql];
   }
 }
 
@@ -703,8 +731,8 @@ static size_t knn_gemm_smem(int ct, int ld, int kp) {
 }
 
 static size_t knn_tf32_smem(int ct, int ldf, int kp) {
-  return ((size_t)kGStages * ct * ldf + (size_t)kGStages * ct + (size_t)kTQ * (ct + 8)) * 4 + (size_t)kTQ * kp * 8 + 8 +
-         2 * kGStages * 8;
+  return ((size_t)kGStages * ct * ldf + (size_t)kGStages * ct + (size_t)kTQ * (ct + 8)) * 4 + (size_t)kTQ * kp * 8 +
+         (size_t)kTQ * 8 + 8 + 2 * kGStages * 8;
 }
 
 // scratch layout shared by knn_scratch_bytes and knn_launch
