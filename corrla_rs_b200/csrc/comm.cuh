@@ -6,6 +6,7 @@
 //    (reduce_exchange_kernel in skinny_gemm.cu): local partial sums -> my region, one release flag per peer, acquire
 //    the peers' flags, sum the P regions in rank order straight out of peer memory.  No NCCL call on that path.
 #pragma once
+#include <mutex>
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -41,6 +42,10 @@ struct corrla_comm {
   int* err_flag = nullptr;
   unsigned long long epoch = 0;
   long long timeout_cycles = 20000000000ll;            // ~10 s; CORRLA_B200_XCHG_TIMEOUT_CYCLES overrides (tests)
+  // A communicator is one collective resource (one exchange region, one epoch counter): calls that take it are serialised
+  // inside a process by this lock (held for the whole call, taken after the context's).  Across ranks the usual rule of
+  // collectives applies: every rank issues its calls on a communicator in the same order.
+  std::recursive_mutex call_mu;
   // sum-all-reduce `count` doubles in place on `stream` with NCCL; returns 0 or a negative corrla_status
   int allreduce_f64(double* buf, size_t count, cudaStream_t stream);
   // next exchange descriptor (advances the epoch); false if the peer path is off or `count` does not fit

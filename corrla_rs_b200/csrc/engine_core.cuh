@@ -666,7 +666,8 @@ inline int pack_small(corrla_ctx* ctx, cudaStream_t st, const double* src, int64
 struct Scope {
   corrla_ctx* ctx = nullptr; bool owned = false; cudaStream_t st = nullptr;
   std::unique_lock<std::recursive_mutex> lock;
-  ~Scope() { if (lock.owns_lock()) lock.unlock(); if (owned) delete ctx; }
+  std::unique_lock<std::recursive_mutex> comm_lock;      // opts.comm, if any: one call at a time per communicator
+  ~Scope() { if (comm_lock.owns_lock()) comm_lock.unlock(); if (lock.owns_lock()) lock.unlock(); if (owned) delete ctx; }
 };
 
 inline int open_scope(const corrla_rsvd_opts* o, Scope* s) {
@@ -675,6 +676,7 @@ inline int open_scope(const corrla_rsvd_opts* o, Scope* s) {
   if (o && o->ctx) { s->ctx = o->ctx; s->owned = false; CU_TRY(cudaSetDevice(s->ctx->device)); }
   else { ST_TRY(ctx_create(device, &s->ctx)); s->owned = true; }
   s->lock = std::unique_lock<std::recursive_mutex>(s->ctx->mu);
+  if (o && o->comm) s->comm_lock = std::unique_lock<std::recursive_mutex>(o->comm->call_mu);
   s->st = (o && o->stream) ? static_cast<cudaStream_t>(o->stream) : s->ctx->own_stream;
   return CORRLA_OK;
 }
