@@ -127,12 +127,16 @@ struct Wide {
             status = c.mm(qi, true, Cn, X[j], c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 0, false, nullptr, 0, 0, true); // X_j -= Q_i (..)
           }
         if (status != CORRLA_OK) break;
-        const int refills = c.n_refill;
+        const int refills = c.n_refill, robusts = c.n_robust;
         status = c.qr_inplace(X[j], rows, distributed, rows_for_shift, Tq, from_a, complete, basis_only);
         if (status == CORRLA_OK)      // Tq may be the symmetric first-order factor of the fast path: general product, in place
           status = c.mm(c.view_rows(X[j], rows), true, Tq, X[j], c.ld, 1, c.Lc, nullptr, nullptr, nullptr, 1);
-        // columns refilled inside the panel QR are not orthogonal to the earlier panels yet: project and factor again
-        if (c.n_refill == refills || j == 0) break;
+        // Columns refilled inside the panel QR are not orthogonal to the earlier panels yet.  And a panel that needed the
+        // robust stage may hold columns that COLLAPSED in the projection (exactly rank-deficient input: a column that lay in
+        // the span of the earlier panels is rounding noise afterwards, full rank relative to itself, and the normalisation
+        // blows that noise up together with its components along the earlier panels -- cross-orthogonality 1e-10 instead
+        // of 1e-16, round-2 finding on the CPU model).  In both cases: project and factor again.
+        if ((c.n_refill == refills && c.n_robust == robusts) || j == 0) break;
       }
     }
     c.l = l_keep;

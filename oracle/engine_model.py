@@ -120,6 +120,10 @@ def hqr_inv(sk: np.ndarray):
     return t, dead
 
 
+N_REFILL = [0]
+N_ROBUST = [0]
+
+
 def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng=None, sketch_rng=None,
             refill_a: np.ndarray | None = None, complete: bool = False, basis_only: bool = False):
     """CholeskyQR2 when a Cholesky probe says cond(x) is below ~1e4, else sketch-preconditioned CholeskyQR with refill
@@ -141,6 +145,7 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
         else:
             tf, _, _ = chol_inv(g, False, global_rows)
         return x, tf, False, x.shape[1]
+    N_ROBUST[0] += 1                                    # Core::n_robust
     lc = (x.shape[1] + 7) // 8 * 8
     sk = distributed_allreduce(sparse_sign_sketch(x, sketch_rows(lc), sketch_rng or np.random.default_rng(777)))
     t1, dead = hqr_inv(sk)
@@ -156,6 +161,7 @@ def qr_fold(x: np.ndarray, distributed_allreduce, global_rows: float, refill_rng
         tf, _, dead2 = chol_inv(g, False, global_rows)
     dead = dead | dead2
     if dead.any():
+        N_REFILL[0] += 1                                # Core::n_refill: Wide::block_qr re-projects a refilled panel
         rng = refill_rng or np.random.default_rng(12345)
         x = x @ tf
         nd = int(dead.sum())
@@ -325,13 +331,20 @@ def block_qr(x: np.ndarray, w: int, allreduce, global_rows: float, refill_a=None
     l = q.shape[1]
     for j0 in range(0, l, w):
         j1 = min(l, j0 + w)
-        for _rep in range(1 if basis_only else 2):
-            for i0 in range(0, j0, w):
-                qi = q[:, i0:i0 + w]
-                q[:, j0:j1] -= qi @ allreduce(qi.T @ q[:, j0:j1])
-        xj, tf, _, _ = qr_fold(q[:, j0:j1].copy(), allreduce, global_rows, refill_a=refill_a, complete=complete,
-                               basis_only=basis_only)
-        q[:, j0:j1] = xj @ tf
+        for _attempt in range(3):
+            for _rep in range(1 if basis_only else 2):
+                for i0 in range(0, j0, w):
+                    qi = q[:, i0:i0 + w]
+                    q[:, j0:j1] -= qi @ allreduce(qi.T @ q[:, j0:j1])
+            refills, robusts = N_REFILL[0], N_ROBUST[0]
+            xj, tf, _, _ = qr_fold(q[:, j0:j1].copy(), allreduce, global_rows, refill_a=refill_a, complete=complete,
+                                   basis_only=basis_only)
+            q[:, j0:j1] = xj @ tf
+            # Columns refilled inside the panel QR are not orthogonal to the earlier panels yet; and a panel that needed the
+            # robust stage may hold columns that collapsed in the projection (what is left of them is rounding noise, which
+            # the normalisation blows up with its components along the earlier panels): project and factor again.
+            if (N_REFILL[0] == refills and N_ROBUST[0] == robusts) or j0 == 0:
+                break
     return q
 
 

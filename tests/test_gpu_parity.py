@@ -700,6 +700,18 @@ def test_wide_sketch_rank_deficient_and_pca(cb):
     assert np.max(np.abs(s.ravel()[:60] - s0[:60])) < 1e-10 * s0[0]
     assert np.max(np.abs(s.ravel()[60:])) < 1e-9 * s0[0]
     assert np.max(np.abs((u * s.ravel()) @ vt - a)) < 1e-9 * s0[0]
+    # the live singular subspaces, and a rank just above one panel (150 of a 160-column sketch: columns of the second panel
+    # collapse in the projection against the first) -- 1e-6 before the re-projection of panels that took the robust stage
+    ux, _, vxt = np.linalg.svd(a, full_matrices=False)
+    assert ref_rsvd.subspace_sine(ux[:, :60], np.asarray(u)[:, :60]) < 1e-9
+    a2 = rng.standard_normal((m, 150)) @ rng.standard_normal((150, n))
+    u2, s2, vt2 = cb.rsvd(a2, 150, 4, 10, seed=5)
+    ux2, sx2, vxt2 = np.linalg.svd(a2, full_matrices=False)
+    assert np.max(np.abs(s2.ravel() - sx2[:150])) < 1e-10 * sx2[0]
+    assert np.max(np.abs(np.asarray(u2).T @ np.asarray(u2) - np.eye(150))) < 1e-12
+    assert ref_rsvd.subspace_sine(ux2[:, :150], np.asarray(u2)) < 1e-8
+    assert ref_rsvd.subspace_sine(vxt2[:150].T, np.asarray(vt2).T) < 1e-8
+    assert np.max(np.abs((np.asarray(u2) * s2.ravel()) @ np.asarray(vt2) - a2)) < 1e-10 * sx2[0]
     x = lowrank_noise(rng, 3000, 260, 180, 1e-6) + rng.standard_normal((1, 260))
     sv, comps = cb.rpca(x, 130, seed=4)
     xc = x - x.mean(axis=0)
