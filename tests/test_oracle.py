@@ -128,6 +128,25 @@ def test_engine_model_rank_deficient_refill():
     assert np.max(np.abs(u @ np.diag(s.ravel()) @ vt - g["a"])) < 1e-12
 
 
+def test_engine_model_wide_sketch_on_exactly_rank_deficient_input():
+    """Panel path (l > 128) on a matrix whose rank lies just above one panel: the columns of the second panel that fall into
+    the span of the first collapse to rounding noise in the projection.  A panel whose QR needed the robust stage is
+    projected and factored again (Wide::block_qr); without that the panels were orthogonal to 2e-10 only and the subspaces
+    matched the reference to 8e-10 -- with it, to rounding."""
+    rng = np.random.default_rng(5)
+    m, n, r = 1200, 200, 150
+    a = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+    k, q, p = 150, 4, 10
+    omega = rng.standard_normal((n, k + p))
+    u0, s0, v0 = ref_rsvd.random_svd(a, k, q, p, omega=omega)
+    u1, s1, v1 = engine_model.wide_rsvd(a, k, q, p, omega)
+    assert ref_rsvd.sigma_rel_err(s0, s1) < 1e-11
+    assert ref_rsvd.subspace_sine(u0, u1) < 1e-11
+    assert ref_rsvd.subspace_sine(v0.T, v1.T) < 1e-11
+    assert np.max(np.abs(u1.T @ u1 - np.eye(k))) < 1e-12
+    assert np.max(np.abs((u1 * s1.ravel()) @ v1 - a)) < 1e-12 * s0[0, 0]
+
+
 def test_engine_model_jacobi_svd():
     rng = np.random.default_rng(9)
     w = np.triu(rng.standard_normal((37, 37))) * (0.8 ** np.arange(37))[None, :]
