@@ -100,6 +100,28 @@ def main():
         res = json.loads((out_dir / "result.json").read_text())
         res["replicated_identical"] = bool(torch.equal(mx, mn))
         (out_dir / "result.json").write_text(json.dumps(res))
+    # the panel path (l > 128) on exactly rank-deficient input, row-sharded: the cross products of the block Gram-Schmidt and
+    # the panel Gram matrices are the all-reduced quantities; a panel that took the robust stage is projected again
+    rng3 = np.random.default_rng(31)
+    mw, nw, rw, kw, pw = 1203, 180, 150, 150, 10
+    aw = rng3.standard_normal((mw, rw)) @ rng3.standard_normal((rw, nw))
+    omw = rng3.standard_normal((nw, kw + pw))
+    per = (mw + world - 1) // world
+    w0, w1 = rank * per, min(mw, (rank + 1) * per)
+    uw_loc, sw, vw = engine_model.wide_rsvd(aw[w0:w1], kw, 4, pw, omw, allreduce=allreduce, global_rows=mw)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (w0, w1, uw_loc))
+    if rank == 0:
+        uw = np.zeros((mw, kw))
+        for g0, g1, blk in gathered:
+            uw[g0:g1] = blk
+        u0, s0, vt0 = ref_rsvd.random_svd(aw, kw, 4, pw, omega=omw)
+        res = json.loads((out_dir / "result.json").read_text())
+        res["wide_sigma_rel"] = ref_rsvd.sigma_rel_err(s0, sw)
+        res["wide_sin_u"] = ref_rsvd.subspace_sine(u0, uw)
+        res["wide_sin_v"] = ref_rsvd.subspace_sine(vt0.T, vw.T)
+        res["wide_orth"] = float(np.max(np.abs(uw.T @ uw - np.eye(kw))))
+        (out_dir / "result.json").write_text(json.dumps(res))
     dist.destroy_process_group()
 
 

@@ -35,6 +35,8 @@ def test_row_sharded_algorithm_matches_oracle(tmp_path, world):
     # rank's block, POD with the points split; against the single-process oracle
     assert res["dmdc_b_err"] < 1e-8 and res["dmdc_eig_err"] < 1e-8 and res["dmdc_sigma_rel"] < 1e-10, res
     assert res["pod_sin_modes"] < 1e-8 and res["pod_recon_err"] < 1e-8, res
+    # the panel path on exactly rank-deficient input (rank 150 under a 160-column sketch), row-sharded
+    assert res["wide_sigma_rel"] < 1e-10 and res["wide_sin_u"] < 1e-8 and res["wide_sin_v"] < 1e-8 and res["wide_orth"] < 1e-12, res
 
 
 def test_bench_shard_partition_is_gpu_count_independent():
