@@ -28,10 +28,15 @@ def main():
              # Z = n16 x ld = 16000 x 36 doubles exceeds the 4 MiB peer-memory half: this case takes the NCCL fallback
              "wide_nccl_fallback": (18000, 16000, 20, 2, 8, "C"),
              # l = 160 > 128: the column-panel path (csrc/wide.cuh), cross-panel projections summed over the ranks
-             "panels_l160": (12000, 400, 150, 3, 10, "C")}
+             "panels_l160": (12000, 400, 150, 3, 10, "C"),
+             # the panel path on EXACTLY rank-deficient input (rank 150 under a 160-column sketch): columns of the second
+             # panel collapse in the projection; the panel is projected and factored again (identical decision on every rank)
+             "panels_rank150": (9000, 300, 150, 4, 10, "C")}
     for name, (m, n, k, q, p, order) in cases.items():
         rng = np.random.default_rng(77)
-        if name.startswith("panels"):
+        if name == "panels_rank150":
+            a = rng.standard_normal((m, 150)) @ rng.standard_normal((150, n))
+        elif name.startswith("panels"):
             u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
             v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
             a = (u0 * (10.0 * 0.99 ** np.arange(n))) @ v0.T

@@ -38,7 +38,8 @@ def test_row_sharded_rsvd_over_nccl(tmp_path, world):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     res = json.loads((tmp_path / "result.json").read_text())
-    for name in ("gauss_rowmajor", "lowrank_colmajor", "tiny_rank_deficient", "wide_nccl_fallback", "panels_l160"):
+    for name in ("gauss_rowmajor", "lowrank_colmajor", "tiny_rank_deficient", "wide_nccl_fallback", "panels_l160",
+                 "panels_rank150"):
         c = res[name]
         assert c["sigma_rel"] < 1e-10, (name, c)
         assert c["sin_u"] < 1e-8 and c["sin_v"] < 1e-8, (name, c)
